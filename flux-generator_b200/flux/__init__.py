@@ -1,0 +1,8 @@
+"""B200-native drop-in for the reference's ``flux`` package (flux/__init__.py:3-16).
+
+Same import surface (``from flux import FluxPipeline, FluxSampler, load_* ...``); the denoising hot
+path runs in ``libflux_b200.so`` (hand-written sm_100a CUDA behind the C ABI in include/flux_b200.h),
+which is loaded on first use and fails loudly when missing -- there is no CPU fallback.
+"""
+from .sampler import FluxSampler  # noqa: F401
+from .specs import AutoEncoderParams, CLIPTextModelConfig, FluxParams, T5Config  # noqa: F401

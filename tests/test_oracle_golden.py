@@ -1,0 +1,130 @@
+"""CPU: the oracle (oracle/flux_oracle.py) against the golden vectors written by the reference's
+own code over the MLX shim (oracle/gen_golden.py).  fp32 on both sides -> tight tolerances."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from flux import specs, synthetic
+from oracle import flux_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def close(a, b, rtol=2e-5, atol=2e-5):
+    a = a.detach().to(torch.float32).numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def test_schedule_bit_exact():
+    g = load("schedule.npz")
+    for key in g.files:
+        name, steps, L = key.split("_")
+        got = O.timesteps(int(steps), int(L), schnell=(name == "schnell"))
+        assert np.array_equal(np.asarray(got, dtype=np.float64), g[key]), key
+    # known answers from SURVEY 8-a1
+    assert O.timesteps(2, 1024, True) == [1.0, 0.5, 0.0]
+    assert O.timesteps(4, 4096, True) == [1.0, 0.75, 0.5, 0.25, 0.0]
+    dev = O.timesteps(50, 4096, False)
+    assert abs(dev[1] - 0.99357950687) < 1e-7 and dev[-1] == 0.0 and dev[0] == 1.0
+
+
+def test_patchify_bit_exact():
+    g = load("patchify.npz")
+    x = torch.from_numpy(g["x"])
+    p, ids = O.prepare_latent_images(x)
+    assert np.array_equal(p.numpy(), g["packed"])
+    assert np.array_equal(ids.numpy(), g["ids"])
+    assert np.array_equal(O.unpatchify(p, (4, 6)).numpy(), g["back"])
+    assert np.array_equal(g["back"], g["x"])
+    # feature order c*4 + dy*2 + dx
+    assert p[0, 0, :8].tolist() == [x[0, 0, 0, 0], x[0, 0, 1, 0], x[0, 1, 0, 0], x[0, 1, 1, 0],
+                                    x[0, 0, 0, 1], x[0, 0, 1, 1], x[0, 1, 0, 1], x[0, 1, 1, 1]]
+
+
+@pytest.mark.parametrize("variant", ["schnell", "dev"])
+def test_flow_forward(variant):
+    g = load(f"flow_{variant}.npz")
+    cfg = json.loads(str(g["config"]))
+    ge = bool(g["guidance_embed"])
+    p = O.FluxParams(**cfg, guidance_embed=ge)
+    sd = synthetic.synthetic_state_dict(specs.flow_manifest(specs.FluxParams(**cfg, guidance_embed=ge)))
+    assert synthetic.state_dict_checksum(sd) == int(g["weights_crc"]), "synthetic weight generator drifted"
+    B = g["img"].shape[0]
+    t = torch.full((B,), float(g["t"]), dtype=torch.bfloat16)
+    gd = torch.full((B,), float(g["guidance"]), dtype=torch.bfloat16)
+    taps = {}
+    out = O.flux_forward(sd, p, torch.from_numpy(g["img"]), torch.from_numpy(g["img_ids"]),
+                         torch.from_numpy(g["txt"]), torch.from_numpy(g["txt_ids"]), t,
+                         torch.from_numpy(g["y"]), gd, taps=taps)
+    for k, v in taps.items():
+        close(v, g["tap." + k], rtol=1e-4, atol=1e-4)
+    close(out, g["out"], rtol=1e-4, atol=1e-4)
+
+
+def test_ae_decode():
+    g = load("ae_decode.npz")
+    cfg = json.loads(str(g["config"]))
+    sd = synthetic.synthetic_state_dict(specs.ae_decoder_manifest(specs.AutoEncoderParams(**cfg)))
+    assert synthetic.state_dict_checksum(sd) == int(g["weights_crc"])
+    h, w = (int(v) for v in g["latent_size"])
+    img = O.decode(sd, O.AutoEncoderParams(**cfg), torch.from_numpy(g["latents"]), (h, w))
+    close(img, g["image"], rtol=1e-4, atol=1e-4)
+    u8 = O.to_uint8(img).numpy()
+    assert (np.abs(u8.astype(int) - g["image_u8"].astype(int)) <= 1).all()
+
+
+def test_text_encoders():
+    g = load("text_encoders.npz")
+    t5c = json.loads(str(g["t5_config"]))
+    clc = json.loads(str(g["clip_config"]))
+    t5_sd = synthetic.synthetic_state_dict(specs.t5_manifest(specs.T5Config(**t5c)))
+    clip_sd = synthetic.synthetic_state_dict(specs.clip_manifest(specs.CLIPTextModelConfig(**clc)))
+    assert synthetic.state_dict_checksum(t5_sd) == int(g["t5_crc"])
+    assert synthetic.state_dict_checksum(clip_sd) == int(g["clip_crc"])
+    ocfg = O.T5Config(**{k: v for k, v in t5c.items() if k in O.T5Config.__dataclass_fields__})
+    close(O.t5_position_bias(t5_sd, ocfg, 16), g["t5_bias"], rtol=0, atol=0)
+    close(O.t5_encode(t5_sd, ocfg, torch.from_numpy(g["t5_tokens"])), g["t5_out"], rtol=1e-4, atol=1e-4)
+    pooled, last = O.clip_encode(clip_sd, O.CLIPConfig(**clc), torch.from_numpy(g["clip_tokens"]))
+    close(last, g["clip_last"], rtol=1e-4, atol=1e-4)
+    close(pooled, g["clip_pooled"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("variant", ["schnell", "dev"])
+def test_pipeline_end_to_end(variant):
+    """tokens -> T5/CLIP -> Euler loop -> decode, all through the oracle, vs FluxPipeline over the shim."""
+    g = load(f"pipeline_{variant}.npz")
+    fcfg = json.loads(str(load(f"flow_{variant}.npz")["config"]))
+    ge = variant == "dev"
+    acfg = json.loads(str(load("ae_decode.npz")["config"]))
+    te = load("text_encoders.npz")
+    t5c, clc = json.loads(str(te["t5_config"])), json.loads(str(te["clip_config"]))
+    flow_sd = synthetic.synthetic_state_dict(specs.flow_manifest(specs.FluxParams(**fcfg, guidance_embed=ge)))
+    ae_sd = synthetic.synthetic_state_dict(specs.ae_decoder_manifest(specs.AutoEncoderParams(**acfg)))
+    t5_sd = synthetic.synthetic_state_dict(specs.t5_manifest(specs.T5Config(**t5c)))
+    clip_sd = synthetic.synthetic_state_dict(specs.clip_manifest(specs.CLIPTextModelConfig(**clc)))
+    ocfg = O.T5Config(**{k: v for k, v in t5c.items() if k in O.T5Config.__dataclass_fields__})
+    B = g["x_T"].shape[0]
+    txt = O.t5_encode(t5_sd, ocfg, torch.from_numpy(g["t5_tokens"])).expand(B, -1, -1)
+    vec = O.clip_encode(clip_sd, O.CLIPConfig(**clc), torch.from_numpy(g["clip_tokens"]))[0].expand(B, -1)
+    close(txt, g["txt"], rtol=1e-4, atol=1e-4)
+    close(vec, g["vec"], rtol=1e-4, atol=1e-4)
+    steps = int(g["steps"])
+    h, w = (int(v) for v in g["latent_size"])
+    x_T = torch.from_numpy(g["x_T_nhwc"])
+    packed, ids = O.prepare_latent_images(x_T)
+    assert np.array_equal(packed.numpy(), g["x_T"]) and np.array_equal(ids.numpy(), g["x_ids"])
+    ts = O.timesteps(steps, packed.shape[1], schnell=not ge)
+    assert np.array_equal(np.asarray(ts, dtype=np.float64), g["timesteps"])
+    lats, img = O.generate_images(flow_sd, ae_sd, O.FluxParams(**fcfg, guidance_embed=ge),
+                                  O.AutoEncoderParams(**acfg), x_T, txt, vec, steps, float(g["guidance"]),
+                                  schnell=not ge)
+    for i in range(steps):
+        close(lats[i], g["latents"][i], rtol=2e-4, atol=2e-4)
+    close(img, g["image"], rtol=5e-4, atol=5e-4)
