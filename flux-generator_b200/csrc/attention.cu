@@ -1,0 +1,446 @@
+// Joint (text+image) attention for the MMDiT on tcgen05:  out = softmax(q k^T * scale) v, head_dim 128,
+// no mask (flux/layers.py:36-43).  Flash-style: one CTA owns 256 query rows of one (batch, head) as two
+// 128-row tiles that ping-pong on the tensor pipe; K/V tiles stream through a TMA ring; S and O live
+// in TMEM; two softmax warpgroups (one row per thread) run the online softmax in fp32 with exp2 and a
+// lazy O-rescale (only when the running max grows by > 2^8).
+//   warp 0: TMA producer      warp 1: tcgen05.mma issuer + TMEM owner
+//   warps 4-7: softmax/correction/epilogue for tile 0      warps 8-11: same for tile 1
+// P (bf16 probabilities) is handed to the P.V MMA either through TMEM (aliasing S, default) or through
+// 128B-swizzled shared memory (variant 1, bring-up fallback).  V is consumed MN-major straight from its
+// [seq][128] layout (no transposed copy).
+#include "api_common.cuh"
+#include "sm100.cuh"
+#include "tmap.cuh"
+
+namespace fx {
+
+constexpr int ATT_THREADS = 384;
+constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // one 128x128 bf16 tile = two 16 KB swizzled halves
+
+struct AttnParams {
+  int seq, heads, kv_tiles;
+  float scale_log2;
+  __nv_bfloat16* out;
+  long long ld_out, out_bs;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool P_TMEM>
+struct AttnCfg {
+  static constexpr int KV_STAGES = P_TMEM ? 5 : 3;
+  static constexpr int Q_OFF = 0;
+  static constexpr int KV_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int P_OFF = KV_OFF + KV_STAGES * ATT_TILE_BYTES;
+  static constexpr int BAR_OFF = P_OFF + (P_TMEM ? 0 : 2 * ATT_TILE_BYTES);
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
+
+template <bool P_TMEM>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+            const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<P_TMEM>;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;             // 1
+  uint64_t* kv_full = bars + 1;        // NS
+  uint64_t* kv_empty = kv_full + NS;   // NS
+  uint64_t* s_full = kv_empty + NS;    // 2
+  uint64_t* p_full = s_full + 2;       // 2
+  uint64_t* o_full = p_full + 2;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int bh = blockIdx.z * p.heads + blockIdx.y;
+  const int T = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases S_i[0,64)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: Q (both tiles), then K0 V0 K1 V1 ...
+      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int hf = 0; hf < 2; ++hf)
+          tma_load_3d(smem + Cfg::Q_OFF + i * ATT_TILE_BYTES + hf * 16384, &tmap_q, q_full, hf * 64, q0 + i * 128, bh);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < 2 * T; ++t) {
+        const CUtensorMap* m = (t & 1) ? &tmap_v : &tmap_k;
+        const int row = (t >> 1) * 128;
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
+        uint8_t* dst = smem + Cfg::KV_OFF + stage * ATT_TILE_BYTES;
+        tma_load_3d(dst, m, &kv_full[stage], 0, row, bh);
+        tma_load_3d(dst + 16384, m, &kv_full[stage], 64, row, bh);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_base = smem_u32(smem + Cfg::Q_OFF);
+      const uint32_t kv_base = smem_u32(smem + Cfg::KV_OFF);
+      const uint32_t p_base = smem_u32(smem + Cfg::P_OFF);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto issue_qk = [&](int i, uint32_t k_addr) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_ss(tmem + i * 128, make_smem_desc_sw128(q_base + i * ATT_TILE_BYTES + off, 16, 1024),
+                  make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int i, uint32_t v_addr, bool acc) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t vd = make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024);
+          if (P_TMEM) {
+            umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, vd, idesc_pv, (acc || ks != 0) ? 1u : 0u);
+          } else {
+            const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+            umma_ss(tmem + 256 + i * 128, make_smem_desc_sw128(p_base + i * ATT_TILE_BYTES + off, 16, 1024), vd,
+                    idesc_pv, (acc || ks != 0) ? 1u : 0u);
+          }
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[stage], phase);  // K(0)
+      tc_fence_after();
+      {
+        const uint32_t k_addr = kv_base + stage * ATT_TILE_BYTES;
+        issue_qk(0, k_addr);
+        tc_commit(&s_full[0]);
+        issue_qk(1, k_addr);
+        tc_commit(&s_full[1]);
+        tc_commit(&kv_empty[stage]);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+      for (int j = 0; j < T; ++j) {
+        const bool more = (j + 1 < T);
+        const int vs = stage;
+        mbar_wait(&kv_full[vs], phase);  // V(j)
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        const int ks_ = stage;
+        const uint32_t v_addr = kv_base + vs * ATT_TILE_BYTES;
+        const uint32_t k_addr = kv_base + ks_ * ATT_TILE_BYTES;
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, v_addr, j > 0);
+        if (more) {
+          mbar_wait(&kv_full[ks_], phase);  // K(j+1)
+          tc_fence_after();
+          issue_qk(0, k_addr);
+          tc_commit(&s_full[0]);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_addr, j > 0);
+        tc_commit(&kv_empty[vs]);
+        if (more) {
+          issue_qk(1, k_addr);
+          tc_commit(&s_full[1]);
+          tc_commit(&kv_empty[ks_]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+      tc_commit(&o_full[0]);
+      tc_commit(&o_full[1]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax / correction / epilogue warpgroups
+    const int i = (warp - 4) >> 2;   // query tile 0/1
+    const int quarter = warp & 3;    // TMEM lane quarter
+    const int r = quarter * 32 + lane;
+    const int q_row = q0 + i * 128 + r;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const uint32_t s_addr = tmem + lane_base + i * 128;
+    const uint32_t o_addr = tmem + lane_base + 256 + i * 128;
+    uint8_t* p_smem = smem + Cfg::P_OFF + i * ATT_TILE_BYTES;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      const int kv_valid = min(128, p.seq - j * 128);
+      mbar_wait(&s_full[i], j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(s_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float s = (c * 32 + e < kv_valid) ? __uint_as_float(v[e]) : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * sl2);
+      const bool need = (m_new - m_run) > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+        if (need) {
+          m_run = m_new;
+          l_run *= alpha;
+        }
+        if (j > 0) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_x32(o_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_x32(o_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      // pass 2: probabilities
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(s_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float s0 = (c * 32 + e < kv_valid) ? __uint_as_float(v[e]) : -INFINITY;
+          const float s1 = (c * 32 + e + 1 < kv_valid) ? __uint_as_float(v[e + 1]) : -INFINITY;
+          const float p0 = fast_exp2(s0 * sl2 - m_run);
+          const float p1 = fast_exp2(s1 * sl2 - m_run);
+          l_run += p0 + p1;
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+        if (P_TMEM) {
+          tmem_st_x16(s_addr + c * 16, pk);
+        } else {
+          // K-major SW128 tile: row r, keys c*32 .. c*32+31 -> half c>>1, 16-byte chunks ((c&1)*4 + q) ^ (r&7)
+          uint8_t* rowp = p_smem + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+      }
+      if (P_TMEM) {
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i]);
+    }
+
+    // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* dst = p.out + (long long)blockIdx.z * p.out_bs + (long long)q_row * p.ld_out + blockIdx.y * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_x32(o_addr + c * 32, v);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + e) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small generic attention (text encoders; head_dim 64; seq <= 512): one warp per (b, h, query).
+// ------------------------------------------------------------------------------------------
+struct AttnSmallParams {
+  const __nv_bfloat16 *q, *k, *v;
+  long long ld, bs;
+  const float* bias;
+  __nv_bfloat16* out;
+  long long ld_out, out_bs;
+  float scale;
+  int batch, heads, seq, causal;
+};
+
+__global__ void __launch_bounds__(256) attn_small_kernel(const AttnSmallParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)p.batch * p.heads * p.seq;
+  if (gw >= total) return;
+  const int qi = int(gw % p.seq);
+  const int h = int((gw / p.seq) % p.heads);
+  const int b = int(gw / ((long long)p.seq * p.heads));
+  const __nv_bfloat16* qp = p.q + b * p.bs + (long long)qi * p.ld + h * 64;
+  // each lane keeps the full (scaled) query: 64 floats
+  float qv[64];
+#pragma unroll
+  for (int d = 0; d < 64; d += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(qp + d);
+    float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+    qv[d] = a.x * p.scale; qv[d + 1] = a.y * p.scale; qv[d + 2] = bb.x * p.scale; qv[d + 3] = bb.y * p.scale;
+    qv[d + 4] = c.x * p.scale; qv[d + 5] = c.y * p.scale; qv[d + 6] = e.x * p.scale; qv[d + 7] = e.y * p.scale;
+  }
+  constexpr int MAXK = 16;  // keys per lane: seq <= 512
+  float sc[MAXK];
+  float mx = -INFINITY;
+  const int nk = p.causal ? qi + 1 : p.seq;
+#pragma unroll
+  for (int t = 0; t < MAXK; ++t) {
+    const int kj = t * 32 + lane;
+    float s = -INFINITY;
+    if (kj < nk) {
+      const __nv_bfloat16* kp = p.k + b * p.bs + (long long)kj * p.ld + h * 64;
+      s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; d += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(kp + d);
+        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+        s += qv[d] * a.x + qv[d + 1] * a.y + qv[d + 2] * bb.x + qv[d + 3] * bb.y + qv[d + 4] * c.x + qv[d + 5] * c.y +
+             qv[d + 6] * e.x + qv[d + 7] * e.y;
+      }
+      if (p.bias) s += p.bias[((long long)h * p.seq + qi) * p.seq + kj];
+    }
+    sc[t] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < MAXK; ++t) {
+    sc[t] = (sc[t] == -INFINITY) ? 0.f : __expf(sc[t] - mx);
+    sum += sc[t];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  // out[d]: lane owns dims 2*lane, 2*lane+1; loop over all keys, probabilities broadcast by shuffle
+  float o0 = 0.f, o1 = 0.f;
+  for (int t = 0; t < MAXK; ++t) {
+    if (t * 32 >= nk) break;
+    for (int src = 0; src < 32; ++src) {
+      const int kj = t * 32 + src;
+      const float pj = __shfl_sync(0xffffffffu, sc[t], src);
+      if (kj < nk) {
+        const __nv_bfloat162 vv =
+            *reinterpret_cast<const __nv_bfloat162*>(p.v + b * p.bs + (long long)kj * p.ld + h * 64 + 2 * lane);
+        const float2 f = __bfloat1622float2(vv);
+        o0 += pj * f.x;
+        o1 += pj * f.y;
+      }
+    }
+  }
+  __nv_bfloat16* op = p.out + b * p.out_bs + (long long)qi * p.ld_out + h * 64 + 2 * lane;
+  *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+template <bool P_TMEM>
+static int launch_attn(const fx_attn_args* a, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, cudaStream_t st) {
+  using Cfg = AttnCfg<P_TMEM>;
+  auto kern = attn_kernel<P_TMEM>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    FX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  dim3 grid((a->seq + 255) / 256, a->heads, a->batch);
+  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  return launched("attn_kernel");
+}
+
+extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->heads > 0 && a->seq > 0, "fx_attention: empty problem");
+  FX_REQUIRE(a->ld_out % 8 == 0 && a->out_bs % 8 == 0 && aligned16(a->out), "fx_attention: out must be 16-byte aligned rows");
+  FX_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v), "fx_attention: q/k/v must be 16-byte aligned");
+  AttnParams p{};
+  p.seq = a->seq; p.heads = a->heads; p.kv_tiles = (a->seq + 127) / 128;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out; p.out_bs = a->out_bs;
+  CUtensorMap tq, tk, tv;
+  const uint64_t dims[3] = {128, (uint64_t)a->seq, (uint64_t)a->batch * a->heads};
+  const uint64_t strides[2] = {256, (uint64_t)a->seq * 256};
+  const uint32_t box[3] = {64, 128, 1};
+  int rc;
+  if ((rc = make_tmap_bf16(&tq, a->q, 3, dims, strides, box))) return rc;
+  if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box))) return rc;
+  if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box))) return rc;
+  if (a->variant == 1) return launch_attn<false>(a, tq, tk, tv, p, (cudaStream_t)stream);
+  return launch_attn<true>(a, tq, tk, tv, p, (cudaStream_t)stream);
+}
+
+extern "C" int fx_attention_small(const fx_attn_small_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention_small: null pointer");
+  FX_REQUIRE(a->seq > 0 && a->seq <= 512, "fx_attention_small: seq %d out of range (1..512)", a->seq);
+  FX_REQUIRE(a->ld % 8 == 0 && a->bs % 8 == 0 && a->ld_out % 2 == 0, "fx_attention_small: unaligned strides");
+  AttnSmallParams p{(const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k, (const __nv_bfloat16*)a->v, a->ld, a->bs,
+                    a->bias, (__nv_bfloat16*)a->out, a->ld_out, a->out_bs, a->scale, a->batch, a->heads, a->seq, a->causal};
+  const long long warps = (long long)a->batch * a->heads * a->seq;
+  const int blocks = int((warps + 7) / 8);
+  attn_small_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  return launched("attn_small_kernel");
+}

@@ -1,0 +1,534 @@
+// HBM-bound kernels of the hot path: row norms (+AdaLN modulation), conditioning GEMVs, timestep
+// embedding, Euler step, latent packing, GroupNorm(+SiLU), nearest upsample, row softmax, transpose,
+// image finish, embedding gather, gated activation.  All vectorised to 16-byte accesses, bf16 in HBM,
+// fp32 in registers.
+#include "api_common.cuh"
+#include "sm100.cuh"
+
+namespace fx {
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ row norm: one warp per row
+struct RowNormParams {
+  const __nv_bfloat16* x; long long ldx, x_bs;
+  __nv_bfloat16* out; long long ldo, out_bs;
+  const __nv_bfloat16 *p0, *p1; long long p_bs;
+  float eps; int mode, batch, rows, D;
+};
+
+template <int ITERS>  // D = ITERS * 256
+__global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gw >= (long long)p.batch * p.rows) return;
+  const int b = int(gw / p.rows);
+  const long long r = gw - (long long)b * p.rows;
+  const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
+  float v[ITERS * 8];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) load8(xr + i * 256 + lane * 8, v + i * 8);
+  float mean = 0.f;
+  if (p.mode != 2) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < ITERS * 8; ++i) s += v[i];
+    mean = warp_sum(s) / float(p.D);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS * 8; ++i) {
+    const float d = v[i] - mean;
+    ss += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
+  const long long pb = (p.mode == 0) ? b * p.p_bs : 0;
+  __nv_bfloat16* orow = p.out + b * p.out_bs + r * p.ldo;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 256 + lane * 8;
+    float a[8], s[8], o[8];
+    load8(p.p0 + pb + c, a);
+    if (p.mode != 2) load8(p.p1 + pb + c, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = (v[i * 8 + j] - mean) * rstd;
+      if (p.mode == 0) o[j] = (1.0f + s[j]) * y + a[j];  // p0 = shift, p1 = scale
+      else if (p.mode == 1) o[j] = y * a[j] + s[j];      // p0 = weight, p1 = bias
+      else o[j] = y * a[j];                              // p0 = weight
+    }
+    store8(orow + c, o);
+  }
+}
+
+// ------------------------------------------------------------------ conditioning GEMV
+// out[b][n] = f_out( sum_k f_in(in[b][k]) W[n][k] + bias[n] + add[b][n] ), batch <= 8 per launch pass.
+struct GemvParams {
+  const __nv_bfloat16* in; long long ld_in;
+  const __nv_bfloat16* W; long long ldw;
+  const __nv_bfloat16 *bias, *add; long long ld_add;
+  __nv_bfloat16* out; long long ld_out;
+  int batch, N, K, silu_in, silu_out;
+};
+
+__global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
+  extern __shared__ __nv_bfloat16 s_in[];  // [batch][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int idx = threadIdx.x; idx < p.batch * p.K; idx += blockDim.x) {
+    const int b = idx / p.K, k = idx - b * p.K;
+    float x = __bfloat162float(p.in[b * p.ld_in + k]);
+    if (p.silu_in) x = silu(x);
+    s_in[idx] = __float2bfloat16(x);  // bf16 like the reference's nn.silu output
+  }
+  __syncthreads();
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int n = blockIdx.x * (blockDim.x >> 5) + warp; n < p.N; n += warps_total) {
+    float acc[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+    const __nv_bfloat16* wr = p.W + (long long)n * p.ldw;
+    for (int k = lane * 8; k < p.K; k += 256) {
+      float w[8];
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
+      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      w[0] = a.x; w[1] = a.y; w[2] = bb.x; w[3] = bb.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        if (b < p.batch) {
+          float x[8];
+          load8(s_in + b * p.K + k, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[b] += w[j] * x[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b] = warp_sum(acc[b]);
+    if (lane == 0) {
+      const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+      for (int b = 0; b < p.batch; ++b) {
+        float v = acc[b] + bias;
+        if (p.silu_out) v = silu(__bfloat162float(__float2bfloat16(v)));
+        if (p.add) v = __bfloat162float(__float2bfloat16(v)) + __bfloat162float(p.add[b * p.ld_add + n]);
+        p.out[b * p.ld_out + n] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ timestep embedding
+__global__ void timestep_embedding_kernel(const __nv_bfloat16* t, __nv_bfloat16* out, int batch, int dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= batch * half) return;
+  const int b = idx / half, j = idx - b * half;
+  // bf16(1000 * bf16(t)) -- the multiply happens in bf16 in the reference (flux/layers.py:54)
+  const float tt = __bfloat162float(__float2bfloat16(1000.0f * __bfloat162float(t[b])));
+  const float freq = expf(-9.210340371976184f * (float(j) / float(half)));
+  const float x = tt * freq;
+  out[b * dim + j] = __float2bfloat16(cosf(x));
+  out[b * dim + half + j] = __float2bfloat16(sinf(x));
+}
+
+// ------------------------------------------------------------------ Euler step
+__global__ void euler_kernel(__nv_bfloat16* x, const __nv_bfloat16* pred, float dt, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float a[8], b[8];
+    load8(x + i, a);
+    load8(pred + i, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = a[j] + __bfloat162float(__float2bfloat16(dt * b[j]));
+    store8(x + i, a);
+  } else {
+    for (long long k = i; k < n; ++k)
+      x[k] = __float2bfloat16(__bfloat162float(x[k]) + __bfloat162float(__float2bfloat16(dt * __bfloat162float(pred[k]))));
+  }
+}
+
+// ------------------------------------------------------------------ latent packing
+__global__ void patchify_kernel(const __nv_bfloat16* x, __nv_bfloat16* out, int b, int h, int w, int c) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)b * h * w * c;
+  if (idx >= total) return;
+  // out index: [b][row*(w/2)+col][ch*4 + dy*2 + dx]
+  const int f = int(idx % (4 * c));
+  const long long tok = idx / (4 * c);
+  const int col = int(tok % (w / 2));
+  const int row = int((tok / (w / 2)) % (h / 2));
+  const int bi = int(tok / ((long long)(w / 2) * (h / 2)));
+  const int ch = f >> 2, dy = (f >> 1) & 1, dx = f & 1;
+  out[idx] = x[(((long long)bi * h + (row * 2 + dy)) * w + (col * 2 + dx)) * c + ch];
+}
+
+__global__ void unpatchify_scale_kernel(const __nv_bfloat16* packed, __nv_bfloat16* z, int b, int h, int w, int c,
+                                        int c_pad, float inv_scale, float shift) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)b * h * w * c_pad;
+  if (idx >= total) return;
+  const int ch = int(idx % c_pad);
+  const long long pix = idx / c_pad;
+  const int x = int(pix % w), y = int((pix / w) % h), bi = int(pix / ((long long)w * h));
+  float v = 0.f;
+  if (ch < c) {
+    const long long tok = ((long long)bi * (h / 2) + y / 2) * (w / 2) + x / 2;
+    const float pv = __bfloat162float(packed[tok * (4 * c) + ch * 4 + (y & 1) * 2 + (x & 1)]);
+    // z / scale_factor then + shift_factor, each rounded like the reference's two bf16 ops
+    v = __bfloat162float(__float2bfloat16(pv * inv_scale)) + shift;
+  }
+  z[idx] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------ GroupNorm (32 groups) on NHWC
+// stats: each block reduces a slab of rows; thread owns 8 consecutive channels.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* x, double* sums, long long hw, int C,
+                                                              int rows_per_block) {
+  __shared__ float s_sum[32], s_sq[32];
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int tpr = C / 8;                 // threads per row
+  const int rpi = 256 / tpr;             // rows per iteration
+  const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(hw, r0 + rows_per_block);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (tr < rpi) {
+    const __nv_bfloat16* base = x + (long long)b * hw * C + tc * 8;
+    for (long long r = r0 + tr; r < r1; r += rpi) {
+      float v[8];
+      load8(base + r * C, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
+    }
+  }
+  const int gs = C / 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (tc * 8 + j) / gs;
+    atomicAdd(&s_sum[g], s[j]);
+    atomicAdd(&s_sq[g], q[j]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&sums[((long long)b * 32 + threadIdx.x) * 2], (double)s_sum[threadIdx.x]);
+    atomicAdd(&sums[((long long)b * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  }
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* x, const double* sums,
+                                                              const __nv_bfloat16* weight, const __nv_bfloat16* bias,
+                                                              __nv_bfloat16* out, long long hw, int C, float eps,
+                                                              int do_silu) {
+  const int b = blockIdx.y;
+  const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel vector index in image
+  const long long nvec = hw * (C / 8);
+  if (vec >= nvec) return;
+  const int c0 = int(vec % (C / 8)) * 8;
+  const int gs = C / 32;
+  const double n = (double)hw * gs;
+  float v[8], w[8], bb[8], o[8];
+  const long long off = (long long)b * hw * C + vec * 8;
+  load8(x + off, v);
+  load8(weight + c0, w);
+  load8(bias + c0, bb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / gs;
+    const double su = sums[((long long)b * 32 + g) * 2], sq = sums[((long long)b * 32 + g) * 2 + 1];
+    const double mean = su / n;
+    const double var = fmax(sq / n - mean * mean, 0.0);
+    const float rstd = rsqrtf((float)var + eps);
+    float y = (v[j] - (float)mean) * rstd * w[j] + bb[j];
+    if (do_silu) y = silu(__bfloat162float(__float2bfloat16(y)));
+    o[j] = y;
+  }
+  store8(out + off, o);
+}
+
+// ------------------------------------------------------------------ nearest 2x upsample (NHWC)
+__global__ void upsample2x_kernel(const uint4* x, uint4* out, int batch, int H, int W, int cv /* C/8 */) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)batch * (2 * H) * (2 * W) * cv;
+  if (idx >= total) return;
+  const int c = int(idx % cv);
+  const long long pix = idx / cv;
+  const int ox = int(pix % (2 * W)), oy = int((pix / (2 * W)) % (2 * H)), b = int(pix / ((long long)4 * W * H));
+  out[idx] = x[(((long long)b * H + oy / 2) * W + ox / 2) * cv + c];
+}
+
+// ------------------------------------------------------------------ row softmax fp32 -> bf16
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* S, long long ld_s, __nv_bfloat16* P,
+                                                           long long ld_p, int cols, float scale) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* row = S + (long long)blockIdx.x * ld_s;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast * scale;
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    sum += __expf(v.x * scale - mx) + __expf(v.y * scale - mx) + __expf(v.z * scale - mx) + __expf(v.w * scale - mx);
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i];
+    bcast = 1.0f / s;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  __nv_bfloat16* prow = P + (long long)blockIdx.x * ld_p;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c);
+    uint2 u;
+    u.x = pack_bf16(__expf(v.x * scale - mx) * inv, __expf(v.y * scale - mx) * inv);
+    u.y = pack_bf16(__expf(v.z * scale - mx) * inv, __expf(v.w * scale - mx) * inv);
+    *reinterpret_cast<uint2*>(prow + c) = u;
+  }
+}
+
+// ------------------------------------------------------------------ bf16 transpose (32x32 smem tiles)
+__global__ void transpose_kernel(const __nv_bfloat16* x, long long ldx, __nv_bfloat16* out, long long ldo, int rows,
+                                 int cols) {
+  __shared__ __nv_bfloat16 t[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = blockIdx.y * 32 + i;
+    if (r < rows && c < cols) t[i][threadIdx.x] = x[(long long)r * ldx + c];
+  }
+  __syncthreads();
+  const int orow_c = blockIdx.y * 32 + threadIdx.x;  // original row -> output column
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ocol = blockIdx.x * 32 + i;  // original column -> output row
+    if (ocol < cols && orow_c < rows) out[(long long)ocol * ldo + orow_c] = t[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ image finish
+__global__ void finish_image_kernel(const float* x, float* img, uint8_t* u8, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(x[i] + 1.0f, 0.0f), 2.0f) * 0.5f;
+  if (img) img[i] = v;
+  if (u8) u8[i] = (uint8_t)(v * 255.0f);  // truncation, like astype(uint8)
+}
+
+// ------------------------------------------------------------------ embedding gather
+__global__ void embedding_kernel(const int32_t* ids, const uint4* table, const __nv_bfloat16* pos_table, uint4* out,
+                                 long long n_ids, int seq, int dv /* D/8 */) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_ids * dv) return;
+  const long long t = idx / dv;
+  const int c = int(idx % dv);
+  uint4 v = table[(long long)ids[t] * dv + c];
+  if (pos_table) {
+    float a[8], b[8];
+    float2 f;
+    f = unpack_bf16(v.x); a[0] = f.x; a[1] = f.y; f = unpack_bf16(v.y); a[2] = f.x; a[3] = f.y;
+    f = unpack_bf16(v.z); a[4] = f.x; a[5] = f.y; f = unpack_bf16(v.w); a[6] = f.x; a[7] = f.y;
+    load8(pos_table + ((long long)(t % seq) * dv + c) * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    v.x = pack_bf16(a[0], a[1]); v.y = pack_bf16(a[2], a[3]); v.z = pack_bf16(a[4], a[5]); v.w = pack_bf16(a[6], a[7]);
+  }
+  out[idx] = v;
+}
+
+__global__ void act_mul_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* out, long long n, int act) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float x[8], y[8];
+    load8(a + i, x);
+    load8(b + i, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = __bfloat162float(__float2bfloat16(apply_act(x[j], act))) * y[j];
+    store8(out + i, x);
+  } else {
+    for (long long k = i; k < n; ++k)
+      out[k] = __float2bfloat16(__bfloat162float(__float2bfloat16(apply_act(__bfloat162float(a[k]), act))) *
+                                __bfloat162float(b[k]));
+  }
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->x && a->out && a->p0, "fx_rownorm: null pointer");
+  FX_REQUIRE(a->mode >= 0 && a->mode <= 2, "fx_rownorm: bad mode %d", a->mode);
+  FX_REQUIRE(a->mode == 2 || a->p1, "fx_rownorm: p1 required for mode %d", a->mode);
+  FX_REQUIRE(a->D % 256 == 0 && a->D >= 256 && a->D <= 4096, "fx_rownorm: D (%d) must be a multiple of 256 in [256, 4096]", a->D);
+  FX_REQUIRE(a->ldx % 8 == 0 && a->ldo % 8 == 0 && a->x_bs % 8 == 0 && a->out_bs % 8 == 0 && a->p_bs % 8 == 0,
+             "fx_rownorm: strides must be multiples of 8 elements");
+  if (a->batch <= 0 || a->rows <= 0) return FX_OK;
+  RowNormParams p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, (__nv_bfloat16*)a->out, a->ldo, a->out_bs,
+                  (const __nv_bfloat16*)a->p0, (const __nv_bfloat16*)a->p1, a->p_bs, a->eps, a->mode, a->batch, a->rows, a->D};
+  const long long rows = (long long)a->batch * a->rows;
+  const int blocks = int((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->D / 256) {
+#define FX_RN(I) case I: rownorm_kernel<I><<<blocks, 256, 0, st>>>(p); break;
+    FX_RN(1) FX_RN(2) FX_RN(3) FX_RN(4) FX_RN(5) FX_RN(6) FX_RN(7) FX_RN(8)
+    FX_RN(9) FX_RN(10) FX_RN(11) FX_RN(12) FX_RN(13) FX_RN(14) FX_RN(15) FX_RN(16)
+#undef FX_RN
+  }
+  return launched("rownorm_kernel");
+}
+
+extern "C" int fx_gemv(const fx_gemv_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->in && a->W && a->out, "fx_gemv: null pointer");
+  FX_REQUIRE(a->K % 8 == 0 && a->ldw % 8 == 0 && a->K > 0 && a->N > 0 && a->batch > 0, "fx_gemv: K, ldw multiples of 8");
+  FX_REQUIRE(a->K <= 8192, "fx_gemv: K too large");
+  static bool done = false;
+  if (!done) {
+    FX_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192 * 2));
+    done = true;
+  }
+  for (int b0 = 0; b0 < a->batch; b0 += 8) {
+    const int nb = a->batch - b0 < 8 ? a->batch - b0 : 8;
+    GemvParams p{(const __nv_bfloat16*)a->in + b0 * a->ld_in, a->ld_in, (const __nv_bfloat16*)a->W, a->ldw,
+                 (const __nv_bfloat16*)a->bias, a->add ? (const __nv_bfloat16*)a->add + b0 * a->ld_add : nullptr, a->ld_add,
+                 (__nv_bfloat16*)a->out + b0 * a->ld_out, a->ld_out, nb, a->N, a->K, a->silu_in, a->silu_out};
+    const int warps_needed = a->N;
+    int blocks = (warps_needed + 7) / 8;
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    gemv_kernel<<<blocks, 256, (size_t)nb * a->K * 2, (cudaStream_t)stream>>>(p);
+    int rc = launched("gemv_kernel");
+    if (rc) return rc;
+  }
+  return FX_OK;
+}
+
+extern "C" int fx_timestep_embedding(const void* t, void* out, int32_t batch, int32_t dim, fx_stream stream) {
+  FX_REQUIRE(t && out && batch > 0 && dim > 0 && dim % 2 == 0, "fx_timestep_embedding: bad arguments");
+  const int n = batch * dim / 2;
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)t, (__nv_bfloat16*)out, batch, dim);
+  return launched("timestep_embedding_kernel");
+}
+
+extern "C" int fx_euler_step(void* x, const void* pred, float dt, int64_t n, fx_stream stream) {
+  FX_REQUIRE(x && pred && n > 0, "fx_euler_step: bad arguments");
+  FX_REQUIRE(aligned16(x) && aligned16(pred), "fx_euler_step: unaligned");
+  const long long vecs = (n + 7) / 8;
+  euler_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x, (const __nv_bfloat16*)pred, dt, n);
+  return launched("euler_kernel");
+}
+
+extern "C" int fx_patchify(const void* x, void* out, int32_t b, int32_t h, int32_t w, int32_t c, fx_stream stream) {
+  FX_REQUIRE(x && out && b > 0 && h > 0 && w > 0 && c > 0, "fx_patchify: bad arguments");
+  FX_REQUIRE(h % 2 == 0 && w % 2 == 0, "fx_patchify: latent size (%d, %d) must be even", h, w);
+  const long long n = (long long)b * h * w * c;
+  patchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, b, h, w, c);
+  return launched("patchify_kernel");
+}
+
+extern "C" int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32_t h, int32_t w, int32_t c, int32_t c_pad,
+                                   float scale_factor, float shift_factor, fx_stream stream) {
+  FX_REQUIRE(packed && z && b > 0 && h > 0 && w > 0 && c > 0 && c_pad >= c, "fx_unpatchify_scale: bad arguments");
+  FX_REQUIRE(h % 2 == 0 && w % 2 == 0, "fx_unpatchify_scale: latent size (%d, %d) must be even", h, w);
+  const long long n = (long long)b * h * w * c_pad;
+  unpatchify_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)packed, (__nv_bfloat16*)z, b, h, w, c, c_pad, 1.0f / scale_factor, shift_factor);
+  return launched("unpatchify_scale_kernel");
+}
+
+extern "C" int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, int64_t hw, int32_t C, fx_stream stream) {
+  FX_REQUIRE(x && sums && batch > 0 && hw > 0, "fx_groupnorm_stats: bad arguments");
+  FX_REQUIRE(C % 32 == 0 && C >= 64 && C <= 2048 && (C / 8) <= 256 && 256 % (C / 8) == 0,
+             "fx_groupnorm_stats: unsupported channel count %d", C);
+  const int rows_per_block = 256;
+  dim3 grid((unsigned)((hw + rows_per_block - 1) / rows_per_block), batch);
+  groupnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sums, hw, C, rows_per_block);
+  return launched("groupnorm_stats_kernel");
+}
+
+extern "C" int fx_groupnorm_apply(const void* x, const double* sums, const void* weight, const void* bias, void* out,
+                                  int32_t batch, int64_t hw, int32_t C, float eps, int32_t do_silu, fx_stream stream) {
+  FX_REQUIRE(x && sums && weight && bias && out && batch > 0 && hw > 0 && C % 32 == 0 && C % 8 == 0, "fx_groupnorm_apply: bad arguments");
+  const long long nvec = hw * (C / 8);
+  dim3 grid((unsigned)((nvec + 255) / 256), batch);
+  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sums, (const __nv_bfloat16*)weight,
+                                                              (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, hw, C, eps, do_silu);
+  return launched("groupnorm_apply_kernel");
+}
+
+extern "C" int fx_upsample2x(const void* x, void* out, int32_t batch, int32_t H, int32_t W, int32_t C, fx_stream stream) {
+  FX_REQUIRE(x && out && batch > 0 && H > 0 && W > 0 && C % 8 == 0, "fx_upsample2x: bad arguments");
+  const long long n = (long long)batch * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, batch, H, W, C / 8);
+  return launched("upsample2x_kernel");
+}
+
+extern "C" int fx_softmax_rows(const float* S, int64_t ld_s, void* P, int64_t ld_p, int64_t rows, int32_t cols, float scale,
+                               fx_stream stream) {
+  FX_REQUIRE(S && P && rows > 0 && cols > 0 && cols % 4 == 0 && ld_s % 4 == 0 && ld_p % 4 == 0, "fx_softmax_rows: bad arguments");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(S, ld_s, (__nv_bfloat16*)P, ld_p, cols, scale);
+  return launched("softmax_rows_kernel");
+}
+
+extern "C" int fx_transpose(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t rows, int32_t cols, fx_stream stream) {
+  FX_REQUIRE(x && out && rows > 0 && cols > 0, "fx_transpose: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, rows, cols);
+  return launched("transpose_kernel");
+}
+
+extern "C" int fx_finish_image(const float* x, float* img, uint8_t* u8, int64_t n, fx_stream stream) {
+  FX_REQUIRE(x && n > 0 && (img || u8), "fx_finish_image: bad arguments");
+  finish_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, img, u8, n);
+  return launched("finish_image_kernel");
+}
+
+extern "C" int fx_embedding(const int32_t* ids, const void* table, const void* pos_table, void* out, int64_t n_ids,
+                            int32_t seq, int32_t D, fx_stream stream) {
+  FX_REQUIRE(ids && table && out && n_ids > 0 && D % 8 == 0 && seq > 0, "fx_embedding: bad arguments");
+  const long long n = n_ids * (D / 8);
+  embedding_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, (const uint4*)table, (const __nv_bfloat16*)pos_table,
+                                                                               (uint4*)out, n_ids, seq, D / 8);
+  return launched("embedding_kernel");
+}
+
+extern "C" int fx_act_mul(const void* a, const void* b, void* out, int64_t n, int32_t act, fx_stream stream) {
+  FX_REQUIRE(a && b && out && n > 0, "fx_act_mul: bad arguments");
+  const long long vecs = (n + 7) / 8;
+  act_mul_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                                                (__nv_bfloat16*)out, n, act);
+  return launched("act_mul_kernel");
+}

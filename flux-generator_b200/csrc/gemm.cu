@@ -1,0 +1,199 @@
+// Host launchers for the tcgen05 GEMM family (fx_gemm, fx_gemm_qkv, fx_conv3x3).
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "api_common.cuh"
+#include "gemm.cuh"
+#include "tmap.cuh"
+
+namespace fx {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
+  p.tiles_m_per_batch = tiles_m_per_batch;
+  p.tiles_m = tiles_m_per_batch * p.batch;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  // raster: GROUP_M m-tiles x all n-tiles per group; a wave of ~148 CTAs then touches
+  // group_m A-tiles and ~148/group_m W-slabs -> both operands are re-read from L2, not HBM.
+  p.group_m = p.tiles_m < 16 ? p.tiles_m : 16;
+}
+
+template <int BN, int EPI, bool CONV>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, EPI, CONV>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, p);
+  return launched("gemm_kernel");
+}
+
+template <int EPI, bool CONV>
+static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  if (bn == 256) return launch<256, EPI, CONV>(ta, tw, p, st);
+  if (bn == 128) return launch<128, EPI, CONV>(ta, tw, p, st);
+  return launch<64, EPI, CONV>(ta, tw, p, st);
+}
+
+static int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->A && a->W && a->out, "fx_gemm: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm: empty problem (batch %d rows %d N %d K %d)",
+             a->batch, a->rows, a->N, a->K);
+  FX_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->a_bs % 8 == 0,
+             "fx_gemm: K, lda, ldw, a_bs must be multiples of 8 elements (TMA 16-byte strides)");
+  FX_REQUIRE(aligned16(a->A) && aligned16(a->W), "fx_gemm: A and W must be 16-byte aligned");
+  GemmParams p{};
+  p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
+  p.k_blocks = (a->K + GEMM_BK - 1) / GEMM_BK;
+  p.bias = (const __nv_bfloat16*)a->bias;
+  p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
+  p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
+  p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
+  const int bn = pick_bn(a->N);
+  fill_tiling(p, (a->rows + GEMM_BM - 1) / GEMM_BM, bn);
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a->batch > 1 ? a->a_bs : a->lda * (int64_t)a->rows) * 2};
+    const uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
+    int rc = make_tmap_bf16(&ta, a->A, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    const uint32_t box[2] = {GEMM_BK, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch_bn<EPI_GENERIC, false>(bn, ta, tw, p, (cudaStream_t)stream);
+}
+
+extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->A && a->W && a->q && a->k && a->v && a->pe && a->q_scale && a->k_scale, "fx_gemm_qkv: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->K > 0 && a->heads > 0, "fx_gemm_qkv: empty problem");
+  const int D3 = 3 * a->heads * 128;
+  FX_REQUIRE(a->N >= D3 && a->N % 128 == 0, "fx_gemm_qkv: N (%d) must be >= 3*heads*128 and a multiple of 128", a->N);
+  FX_REQUIRE(a->N == D3 || a->mlp_out, "fx_gemm_qkv: mlp_out required when N > 3*heads*128");
+  FX_REQUIRE(a->seq_off >= 0 && a->seq_off + a->rows <= a->seq_total, "fx_gemm_qkv: rows exceed seq_total");
+  FX_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->a_bs % 8 == 0 && a->ld_mlp % 8 == 0 &&
+                 a->mlp_bs % 8 == 0,
+             "fx_gemm_qkv: strides must be multiples of 8 elements");
+  GemmParams p{};
+  p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
+  p.k_blocks = (a->K + GEMM_BK - 1) / GEMM_BK;
+  p.bias = (const __nv_bfloat16*)a->bias;
+  p.out = a->mlp_out; p.ldo = a->ld_mlp; p.out_bs = a->mlp_bs; p.out_f32 = 0; p.act = FX_ACT_GELU_TANH;
+  p.heads = a->heads; p.seq_total = a->seq_total; p.seq_off = a->seq_off; p.rms_eps = a->rms_eps;
+  p.qnorm_w = (const __nv_bfloat16*)a->q_scale; p.knorm_w = (const __nv_bfloat16*)a->k_scale;
+  p.pe = (const uint32_t*)a->pe;
+  p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
+  fill_tiling(p, (a->rows + GEMM_BM - 1) / GEMM_BM, 256);
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
+    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a->batch > 1 ? a->a_bs : a->lda * (int64_t)a->rows) * 2};
+    const uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
+    int rc = make_tmap_bf16(&ta, a->A, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
+    const uint32_t box[2] = {GEMM_BK, 256};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch<256, EPI_QKV, false>(ta, tw, p, (cudaStream_t)stream);
+}
+
+extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->x && a->W && a->out, "fx_conv3x3: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->H > 0 && a->Wd > 0 && a->Cout > 0, "fx_conv3x3: empty problem");
+  FX_REQUIRE(a->Cin % 64 == 0 && a->Cin > 0, "fx_conv3x3: Cin (%d) must be a multiple of 64", a->Cin);
+  GemmParams p{};
+  p.batch = a->batch; p.rows = a->H * a->Wd; p.N = a->Cout; p.K = 9 * a->Cin;
+  p.cin_blocks = a->Cin / GEMM_BK;
+  p.k_blocks = 9 * p.cin_blocks;
+  p.conv_H = a->H; p.conv_W = a->Wd;
+  p.conv_tiles_x = (a->Wd + 15) / 16;
+  p.conv_tiles_y = (a->H + 7) / 8;
+  p.bias = (const __nv_bfloat16*)a->bias;
+  p.out = a->out; p.ldo = a->Cout; p.out_bs = (long long)a->H * a->Wd * a->Cout; p.out_f32 = a->out_f32;
+  p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = p.out_bs;
+  const int bn = pick_bn(a->Cout);
+  fill_tiling(p, p.conv_tiles_x * p.conv_tiles_y, bn);
+  CUtensorMap ta, tw;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->batch};
+    const uint64_t strides[3] = {(uint64_t)a->Cin * 2, (uint64_t)a->Wd * a->Cin * 2, (uint64_t)a->H * a->Wd * a->Cin * 2};
+    const uint32_t box[4] = {GEMM_BK, 16, 8, 1};
+    int rc = make_tmap_bf16(&ta, a->x, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)a->Cout};
+    const uint64_t strides[1] = {(uint64_t)p.K * 2};
+    const uint32_t box[2] = {GEMM_BK, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch_bn<EPI_GENERIC, true>(bn, ta, tw, p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// misc API
+// ------------------------------------------------------------------------------------------
+extern "C" int fx_version(void) { return 100; }
+extern "C" const char* fx_last_error(void) { return g_err; }
+extern "C" uint64_t fx_launch_count(void) { return g_launches.load(); }
+extern "C" int fx_check_device(int device) {
+  int major = 0, minor = 0;
+  FX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  FX_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) return fail(FX_ERR_ARCH, "device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
+  return FX_OK;
+}
+
+// CUDA-core reference GEMM (tests only): out[m][n] = sum_k A[m][k] W[n][k], fp32 out
+__global__ void dbg_gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
+                                    float* out, long long ldo, int M, int N, int K) {
+  __shared__ float sa[16][17], sw[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx;
+    sa[ty][tx] = (m < M && ka < K) ? __bfloat162float(A[(long long)m * lda + ka]) : 0.f;
+    const int nw = blockIdx.x * 16 + ty;
+    sw[ty][tx] = (nw < N && ka < K) ? __bfloat162float(W[(long long)nw * ldw + ka]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
+    __syncthreads();
+  }
+  if (m < M && n < N) out[(long long)m * ldo + n] = acc;
+}
+
+extern "C" int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo,
+                               int32_t M, int32_t N, int32_t K, fx_stream stream) {
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  dbg_gemm_ref_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W,
+                                                               ldw, out, ldo, M, N, K);
+  return launched("dbg_gemm_ref_kernel");
+}

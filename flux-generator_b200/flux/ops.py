@@ -1,0 +1,306 @@
+"""Thin torch-tensor wrappers over the C ABI (include/flux_b200.h).
+
+torch is used for device memory and streams only; every function enqueues one library call on the
+current CUDA stream.  Tensors may be strided views (column / row slices of wider buffers) as long
+as the innermost stride is 1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+ACT = {"none": 0, None: 0, "gelu_tanh": 1, "quick_gelu": 2, "gelu": 3, "gelu_erf": 3}
+bf16 = torch.bfloat16
+
+
+def _as3(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
+    """(batch, rows, cols, ld, batch_stride) of a 2-D/3-D view with unit inner stride."""
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError(f"expected a 2-D or 3-D tensor, got {tuple(t.shape)}")
+    if t.stride(2) != 1 and t.shape[2] > 1:
+        raise ValueError("innermost dimension must be contiguous")
+    b, r, c = t.shape
+    bs = t.stride(0) if b > 1 else r * t.stride(1)
+    return b, r, c, t.stride(1), bs
+
+
+def _chk(t: torch.Tensor, dtype=bf16) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("flux_b200 ops need CUDA tensors; there is no CPU fallback")
+    if t.dtype != dtype:
+        raise ValueError(f"expected {dtype}, got {t.dtype}")
+    return t
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         act=None, gate: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = bf16) -> torch.Tensor:
+    """out = resid + gate * act(a @ w.T + bias).  a [B,R,K] | [R,K]; w [N,K]; gate [B,N]; resid like out."""
+    _chk(a), _chk(w)
+    B, R, K, lda, abs_ = _as3(a)
+    Nn = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"weight {tuple(w.shape)} does not match K={K}")
+    if out is None:
+        out = torch.empty((B, R, Nn) if a.dim() == 3 else (R, Nn), device=a.device, dtype=out_dtype)
+    _chk(out, out.dtype)
+    _, _, _, ldo, obs = _as3(out)
+    args = N.GemmArgs()
+    args.A, args.lda, args.a_bs = a.data_ptr(), lda, abs_
+    args.W, args.ldw = w.data_ptr(), w.stride(0)
+    args.bias = N.ptr(bias)
+    args.out, args.ldo, args.out_bs = out.data_ptr(), ldo, obs
+    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    args.act = ACT[act]
+    if gate is not None:
+        _chk(gate)
+        args.gate, args.gate_bs = gate.data_ptr(), (gate.stride(0) if gate.dim() == 2 else 0)
+    if resid is not None:
+        _chk(resid)
+        _, _, _, ldr, rbs = _as3(resid)
+        args.resid, args.ldr, args.resid_bs = resid.data_ptr(), ldr, rbs
+    args.batch, args.rows, args.N, args.K = B, R, Nn, K
+    N.check(N.lib().fx_gemm(C.byref(args), N.stream()))
+    return out
+
+
+def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_scale: torch.Tensor,
+             k_scale: torch.Tensor, pe: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
+             seq_off: int, mlp_out: Optional[torch.Tensor] = None, rms_eps: float = 1e-5) -> None:
+    """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16."""
+    _chk(a), _chk(w), _chk(q), _chk(k), _chk(v), _chk(pe)
+    B, R, K, lda, abs_ = _as3(a)
+    H, seq_total = q.shape[1], q.shape[2]
+    args = N.QkvArgs()
+    args.A, args.lda, args.a_bs = a.data_ptr(), lda, abs_
+    args.W, args.ldw, args.bias = w.data_ptr(), w.stride(0), N.ptr(bias)
+    args.q_scale, args.k_scale, args.pe = q_scale.data_ptr(), k_scale.data_ptr(), pe.data_ptr()
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    if mlp_out is not None:
+        _chk(mlp_out)
+        _, _, _, ldm, mbs = _as3(mlp_out)
+        args.mlp_out, args.ld_mlp, args.mlp_bs = mlp_out.data_ptr(), ldm, mbs
+    args.rms_eps = rms_eps
+    args.batch, args.rows, args.N, args.K = B, R, w.shape[0], K
+    args.heads, args.seq_total, args.seq_off = H, seq_total, seq_off
+    N.check(N.lib().fx_gemm_qkv(C.byref(args), N.stream()))
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor] = None,
+            out_dtype: torch.dtype = bf16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B,H,W,Cin] NHWC contiguous; w [Cout, 9*Cin] (OHWI flattened)."""
+    _chk(x), _chk(w)
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if not x.is_contiguous():
+        raise ValueError("conv3x3 input must be contiguous NHWC")
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x.device, dtype=out_dtype)
+    args = N.ConvArgs()
+    args.x, args.W, args.bias, args.out = x.data_ptr(), w.data_ptr(), N.ptr(bias), out.data_ptr()
+    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    args.resid = N.ptr(resid)
+    args.batch, args.H, args.Wd, args.Cin, args.Cout = B, H, W, Cin, Cout
+    N.check(N.lib().fx_conv3x3(C.byref(args), N.stream()))
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
+              variant: int = 0) -> torch.Tensor:
+    """q,k,v [B,H,S,128] contiguous; out [B,S,>=H*128] view (head h -> columns h*128..)."""
+    _chk(q), _chk(k), _chk(v), _chk(out)
+    B, H, S, D = q.shape
+    if D != 128:
+        raise ValueError("attention kernel is specialised for head_dim 128")
+    _, _, _, ldo, obs = _as3(out)
+    args = N.AttnArgs()
+    args.q, args.k, args.v, args.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    args.ld_out, args.out_bs, args.scale = ldo, obs, scale
+    args.batch, args.heads, args.seq, args.variant = B, H, S, variant
+    N.check(N.lib().fx_attention(C.byref(args), N.stream()))
+    return out
+
+
+def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
+                    bias: Optional[torch.Tensor] = None, causal: bool = False,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q,k,v [B,S,heads*64] views sharing ld / batch stride; bias fp32 [heads,S,S]."""
+    _chk(q), _chk(k), _chk(v)
+    B, S, _, ld, bs = _as3(q)
+    if out is None:
+        out = torch.empty((B, S, heads * 64), device=q.device, dtype=bf16)
+    _, _, _, ldo, obs = _as3(out)
+    args = N.AttnSmallArgs()
+    args.q, args.k, args.v, args.ld, args.bs = q.data_ptr(), k.data_ptr(), v.data_ptr(), ld, bs
+    args.bias = N.ptr(bias)
+    args.out, args.ld_out, args.out_bs, args.scale = out.data_ptr(), ldo, obs, scale
+    args.batch, args.heads, args.seq, args.causal = B, heads, S, int(causal)
+    N.check(N.lib().fx_attention_small(C.byref(args), N.stream()))
+    return out
+
+
+def rownorm(x: torch.Tensor, mode: int, p0: torch.Tensor, p1: Optional[torch.Tensor], eps: float,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode 0: (1+p1[b])*LN(x)+p0[b]; mode 1: LN(x)*p0+p1; mode 2: RMSNorm(x)*p0."""
+    _chk(x)
+    B, R, D, ldx, xbs = _as3(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=bf16)
+    _, _, _, ldo, obs = _as3(out)
+    args = N.RowNormArgs()
+    args.x, args.ldx, args.x_bs = x.data_ptr(), ldx, xbs
+    args.out, args.ldo, args.out_bs = out.data_ptr(), ldo, obs
+    args.p0, args.p1 = p0.data_ptr(), N.ptr(p1)
+    args.p_bs = p0.stride(0) if (mode == 0 and p0.dim() == 2) else 0
+    args.eps, args.mode, args.batch, args.rows, args.D = eps, mode, B, R, D
+    N.check(N.lib().fx_rownorm(C.byref(args), N.stream()))
+    return out
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,
+         silu_in: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = W @ f(x[b]) + bias (+ add[b]);  x [B,K] (row stride arbitrary), w [N,K]."""
+    _chk(x), _chk(w)
+    B, K = x.shape
+    Nn = w.shape[0]
+    if out is None:
+        out = torch.empty((B, Nn), device=x.device, dtype=bf16)
+    args = N.GemvArgs()
+    args.in_, args.ld_in = x.data_ptr(), x.stride(0)
+    args.W, args.ldw, args.bias = w.data_ptr(), w.stride(0), N.ptr(bias)
+    if add is not None:
+        args.add, args.ld_add = add.data_ptr(), add.stride(0)
+    args.out, args.ld_out = out.data_ptr(), out.stride(0)
+    args.batch, args.N, args.K, args.silu_in, args.silu_out = B, Nn, K, int(silu_in), 0
+    N.check(N.lib().fx_gemv(C.byref(args), N.stream()))
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    _chk(t)
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=bf16)
+    N.check(N.lib().fx_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, N.stream()))
+    return out
+
+
+def euler_step(x: torch.Tensor, pred: torch.Tensor, dt: float) -> torch.Tensor:
+    _chk(x), _chk(pred)
+    if not (x.is_contiguous() and pred.is_contiguous()):
+        raise ValueError("euler_step needs contiguous tensors")
+    N.check(N.lib().fx_euler_step(x.data_ptr(), pred.data_ptr(), float(dt), x.numel(), N.stream()))
+    return x
+
+
+def patchify(x: torch.Tensor) -> torch.Tensor:
+    _chk(x)
+    b, h, w, c = x.shape
+    out = torch.empty((b, h * w // 4, 4 * c), device=x.device, dtype=bf16)
+    N.check(N.lib().fx_patchify(x.contiguous().data_ptr(), out.data_ptr(), b, h, w, c, N.stream()))
+    return out
+
+
+def unpatchify_scale(packed: torch.Tensor, latent_size, c_pad: int, scale_factor: float,
+                     shift_factor: float) -> torch.Tensor:
+    _chk(packed)
+    h, w = latent_size
+    b, L, f = packed.shape
+    if L != h * w // 4:
+        raise ValueError(f"packed latents have {L} tokens, latent_size {latent_size} needs {h * w // 4}")
+    c = f // 4
+    z = torch.empty((b, h, w, c_pad), device=packed.device, dtype=bf16)
+    N.check(N.lib().fx_unpatchify_scale(packed.contiguous().data_ptr(), z.data_ptr(), b, h, w, c, c_pad,
+                                        scale_factor, shift_factor, N.stream()))
+    return z
+
+
+def groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, silu: bool,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32) on NHWC-like [B, ..., C] contiguous (+ optional SiLU)."""
+    _chk(x)
+    B, Cc = x.shape[0], x.shape[-1]
+    hw = x.numel() // (B * Cc)
+    sums = torch.zeros((B, 32, 2), device=x.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty_like(x)
+    l = N.lib()
+    N.check(l.fx_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, hw, Cc, N.stream()))
+    N.check(l.fx_groupnorm_apply(x.data_ptr(), sums.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                 B, hw, Cc, eps, int(silu), N.stream()))
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _chk(x)
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, 2 * H, 2 * W, Cc), device=x.device, dtype=bf16)
+    N.check(N.lib().fx_upsample2x(x.data_ptr(), out.data_ptr(), B, H, W, Cc, N.stream()))
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(s, torch.float32)
+    rows, cols = s.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=s.device, dtype=bf16)
+    N.check(N.lib().fx_softmax_rows(s.data_ptr(), s.stride(0), out.data_ptr(), out.stride(0), rows, cols, scale,
+                                    N.stream()))
+    return out
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    _chk(x)
+    rows, cols = x.shape
+    out = torch.empty((cols, rows), device=x.device, dtype=bf16)
+    N.check(N.lib().fx_transpose(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rows, cols, N.stream()))
+    return out
+
+
+def finish_image(x: torch.Tensor, want_u8: bool = True):
+    _chk(x, torch.float32)
+    img = torch.empty_like(x)
+    u8 = torch.empty(x.shape, device=x.device, dtype=torch.uint8) if want_u8 else None
+    N.check(N.lib().fx_finish_image(x.data_ptr(), img.data_ptr(), N.ptr(u8), x.numel(), N.stream()))
+    return img, u8
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor, pos_table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(table)
+    if ids.dtype != torch.int32:
+        raise ValueError("token ids must be int32")
+    B, S = ids.shape
+    D = table.shape[1]
+    out = torch.empty((B, S, D), device=table.device, dtype=bf16)
+    N.check(N.lib().fx_embedding(ids.contiguous().data_ptr(), table.data_ptr(), N.ptr(pos_table), out.data_ptr(),
+                                 B * S, S, D, N.stream()))
+    return out
+
+
+def act_mul(a: torch.Tensor, b: torch.Tensor, act: str) -> torch.Tensor:
+    _chk(a), _chk(b)
+    out = torch.empty_like(a)
+    N.check(N.lib().fx_act_mul(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), ACT[act], N.stream()))
+    return out
+
+
+def dbg_gemm_ref(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    M, K = a.shape
+    Nn = w.shape[0]
+    out = torch.empty((M, Nn), device=a.device, dtype=torch.float32)
+    N.check(N.lib().fx_dbg_gemm_ref(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), Nn, M, Nn,
+                                    K, N.stream()))
+    return out
+
+
+def dbg_umma_tile(a: torch.Tensor, b: torch.Tensor, n: int, b_mn_major: bool, a_tmem: bool, lbo: int, sbo: int,
+                  kstep: int) -> torch.Tensor:
+    K = a.shape[1]
+    d = torch.empty((128, n), device=a.device, dtype=torch.float32)
+    N.check(N.lib().fx_dbg_umma_tile(a.data_ptr(), b.data_ptr(), d.data_ptr(), K, n, int(b_mn_major), int(a_tmem),
+                                     lbo, sbo, kstep, N.stream()))
+    return d

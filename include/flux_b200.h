@@ -1,0 +1,202 @@
+/* flux_b200.h -- C ABI of libflux_b200.so: the B200-native (sm_100a) kernels behind the Flux
+ * denoising hot path (sampler step -> MMDiT forward -> VAE decode; T5/CLIP helpers).
+ *
+ * The reference (voipnuggets/flux-generator) has no native ABI: its hot path is Python calling
+ * Apple-MLX primitives.  Each entry point below replaces the MLX call sites cited beside it
+ * (paths relative to the reference root); INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add to route those call sites here.
+ *
+ * Conventions
+ *  - plain C: POD structs, raw DEVICE pointers, sizes in elements unless the name says bytes.
+ *  - the library never allocates, frees or synchronises device memory; every function only
+ *    enqueues work on the caller's `stream` (CUDA-graph capturable) and returns 0 or a negative
+ *    fx_status.  fx_last_error() returns a thread-local message for the last failure.
+ *  - bf16 storage everywhere unless stated; accumulation is fp32.
+ *  - "ld" = leading dimension (elements between consecutive rows); "bs" = batch stride (elements).
+ */
+#ifndef FLUX_B200_H
+#define FLUX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fx_stream; /* cudaStream_t */
+
+typedef enum fx_status {
+  FX_OK = 0,
+  FX_ERR_INVALID = -1, /* bad shape / alignment / argument (Python shim raises ValueError) */
+  FX_ERR_CUDA = -2,    /* CUDA runtime / driver error (RuntimeError) */
+  FX_ERR_ARCH = -3     /* device is not sm_100 */
+} fx_status;
+
+int fx_version(void);
+const char* fx_last_error(void);
+/* number of kernels this library has launched on any stream since load (bench.py: gpu_launches) */
+uint64_t fx_launch_count(void);
+/* 0 when `device` is compute capability 10.x */
+int fx_check_device(int device);
+
+/* ---------------------------------------------------------------- tcgen05 GEMM family
+ * out = epilogue(A . W^T), A [batch][rows][K], W [N][K] (nn.Linear layout, K contiguous).
+ * Replaces every nn.Linear on the path: flux/layers.py:82-85,104-106,134,162-166,175-179,250-252,
+ * 292-296; flux/model.py:56-64; flux/autoencoder.py:36-39,84 (1x1 convs); flux/t5.py:126-129,
+ * 166-170; flux/clip.py:55-58 and mlx.nn.MultiHeadAttention's projections. */
+typedef enum fx_act { FX_ACT_NONE = 0, FX_ACT_GELU_TANH = 1, FX_ACT_QUICK_GELU = 2, FX_ACT_GELU_ERF = 3 } fx_act;
+
+typedef struct fx_gemm_args {
+  const void* A; int64_t lda; int64_t a_bs;
+  const void* W; int64_t ldw;
+  const void* bias;            /* [N] or NULL */
+  void* out; int64_t ldo; int64_t out_bs;
+  int32_t out_f32;             /* 1: out is float32 */
+  int32_t act;                 /* fx_act, applied after bias */
+  const void* gate; int64_t gate_bs;               /* [batch][N] multiplier or NULL */
+  const void* resid; int64_t ldr; int64_t resid_bs; /* [batch][rows][N] addend or NULL (may alias out) */
+  int32_t batch, rows, N, K;
+} fx_gemm_args;
+/* v = A.W^T + bias; v = act(v); v *= gate[b][n]; v += resid[b][r][n]   (each optional) */
+int fx_gemm(const fx_gemm_args* a, fx_stream stream);
+
+/* Fused QKV(+MLP-in) projection: W columns are [q | k | v | mlp] (flux/layers.py:195-199,269-277).
+ * Per 128-wide head: +bias, QK-RMSNorm (eps, learned scale; flux/layers.py:88-95), RoPE with the
+ * (cos,sin) table `pe` (flux/layers.py:24-33), scatter to q/k/v [batch][heads][seq_total][128] at
+ * sequence offset seq_off (deletes the split/transpose/concat of flux/layers.py:195-214).  Columns
+ * past 3*heads*128 get +bias, GELU(tanh) and land in `mlp_out` (flux/layers.py:283's concat). */
+typedef struct fx_qkv_args {
+  const void* A; int64_t lda; int64_t a_bs;
+  const void* W; int64_t ldw;
+  const void* bias;
+  const void* q_scale; const void* k_scale; /* [128] RMSNorm weights */
+  const void* pe;              /* [seq_total][64][2] bf16 (cos, sin) */
+  void* q; void* k; void* v;   /* [batch][heads][seq_total][128] */
+  void* mlp_out; int64_t ld_mlp; int64_t mlp_bs; /* [batch][seq_total][ld_mlp] (row = seq_off + r) or NULL */
+  float rms_eps;
+  int32_t batch, rows, N, K, heads, seq_total, seq_off;
+} fx_qkv_args;
+int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream);
+
+/* 3x3 / pad 1 / stride 1 convolution as implicit GEMM on NHWC bf16 (nn.Conv2d at
+ * flux/autoencoder.py:69-81,117-119,237-239,269).  W is OHWI flattened to [Cout][9*Cin]
+ * (AutoEncoder.sanitize's layout, flux/autoencoder.py:336-345).  Cin % 64 == 0.
+ * out = conv + bias (+ resid).  out may be float32. */
+typedef struct fx_conv3x3_args {
+  const void* x;               /* [batch][H][W][Cin] */
+  const void* W; const void* bias;
+  void* out; int32_t out_f32;  /* [batch][H][W][Cout] */
+  const void* resid;           /* [batch][H][W][Cout] or NULL */
+  int32_t batch, H, Wd, Cin, Cout;
+} fx_conv3x3_args;
+int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream);
+
+/* ---------------------------------------------------------------- attention
+ * Non-causal softmax(q k^T * scale) v over head_dim 128 on tcgen05 (flash-style, online softmax);
+ * replaces mx.fast.scaled_dot_product_attention + the transpose/reshape at flux/layers.py:41-43.
+ * q,k,v [batch][heads][seq][128]; out [batch][seq][ld_out], head h at columns h*128. */
+typedef struct fx_attn_args {
+  const void* q; const void* k; const void* v;
+  void* out; int64_t ld_out; int64_t out_bs;
+  float scale;
+  int32_t batch, heads, seq;
+  int32_t variant;             /* 0 = default; other values select bring-up variants (tests) */
+} fx_attn_args;
+int fx_attention(const fx_attn_args* a, fx_stream stream);
+
+/* Small generic attention for the once-per-prompt text encoders (head_dim 64): optional additive
+ * bias [heads][seq][seq] (T5, flux/t5.py:153-155) and causal mask (CLIP, flux/clip.py:90-94).
+ * q,k,v are column slices of [batch][seq][ld] activations, head h at columns h*64. */
+typedef struct fx_attn_small_args {
+  const void* q; const void* k; const void* v; int64_t ld; int64_t bs;
+  const float* bias;           /* fp32 [heads][seq][seq] or NULL */
+  void* out; int64_t ld_out; int64_t out_bs;
+  float scale;
+  int32_t batch, heads, seq, causal;
+} fx_attn_small_args;
+int fx_attention_small(const fx_attn_small_args* a, fx_stream stream);
+
+/* ---------------------------------------------------------------- row-wise normalisation
+ * mode 0: LayerNorm(no affine, eps) then (1+scale[b])*y + shift[b]  (flux/layers.py:193,222,267,300)
+ * mode 1: LayerNorm(affine weight/bias per column)                  (flux/clip.py:52-53,87)
+ * mode 2: RMSNorm(weight per column)                                (flux/t5.py:196-197,216) */
+typedef struct fx_rownorm_args {
+  const void* x; int64_t ldx; int64_t x_bs;
+  void* out; int64_t ldo; int64_t out_bs;
+  const void* p0; const void* p1; int64_t p_bs; /* mode 0: shift, scale [batch][D]; mode 1: weight, bias; mode 2: weight */
+  float eps;
+  int32_t mode, batch, rows, D;
+} fx_rownorm_args;
+int fx_rownorm(const fx_rownorm_args* a, fx_stream stream);
+
+/* ---------------------------------------------------------------- conditioning vector path
+ * out[b][n] = sum_k f(in[b][k]) W[n][k] + bias[n] (+ add[b][n]); f = SiLU when silu_in.
+ * The M=batch GEMVs of MLPEmbedder / Modulation / LastLayer.adaLN (flux/layers.py:78-85,129-143,
+ * 294-299): weight-streaming, HBM-bound. */
+typedef struct fx_gemv_args {
+  const void* in; int64_t ld_in;
+  const void* W; int64_t ldw;
+  const void* bias; const void* add; int64_t ld_add;
+  void* out; int64_t ld_out;
+  int32_t batch, N, K, silu_in, silu_out;
+} fx_gemv_args;
+int fx_gemv(const fx_gemv_args* a, fx_stream stream);
+
+/* timestep_embedding (flux/layers.py:46-57): t [batch] bf16 -> [batch][256] bf16 = bf16([cos|sin]
+ * (bf16(1000*t) * freqs)). */
+int fx_timestep_embedding(const void* t_bf16, void* out, int32_t batch, int32_t dim, fx_stream stream);
+
+/* FluxSampler.step (flux/sampler.py:56-57): x = bf16(x + dt * pred), n elements. */
+int fx_euler_step(void* x, const void* pred, float dt, int64_t n, fx_stream stream);
+
+/* ---------------------------------------------------------------- latent packing
+ * _prepare_latent_images (flux/flux.py:53-58): [b][h][w][c] -> [b][hw/4][4c], feature c*4+dy*2+dx */
+int fx_patchify(const void* x, void* out, int32_t b, int32_t h, int32_t w, int32_t c, fx_stream stream);
+/* FluxPipeline.decode's inverse + AutoEncoder.decode's affine (flux/flux.py:159-160,
+ * flux/autoencoder.py:353): packed [b][hw/4][4c] -> z [b][h][w][c_pad] = x/scale + shift, channels
+ * c..c_pad-1 zero (conv_in reads 64-channel blocks). */
+int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32_t h, int32_t w, int32_t c,
+                        int32_t c_pad, float scale_factor, float shift_factor, fx_stream stream);
+
+/* ---------------------------------------------------------------- VAE decoder pieces
+ * GroupNorm(32 groups, eps, affine) [+ SiLU] on NHWC bf16 (flux/autoencoder.py:29-35,62-78,88-94).
+ * stats: `sums` is double [batch][32][2] (sum, sum of squares), zeroed by the caller. */
+int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, int64_t hw, int32_t C, fx_stream stream);
+int fx_groupnorm_apply(const void* x, const double* sums, const void* weight, const void* bias, void* out,
+                       int32_t batch, int64_t hw, int32_t C, float eps, int32_t silu, fx_stream stream);
+/* upsample_nearest(x, (2,2)) on NHWC (flux/autoencoder.py:122) */
+int fx_upsample2x(const void* x, void* out, int32_t batch, int32_t H, int32_t W, int32_t C, fx_stream stream);
+/* P = softmax(scale * S) row-wise, S fp32 [rows][ld_s] -> P bf16 [rows][ld_p]  (VAE mid attention,
+ * flux/autoencoder.py:49, head_dim 512 via two GEMMs) */
+int fx_softmax_rows(const float* S, int64_t ld_s, void* P, int64_t ld_p, int64_t rows, int32_t cols, float scale,
+                    fx_stream stream);
+/* [rows][cols] -> [cols][rows] bf16 transpose (V^T for the P.V GEMM) */
+int fx_transpose(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t rows, int32_t cols, fx_stream stream);
+/* clip(x+1,0,2)*0.5 (flux/flux.py:162) -> float32 image, and (img*255) truncated to uint8
+ * (txt2image.py:133).  x is float32 [n]; either output may be NULL. */
+int fx_finish_image(const float* x, float* img, uint8_t* u8, int64_t n, fx_stream stream);
+
+/* ---------------------------------------------------------------- text-encoder helpers
+ * rows of `table` [vocab][D] gathered by int32 ids (+ optional pos table row i%seq) */
+int fx_embedding(const int32_t* ids, const void* table, const void* pos_table, void* out, int64_t n_ids,
+                 int32_t seq, int32_t D, fx_stream stream);
+/* y = act(a) * b elementwise (T5 gated FFN, flux/t5.py:178-184), act = fx_act */
+int fx_act_mul(const void* a, const void* b, void* out, int64_t n, int32_t act, fx_stream stream);
+
+/* ---------------------------------------------------------------- bring-up / test kernels
+ * Plain CUDA-core reference kernels used only by tests to check the tcgen05 paths at sizes the CPU
+ * oracle cannot reach.  Never called by the product path. */
+int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int32_t M,
+                    int32_t N, int32_t K, fx_stream stream);
+
+/* One CTA, K/16 tcgen05.mma on hand-laid shared-memory operands with caller-supplied descriptor fields:
+ * sweeps UMMA encodings (MN-major B, A-from-TMEM) against a CPU matmul.  A [128][K]; B [N][K] (K-major) or
+ * [K][N] (MN-major); D float [128][N]. */
+int fx_dbg_umma_tile(const void* A, const void* B, float* D, int32_t K, int32_t N, int32_t b_mn_major,
+                     int32_t a_tmem, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, fx_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUX_B200_H */
