@@ -1,0 +1,291 @@
+"""Flux MMDiT on B200 (reference: flux/model.py:35-136, flux/layers.py).
+
+Host-side mirror of the reference's ``Flux`` module: same constructor argument, same ``__call__``
+signature and error behaviour, same checkpoint key names (``sanitize``).  The forward pass is a
+chain of libflux_b200 kernels over a fixed workspace:
+
+  conditioning vector  : timestep_embedding -> GEMVs (time_in / guidance_in / vector_in) -> ONE GEMV
+                         over all 19*2 + 38 + 1 modulation Linears (weights contiguous in the arena)
+  residual stream      : x [B, S+L, D] joint buffer, text rows first (flux/layers.py:212-214)
+  per block            : rownorm(+AdaLN) -> tcgen05 GEMM with fused QKV epilogue (bias, QK-RMSNorm,
+                         RoPE, head scatter; for single blocks also the GELU'd MLP-in columns written
+                         next to the attention output) -> tcgen05 flash attention -> tcgen05 GEMM with
+                         fused bias + gate + residual epilogue (in place on x)
+
+No concat / split / transpose kernels exist on this path.  All weights live in one contiguous bf16
+arena (one ``ncclBroadcast`` at load for multi-GPU).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .specs import FluxParams, flow_manifest
+
+bf16 = torch.bfloat16
+QK_RMS_EPS = 1e-5  # mlx.nn.RMSNorm default eps (flux/layers.py:91-92 pass none)
+
+
+def _align(n: int, a: int = 128) -> int:
+    return (n + a - 1) // a * a
+
+
+class WeightArena:
+    """One contiguous bf16 device buffer holding every tensor of a manifest (256-byte aligned)."""
+
+    def __init__(self, entries: List[Tuple[str, Tuple[int, ...]]], device):
+        self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for key, shape in entries:
+            n = 1
+            for s in shape:
+                n *= s
+            self.offsets[key] = (off, tuple(shape))
+            off += _align(n)
+        self.buffer = torch.zeros(off, device=device, dtype=bf16)
+        self.loaded = set()
+
+    def __contains__(self, key: str) -> bool:
+        return key in self.offsets
+
+    def __getitem__(self, key: str) -> torch.Tensor:
+        off, shape = self.offsets[key]
+        n = 1
+        for s in shape:
+            n *= s
+        return self.buffer[off:off + n].view(shape)
+
+    def nbytes(self) -> int:
+        return self.buffer.numel() * 2
+
+    def broadcast(self, src: int = 0) -> None:
+        """NCCL broadcast of the whole arena from `src` (north star: weights travel over NVLink once)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.buffer, src=src)
+
+
+class Flux:
+    """Drop-in for flux.model.Flux (flux/model.py:35-136) backed by sm_100a kernels."""
+
+    def __init__(self, params: FluxParams, device: Optional[str] = None):
+        params.validate()  # same ValueErrors as flux/model.py:42-50
+        self.params = params
+        self.in_channels = params.in_channels
+        self.out_channels = self.in_channels
+        self.hidden_size = params.hidden_size
+        self.num_heads = params.num_heads
+        if self.hidden_size // self.num_heads != 128:
+            raise ValueError("the B200 attention kernel is specialised for head_dim 128")
+        if list(params.axes_dim) != [16, 56, 56] and sum(params.axes_dim) != 128:
+            raise ValueError(f"Got {params.axes_dim} but expected positional dim 128")
+        self.device = torch.device(device or "cuda")
+        self._manifest = flow_manifest(params)
+        D = self.hidden_size
+        # arena layout: all modulation Linears first and contiguous (-> one GEMV), then everything else
+        self._mod_keys: List[str] = []
+        for i in range(params.depth):
+            self._mod_keys += [f"double_blocks.{i}.img_mod.lin", f"double_blocks.{i}.txt_mod.lin"]
+        for i in range(params.depth_single_blocks):
+            self._mod_keys.append(f"single_blocks.{i}.modulation.lin")
+        self._mod_keys.append("final_layer.adaLN_modulation.1")
+        shapes = {k: s for k, s, _ in self._manifest}
+        self._mod_off: Dict[str, int] = {}
+        tot = 0
+        for k in self._mod_keys:
+            self._mod_off[k] = tot
+            tot += shapes[k + ".weight"][0]
+        self._mod_total = tot
+        entries = [("__mod_w", (tot, D)), ("__mod_b", (tot,))]
+        entries += [(k, s) for k, s, _ in self._manifest if not any(k.startswith(m + ".") for m in self._mod_keys)]
+        self.arena = WeightArena(entries, self.device)
+        self._ws: Dict[Tuple[int, int, int], dict] = {}
+        self._pe_cache: Dict[tuple, torch.Tensor] = {}
+        self._txt_cache: Optional[tuple] = None
+
+    # ------------------------------------------------------------------ weights
+    def sanitize(self, weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Key clean-up of BFL checkpoints (flux/model.py:85-97).  The reference additionally renames
+        `.scale` -> `.weight` and inserts `.layers.` for its nn.Sequential containers; this class
+        keeps the checkpoint-side names, so only the optional prefix is stripped."""
+        out = {}
+        for k, w in weights.items():
+            if k.startswith("model.diffusion_model."):
+                k = k[22:]
+            out[k] = w
+        return out
+
+    def _dest(self, key: str) -> Optional[torch.Tensor]:
+        for m in self._mod_keys:
+            if key.startswith(m + "."):
+                off = self._mod_off[m]
+                n = self._shape(key)[0]
+                return self.arena["__mod_w"][off:off + n] if key.endswith(".weight") else self.arena["__mod_b"][off:off + n]
+        return self.arena[key] if key in self.arena else None
+
+    def _shape(self, key: str) -> Tuple[int, ...]:
+        if not hasattr(self, "_shapes"):
+            self._shapes = {k: s for k, s, _ in self._manifest}
+        return self._shapes[key]
+
+    def load_weights(self, weights, strict: bool = True) -> "Flux":
+        items = list(weights.items()) if isinstance(weights, dict) else list(weights)
+        for key, w in items:
+            if key not in self._shapes_dict():
+                if strict:
+                    raise ValueError(f"Received parameters not in model: {key}")
+                continue
+            if tuple(w.shape) != self._shape(key):
+                raise ValueError(f"Expected shape {self._shape(key)} but received shape {tuple(w.shape)} for parameter {key}")
+            self._dest(key).copy_(w.to(device=self.device, dtype=bf16))
+            self.arena.loaded.add(key)
+        if strict:
+            missing = [k for k in self._shapes_dict() if k not in self.arena.loaded]
+            if missing:
+                raise ValueError(f"Missing {len(missing)} parameters, e.g. {missing[:3]}")
+        self._txt_cache = None
+        return self
+
+    def _shapes_dict(self):
+        self._shape(self._manifest[0][0])
+        return self._shapes
+
+    def parameters(self):
+        return {"arena": self.arena.buffer}
+
+    # ------------------------------------------------------------------ helpers
+    def _w(self, key: str) -> torch.Tensor:
+        return self.arena[key + ".weight"]
+
+    def _b(self, key: str) -> Optional[torch.Tensor]:
+        k = key + ".bias"
+        return self.arena[k] if k in self.arena else None
+
+    def _mod(self, ws: dict, key: str, idx: int) -> torch.Tensor:
+        """chunk `idx` (shift, scale, gate[, shift2, scale2, gate2]) of modulation `key`: [B, D] view."""
+        D = self.hidden_size
+        off = self._mod_off[key] + idx * D
+        return ws["mod"][:, off:off + D]
+
+    def _workspace(self, B: int, L: int, S: int) -> dict:
+        key = (B, L, S)
+        ws = self._ws.get(key)
+        if ws is None:
+            D, H, M = self.hidden_size, self.num_heads, self.params.mlp_hidden
+            N = S + L
+            dev = self.device
+            e = lambda *s: torch.empty(s, device=dev, dtype=bf16)  # noqa: E731
+            ws = dict(x=e(B, N, D), xm=e(B, N, D), q=e(B, H, N, 128), k=e(B, H, N, 128), v=e(B, H, N, 128),
+                      cat=e(B, N, D + M), mod=e(B, self._mod_total), vec=e(B, D), h=e(B, D), h2=e(B, D),
+                      pred=e(B, L, self.in_channels))
+            self._ws = {key: ws}  # keep one shape resident
+        return ws
+
+    @staticmethod
+    def rope_table(ids: torch.Tensor, axes_dim, theta) -> torch.Tensor:
+        """EmbedND / _rope (flux/layers.py:12-21,60-75) for one batch row of position ids [N, 3] ->
+        [N, 64, 2] (cos, sin) rounded to bf16 (the reference casts `pe` to bf16, flux/model.py:124).
+        Host-side torch math identical to the reference's formula; computed once per (S, h, w)."""
+        ids = ids.to("cpu")
+        cs = []
+        for i, d in enumerate(axes_dim):
+            scale = torch.arange(0, d, 2, dtype=torch.float32) / d
+            omega = 1.0 / (theta ** scale)
+            ang = ids[:, i:i + 1].to(torch.float32) * omega
+            cs.append(torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1))
+        return torch.cat(cs, dim=1).to(bf16).contiguous()
+
+    def _pe(self, txt_ids: torch.Tensor, img_ids: torch.Tensor) -> torch.Tensor:
+        key = (txt_ids.data_ptr(), img_ids.data_ptr(), tuple(txt_ids.shape), tuple(img_ids.shape))
+        pe = self._pe_cache.get(key)
+        if pe is None:
+            ids = torch.cat([txt_ids[0].to("cpu"), img_ids[0].to("cpu")], dim=0)
+            pe = self.rope_table(ids, self.params.axes_dim, self.params.theta).to(self.device)
+            self._pe_cache = {key: pe}
+            self._keep_ids = (txt_ids, img_ids)  # pin the tensors whose addresses key the cache
+        return pe
+
+    def _txt_in(self, txt: torch.Tensor) -> torch.Tensor:
+        """txt_in(txt) is step-invariant (flux/model.py:121 recomputes it every step): cached per tensor."""
+        key = (txt.data_ptr(), txt._version, tuple(txt.shape))
+        if self._txt_cache is None or self._txt_cache[0] != key:
+            out = ops.gemm(txt, self._w("txt_in"), self._b("txt_in"))
+            self._txt_cache = (key, out, txt)
+        return self._txt_cache[1]
+
+    # ------------------------------------------------------------------ forward
+    def __call__(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
+                 timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if img.ndim != 3 or txt.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        p = self.params
+        if p.guidance_embed and guidance is None:
+            raise ValueError("Didn't get guidance strength for guidance distilled model.")
+        B, L, _ = img.shape
+        S = txt.shape[1]
+        D, H, M = self.hidden_size, self.num_heads, p.mlp_hidden
+        ws = self._workspace(B, L, S)
+        x, xm, q, k, v, cat = ws["x"], ws["xm"], ws["q"], ws["k"], ws["v"], ws["cat"]
+        img = img.to(bf16) if img.dtype != bf16 else img
+        txt = txt.to(bf16) if txt.dtype != bf16 else txt
+        y = (y.to(bf16) if y.dtype != bf16 else y).contiguous()
+        timesteps = timesteps.to(bf16) if timesteps.dtype != bf16 else timesteps
+
+        # ---- conditioning vector (flux/model.py:113-120) and every block's modulation in one GEMV
+        temb = ops.timestep_embedding(timesteps, 256)
+        ops.gemv(temb, self._w("time_in.in_layer"), self._b("time_in.in_layer"), out=ws["h"])
+        ops.gemv(ws["h"], self._w("time_in.out_layer"), self._b("time_in.out_layer"), silu_in=True, out=ws["vec"])
+        if p.guidance_embed:
+            gemb = ops.timestep_embedding(guidance.to(bf16), 256)
+            ops.gemv(gemb, self._w("guidance_in.in_layer"), self._b("guidance_in.in_layer"), out=ws["h"])
+            ops.gemv(ws["h"], self._w("guidance_in.out_layer"), self._b("guidance_in.out_layer"), silu_in=True,
+                     add=ws["vec"], out=ws["h2"])
+            ws["vec"], ws["h2"] = ws["h2"], ws["vec"]
+        ops.gemv(y, self._w("vector_in.in_layer"), self._b("vector_in.in_layer"), out=ws["h"])
+        ops.gemv(ws["h"], self._w("vector_in.out_layer"), self._b("vector_in.out_layer"), silu_in=True,
+                 add=ws["vec"], out=ws["h2"])
+        ws["vec"], ws["h2"] = ws["h2"], ws["vec"]
+        ops.gemv(ws["vec"], self.arena["__mod_w"], self.arena["__mod_b"], silu_in=True, out=ws["mod"])
+
+        # ---- embedders write straight into the joint buffer (text rows first)
+        x_txt, x_img = x[:, :S], x[:, S:]
+        ops.gemm(img, self._w("img_in"), self._b("img_in"), out=x_img)
+        x_txt.copy_(self._txt_in(txt))
+        pe = self._pe(txt_ids, img_ids)
+        scale = 128 ** -0.5
+
+        for i in range(p.depth):
+            pre = f"double_blocks.{i}."
+            streams = (("img", x_img, xm[:, S:], cat[:, S:], S), ("txt", x_txt, xm[:, :S], cat[:, :S], 0))
+            for name, xs, xms, _, off in streams:
+                mk = pre + name + "_mod.lin"
+                ops.rownorm(xs, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xms)
+                ak = pre + name + "_attn."
+                ops.gemm_qkv(xms, self._w(ak + "qkv"), self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
+                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS)
+            ops.attention(q, k, v, cat[:, :, :D], scale)
+            for name, xs, xms, cs, off in streams:
+                mk = pre + name + "_mod.lin"
+                ak = pre + name + "_attn."
+                mlp = pre + name + "_mlp."
+                ops.gemm(cs[:, :, :D], self._w(ak + "proj"), self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xs, out=xs)
+                ops.rownorm(xs, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xms)
+                ops.gemm(xms, self._w(mlp + "0"), self._b(mlp + "0"), act="gelu_tanh", out=cs[:, :, D:])
+                ops.gemm(cs[:, :, D:], self._w(mlp + "2"), self._b(mlp + "2"), gate=self._mod(ws, mk, 5), resid=xs, out=xs)
+
+        for i in range(p.depth_single_blocks):
+            pre = f"single_blocks.{i}."
+            mk = pre + "modulation.lin"
+            ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
+            ops.gemm_qkv(xm, self._w(pre + "linear1"), self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
+                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS)
+            ops.attention(q, k, v, cat[:, :, :D], scale)
+            ops.gemm(cat, self._w(pre + "linear2"), self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x)
+
+        # ---- LastLayer (flux/layers.py:298-302): chunks are (shift, scale)
+        mk = "final_layer.adaLN_modulation.1"
+        ops.rownorm(x_img, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, S:])
+        ops.gemm(xm[:, S:], self._w("final_layer.linear"), self._b("final_layer.linear"), out=ws["pred"])
+        return ws["pred"]
