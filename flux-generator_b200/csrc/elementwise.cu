@@ -32,7 +32,7 @@ struct RowNormParams {
   float eps; int mode, batch, rows, D;
 };
 
-template <int ITERS>  // D = ITERS * 256
+template <int ITERS>  // ITERS = ceil(D / 256); D % 8 == 0
 __global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -42,7 +42,14 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
   const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
   float v[ITERS * 8];
 #pragma unroll
-  for (int i = 0; i < ITERS; ++i) load8(xr + i * 256 + lane * 8, v + i * 8);
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 256 + lane * 8;
+    if (c < p.D) load8(xr + c, v + i * 8);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i * 8 + j] = 0.f;
+    }
+  }
   float mean = 0.f;
   if (p.mode != 2) {
     float s = 0.f;
@@ -52,9 +59,14 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
   }
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < ITERS * 8; ++i) {
-    const float d = v[i] - mean;
-    ss += d * d;
+  for (int i = 0; i < ITERS; ++i) {
+    if (i * 256 + lane * 8 < p.D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i * 8 + j] - mean;
+        ss += d * d;
+      }
+    }
   }
   const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
   const long long pb = (p.mode == 0) ? b * p.p_bs : 0;
@@ -62,6 +74,7 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int c = i * 256 + lane * 8;
+    if (c >= p.D) continue;
     float a[8], s[8], o[8];
     load8(p.p0 + pb + c, a);
     if (p.mode != 2) load8(p.p1 + pb + c, s);
@@ -393,7 +406,7 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->x && a->out && a->p0, "fx_rownorm: null pointer");
   FX_REQUIRE(a->mode >= 0 && a->mode <= 2, "fx_rownorm: bad mode %d", a->mode);
   FX_REQUIRE(a->mode == 2 || a->p1, "fx_rownorm: p1 required for mode %d", a->mode);
-  FX_REQUIRE(a->D % 256 == 0 && a->D >= 256 && a->D <= 4096, "fx_rownorm: D (%d) must be a multiple of 256 in [256, 4096]", a->D);
+  FX_REQUIRE(a->D % 8 == 0 && a->D >= 8 && a->D <= 4096, "fx_rownorm: D (%d) must be a multiple of 8 in [8, 4096]", a->D);
   FX_REQUIRE(a->ldx % 8 == 0 && a->ldo % 8 == 0 && a->x_bs % 8 == 0 && a->out_bs % 8 == 0 && a->p_bs % 8 == 0,
              "fx_rownorm: strides must be multiples of 8 elements");
   if (a->batch <= 0 || a->rows <= 0) return FX_OK;
@@ -402,7 +415,7 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
   const long long rows = (long long)a->batch * a->rows;
   const int blocks = int((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (a->D / 256) {
+  switch ((a->D + 255) / 256) {
 #define FX_RN(I) case I: rownorm_kernel<I><<<blocks, 256, 0, st>>>(p); break;
     FX_RN(1) FX_RN(2) FX_RN(3) FX_RN(4) FX_RN(5) FX_RN(6) FX_RN(7) FX_RN(8)
     FX_RN(9) FX_RN(10) FX_RN(11) FX_RN(12) FX_RN(13) FX_RN(14) FX_RN(15) FX_RN(16)

@@ -1,0 +1,158 @@
+"""FluxPipeline on B200 (reference: flux/flux.py:22-193).
+
+Same constructor, attributes and generator protocol as the reference: ``generate_latents`` first
+yields the conditioning 5-tuple ``(x_T, x_ids, txt, txt_ids, vec)`` and then exactly ``num_steps``
+latents ``[B, L, 64]``; ``decode`` maps packed latents to ``[k, 8h, 8w, 3]`` floats in [0, 1].
+Tensors are torch CUDA tensors (bf16 latents, fp32 images); the callers' ``mx.eval(x)`` has no
+equivalent -- kernels are enqueued on the current CUDA stream.
+
+Differences that follow from the platform, not from choice:
+  * prior noise: MLX's threefry stream is not reproducible offline; noise is keyed by
+    (seed, global image index) so sharding a batch over G GPUs never changes an image.  Pass
+    ``x_T=`` to supply the prior explicitly (parity tests do).
+  * T5 / CLIP outputs are cached per prompt (north star: "run once per prompt and cached").
+  * training_loss / LoRA methods are out of scope for this round and raise.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .sampler import FluxSampler
+from .utils import (load_ae, load_clip, load_clip_tokenizer, load_flow_model, load_t5, load_t5_tokenizer)
+
+bf16 = torch.bfloat16
+
+
+class FluxPipeline:
+    def __init__(self, name: str, t5_padding: bool = True, synthetic: Optional[bool] = None,
+                 device: Optional[str] = None, flow_params=None, ae_params=None, t5_config=None, clip_config=None,
+                 first_image_index: int = 0):
+        self.dtype = bf16
+        self.name = name
+        self.t5_padding = t5_padding
+        self.device = torch.device(device or "cuda")
+        self._synthetic = synthetic
+        self._t5_config, self._clip_config = t5_config, clip_config
+        self.first_image_index = first_image_index  # global index of this rank's first image (batch sharding)
+
+        kw = dict(synthetic=synthetic, device=device)
+        self.ae = load_ae(name, params=ae_params, **kw)
+        self.flow = load_flow_model(name, params=flow_params, **kw)
+        self.clip = load_clip(name, config=clip_config, **kw)
+        self.clip_tokenizer = load_clip_tokenizer(name, synthetic=synthetic,
+                                                  vocab_size=self.clip.config.vocab_size)
+        self.t5 = load_t5(name, config=t5_config, **kw)
+        self.t5_tokenizer = load_t5_tokenizer(name, synthetic=synthetic,
+                                              vocab_size=min(self.t5.config.vocab_size, 32100))
+        self.sampler = FluxSampler(name)
+        self._cond_cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def ensure_models_are_loaded(self):
+        torch.cuda.synchronize(self.device)
+
+    def reload_text_encoders(self):
+        kw = dict(synthetic=self._synthetic, device=str(self.device))
+        self.t5 = load_t5(self.name, config=self._t5_config, **kw)
+        self.clip = load_clip(self.name, config=self._clip_config, **kw)
+
+    def tokenize(self, text):
+        t5_tokens = self.t5_tokenizer.encode(text, pad=self.t5_padding)
+        clip_tokens = self.clip_tokenizer.encode(text)
+        return t5_tokens, clip_tokens
+
+    # ------------------------------------------------------------------ flux/flux.py:53-85
+    def _prepare_latent_images(self, x: torch.Tensor):
+        b, h, w, c = x.shape
+        packed = ops.patchify(x.to(device=self.device, dtype=bf16))
+        i = torch.zeros((h // 2, w // 2), dtype=torch.int32)
+        j, k = torch.meshgrid(torch.arange(h // 2, dtype=torch.int32), torch.arange(w // 2, dtype=torch.int32),
+                              indexing="ij")
+        x_ids = torch.stack([i, j, k], dim=-1).reshape(1, h * w // 4, 3).repeat(b, 1, 1).to(self.device)
+        return packed, x_ids
+
+    def _prepare_conditioning(self, n_images, t5_tokens, clip_tokens):
+        key = (tuple(t5_tokens.flatten().tolist()), tuple(clip_tokens.flatten().tolist()))
+        hit = self._cond_cache.get(key)
+        if hit is None:
+            if not hasattr(self, "t5") or not hasattr(self, "clip"):
+                raise RuntimeError("text encoders were deleted; call reload_text_encoders()")
+            txt1 = self.t5(t5_tokens)
+            vec1 = self.clip(clip_tokens).pooled_output
+            hit = (txt1, vec1)
+            self._cond_cache[key] = hit
+        txt, vec = hit
+        if len(txt) == 1 and n_images > 1:
+            txt = txt.expand(n_images, *txt.shape[1:]).contiguous()
+        txt_ids = torch.zeros((n_images, txt.shape[1], 3), dtype=torch.int32, device=self.device)
+        if len(vec) == 1 and n_images > 1:
+            vec = vec.expand(n_images, *vec.shape[1:]).contiguous()
+        return txt, txt_ids, vec
+
+    # ------------------------------------------------------------------ flux/flux.py:87-126
+    def _denoising_loop(self, x_t, x_ids, txt, txt_ids, vec, num_steps: int = 35, guidance: float = 4.0,
+                        start: float = 1, stop: float = 0):
+        B = len(x_t)
+
+        def scalar(x):
+            return torch.full((B,), x, dtype=self.dtype, device=self.device)
+
+        guidance = scalar(guidance)
+        timesteps = self.sampler.timesteps(num_steps, x_t.shape[1], start=start, stop=stop)
+        x_t = x_t.clone()
+        for i in range(num_steps):
+            t = timesteps[i]
+            t_prev = timesteps[i + 1]
+            pred = self.flow.forward(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec,
+                                     timesteps=scalar(t), guidance=guidance)
+            x_t = ops.euler_step(x_t.clone(), pred, t_prev - t)  # sampler.step (flux/sampler.py:56-57)
+            yield x_t
+
+    def generate_latents(self, text: str, n_images: int = 1, num_steps: int = 35, guidance: float = 4.0,
+                         latent_size: Tuple[int, int] = (64, 64), seed=None, x_T: Optional[torch.Tensor] = None):
+        if x_T is None:
+            x_T = self.sampler.sample_prior((n_images, *latent_size, 16), dtype=self.dtype,
+                                            key=0 if seed is None else seed, first_index=self.first_image_index)
+        x_T, x_ids = self._prepare_latent_images(x_T)
+        t5_tokens, clip_tokens = self.tokenize(text)
+        txt, txt_ids, vec = self._prepare_conditioning(n_images, t5_tokens, clip_tokens)
+        yield (x_T, x_ids, txt, txt_ids, vec)
+        yield from self._denoising_loop(x_T, x_ids, txt, txt_ids, vec, num_steps=num_steps, guidance=guidance)
+
+    def decode(self, x: torch.Tensor, latent_size: Tuple[int, int] = (64, 64)) -> torch.Tensor:
+        """flux/flux.py:157-162 -> float32 [k, 8h, 8w, 3] in [0, 1]."""
+        img, _ = self.ae.decode_packed(x, latent_size, want_u8=False)
+        return img
+
+    def decode_uint8(self, x: torch.Tensor, latent_size: Tuple[int, int] = (64, 64)) -> torch.Tensor:
+        """decode + the CLI's truncating `(x * 255).astype(uint8)` (txt2image.py:133) in one pass."""
+        _, u8 = self.ae.decode_packed(x, latent_size, want_u8=True)
+        return u8
+
+    def generate_images(self, text: str, n_images: int = 1, num_steps: int = 35, guidance: float = 4.0,
+                        latent_size: Tuple[int, int] = (64, 64), seed=None, reload_text_encoders: bool = True,
+                        progress: bool = True, x_T: Optional[torch.Tensor] = None, decoding_batch_size: int = 1):
+        """flux/flux.py:164-193.  `reload_text_encoders` is accepted for signature parity; the encoders
+        are never deleted here, so there is nothing to reload."""
+        from tqdm import tqdm
+        latents = self.generate_latents(text, n_images, num_steps, guidance, latent_size, seed, x_T=x_T)
+        next(latents)
+        x_t = None
+        for x_t in tqdm(latents, total=num_steps, disable=not progress, leave=True):
+            pass
+        images = []
+        for i in tqdm(range(0, len(x_t), decoding_batch_size), disable=not progress, desc="generate images"):
+            images.append(self.decode(x_t[i:i + decoding_batch_size], latent_size))
+        return torch.cat(images, dim=0)
+
+    # ------------------------------------------------------------------ out of scope this round
+    def training_loss(self, *a, **k):
+        raise NotImplementedError("training is outside the B200 hot path (SURVEY 8-f N4)")
+
+    def linear_to_lora_layers(self, *a, **k):
+        raise NotImplementedError("LoRA is outside the B200 hot path (SURVEY 8-f N4)")
+
+    def fuse_lora_layers(self, *a, **k):
+        raise NotImplementedError("LoRA is outside the B200 hot path (SURVEY 8-f N4)")

@@ -216,8 +216,9 @@ class Flux:
         return self._txt_cache[1]
 
     # ------------------------------------------------------------------ forward
-    def __call__(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
-                 timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
+                timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call)."""
         if img.ndim != 3 or txt.ndim != 3:
             raise ValueError("Input img and txt tensors must have 3 dimensions.")
         p = self.params
@@ -289,3 +290,7 @@ class Flux:
         ops.rownorm(x_img, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, S:])
         ops.gemm(xm[:, S:], self._w("final_layer.linear"), self._b("final_layer.linear"), out=ws["pred"])
         return ws["pred"]
+
+    def __call__(self, img, img_ids, txt, txt_ids, timesteps, y, guidance=None) -> torch.Tensor:
+        """Flux.__call__ (flux/model.py:99-136): returns a fresh [B, L, in_channels] bf16 tensor."""
+        return self.forward(img, img_ids, txt, txt_ids, timesteps, y, guidance).clone()
