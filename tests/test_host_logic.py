@@ -1,0 +1,172 @@
+"""CPU: host-side logic of the drop-in surface -- schedule, CLI parsing and rounding, tokenizers,
+manifests, batch sharding (incl. a world_size-2 gloo run), and that the C-ABI library loads and
+exports every symbol include/flux_b200.h declares (no compute calls without a GPU)."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "flux-generator_b200"))
+
+import txt2image  # noqa: E402
+from flux import FluxSampler, _native, specs, synthetic  # noqa: E402
+from flux.tokenizers import CLIPTokenizer, SyntheticTokenizer  # noqa: E402
+from helpers import golden  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "flux_b200.h")).read()
+    declared = set(re.findall(r"\b(fx_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _native.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in flux_b200.h but not exported"
+    assert declared == set(_native.SYMBOLS), "ctypes table and header disagree"
+    assert lib.fx_version() >= 100
+    # host-only argument validation works without a GPU and reports through fx_last_error
+    import ctypes as C
+    rc = lib.fx_gemm(C.byref(_native.GemmArgs()), None)
+    assert rc == -1 and b"null" in lib.fx_last_error()
+
+
+def test_product_path_has_no_cpu_fallback():
+    from flux import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            _native.lib()
+    # the product package never imports the oracle
+    pkg = os.path.join(ROOT, "flux-generator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_sampler_schedule_bit_exact_vs_reference_fixture():
+    g = golden("schedule.npz")
+    for key in g.files:
+        name, steps, L = key.split("_")
+        got = FluxSampler("flux-" + name).timesteps(int(steps), int(L))
+        assert np.array_equal(np.asarray(got, dtype=np.float64), g[key]), key
+    s = FluxSampler("flux-schnell")
+    assert s.timesteps(4, 4096) == [1.0, 0.75, 0.5, 0.25, 0.0]
+    # what the model sees: bf16(1000 * bf16(t)) -> 1000, 752, 500, 250
+    seen = [float((1000.0 * torch.tensor(t, dtype=torch.bfloat16))) for t in s.timesteps(4, 4096)[:4]]
+    assert seen == [1000.0, 752.0, 500.0, 250.0]
+
+
+def test_cli_surface():
+    # reference cases (test/test_generation.py:156-164: the two consistent ones) + round-up rule
+    g = golden("patchify.npz")
+    for size, lat in zip(g["sizes"], g["latent_sizes"]):
+        assert txt2image.to_latent_size(tuple(int(v) for v in size)) == tuple(int(v) for v in lat)
+    assert txt2image.to_latent_size((512, 512)) == (64, 64)
+    assert txt2image.to_latent_size((768, 512)) == (96, 64)
+    a = txt2image.parse_args(["a cat"])
+    assert (a.model, a.n_images, a.image_size, a.steps, a.guidance, a.n_rows, a.decoding_batch_size, a.output,
+            a.t5_padding) == ("schnell", 4, (512, 512), 2, 4.0, 1, 1, "out.png", True)
+    assert txt2image.parse_args(["x", "--model", "dev"]).steps == 50
+    assert txt2image.parse_args(["x", "--image-size", "1024x768"]).image_size == (1024, 768)  # height first
+    assert txt2image.parse_args(["x", "--no-t5-padding"]).t5_padding is False
+    with pytest.raises(SystemExit):
+        txt2image.parse_args(["x", "--steps", "0"])
+
+
+def test_clip_tokenizer_semantics():
+    # tiny vocabulary exercising lower-casing, whitespace collapse, BPE merges, BOS/EOS, truncation
+    vocab = {"<|startoftext|>": 0, "<|endoftext|>": 1, "a</w>": 2, "c": 3, "a": 4, "t</w>": 5, "ca": 6, "cat</w>": 7,
+             "!</w>": 8, "t": 9}
+    merges = [("c", "a"), ("ca", "t</w>")]
+    tok = CLIPTokenizer({m: i for i, m in enumerate(merges)}, vocab, max_length=6)
+    assert tok.tokenize("A   CAT!") == [0, 2, 7, 8, 1]
+    assert tok.encode("a cat").tolist() == [[0, 2, 7, 1]]                      # single prompt: not padded
+    assert tok.encode(["a", "a cat !"]).tolist() == [[0, 2, 1, 1, 1], [0, 2, 7, 8, 1]]   # batch pads with EOS
+    assert tok.tokenize("a a a a a a a a") == [0, 2, 2, 2, 2, 1]               # truncated to 6, EOS kept last
+    assert tok.encode("a").dtype == torch.int32
+
+
+def test_synthetic_tokenizers_shape_like_the_real_ones():
+    t5 = SyntheticTokenizer("t5", 256, 32100).encode("a photo of a cat")
+    assert t5.shape == (1, 256) and t5.dtype == torch.int32
+    n = int((t5[0] != 0).sum())
+    assert t5[0, n - 1] == 1 and (t5[0, n:] == 0).all()                        # EOS then pad id 0
+    assert SyntheticTokenizer("t5", 256, 32100).encode("a photo of a cat", pad=False).shape[1] == n
+    cl = SyntheticTokenizer("clip", 77, 49408).encode("a photo of a cat")
+    assert cl[0, 0] == 49406 and cl[0, -1] == 49407 and cl.shape[1] <= 77
+    assert int(cl[0].argmax()) == cl.shape[1] - 1                              # first EOS = pooled position
+    assert torch.equal(t5, SyntheticTokenizer("t5", 256, 32100).encode("a photo of a cat"))  # deterministic
+
+
+def test_manifests_match_the_reference_tensor_inventory():
+    p = specs.FluxParams(guidance_embed=True)
+    m = specs.flow_manifest(p)
+    n = sum(int(np.prod(s)) for _, s, _ in m)
+    assert abs(n / 1e9 - 11.90) < 0.01                                        # 11.90 B parameters
+    keys = {k for k, _, _ in m}
+    assert "double_blocks.18.txt_attn.norm.key_norm.scale" in keys and "single_blocks.37.linear2.weight" in keys
+    assert "guidance_in.in_layer.weight" in keys
+    assert "guidance_in.in_layer.weight" not in {k for k, _, _ in specs.flow_manifest(specs.FluxParams())}
+    ae = specs.ae_decoder_manifest(specs.AutoEncoderParams())
+    assert abs(sum(int(np.prod(s)) for _, s, _ in ae) / 1e6 - 49.5) < 0.1     # 49.5 M decoder parameters
+    assert dict((k, s) for k, s, _ in ae)["decoder.up.1.block.0.nin_shortcut.weight"] == (256, 512, 1, 1)
+    t5 = specs.t5_manifest(specs.T5Config())
+    assert abs(sum(int(np.prod(s)) for _, s, _ in t5) / 1e9 - 4.76) < 0.01
+    with pytest.raises(ValueError, match="divisible"):
+        specs.FluxParams(num_heads=7).validate()
+    with pytest.raises(ValueError, match="positional dim"):
+        specs.FluxParams(axes_dim=[16, 56, 48]).validate()
+
+
+def test_synthetic_prior_is_independent_of_sharding():
+    full = synthetic.synthetic_prior(8, (4, 4), seed=42)
+    lo, hi = txt2image.shard(8, 1, 2)
+    assert (lo, hi) == (4, 8)
+    assert torch.equal(synthetic.synthetic_prior(hi - lo, (4, 4), seed=42, first_index=lo), full[lo:hi])
+    assert [txt2image.shard(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert txt2image.shard(2, 3, 4) == (2, 2)                                  # more ranks than images: empty shard
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(sys.argv[1], "flux-generator_b200"))
+import txt2image
+from flux.synthetic import synthetic_prior
+from flux.model import WeightArena
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+# weight broadcast at load: rank 0 fills the arena, everyone ends up with the same bytes
+arena = WeightArena([("a.weight", (5, 8)), ("b.bias", (8,))], "cpu")
+if r == 0:
+    arena["a.weight"].copy_(torch.arange(40).reshape(5, 8)); arena["b.bias"].fill_(3)
+arena.broadcast(0)
+assert arena["a.weight"].float().sum().item() == 780 and arena["b.bias"].float().sum().item() == 24
+# batch sharding: the union of the ranks' priors equals the unsharded prior
+lo, hi = txt2image.shard(5, r, w)
+mine = synthetic_prior(hi - lo, (4, 4), seed=1, first_index=lo)
+parts = [None] * w
+dist.all_gather_object(parts, mine)
+assert torch.equal(torch.cat(parts), synthetic_prior(5, (4, 4), seed=1))
+# max-over-ranks timing reduction used by bench.py
+t = torch.tensor([float(r + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX); assert t.item() == w
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_two_rank_gloo_sharding_and_broadcast(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok 0" in r.stdout and "ok 1" in r.stdout
