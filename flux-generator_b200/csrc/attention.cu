@@ -29,6 +29,36 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the softmax inner loop
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(uint64_t v) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <bool P_TMEM>
 struct AttnCfg {
@@ -89,6 +119,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   const uint32_t tmem = *tmem_slot;
   // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases S_i[0,64)
 
+  // warpgroup 0 (TMA / MMA / 2 idle warps) gives registers to the two softmax warpgroups
+  if (warp < 4) {
+  reg_dec<88>();
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: Q (both tiles), then K0 V0 K1 V1 ...
@@ -183,8 +216,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       tc_commit(&o_full[0]);
       tc_commit(&o_full[1]);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ---------------- softmax / correction / epilogue warpgroups
+    reg_inc<208>();
     const int i = (warp - 4) >> 2;   // query tile 0/1
     const int quarter = warp & 3;    // TMEM lane quarter
     const int r = quarter * 32 + lane;
@@ -196,24 +231,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
 
+    const uint64_t sl2_2 = pack2(sl2, sl2);
     for (int j = 0; j < T; ++j) {
       const int kv_valid = min(128, p.seq - j * 128);
       mbar_wait(&s_full[i], j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_x32(s_addr + c * 32, v);
-        tmem_ld_wait();
+      // the whole S row (128 fp32) lives in registers: one TMEM read per tile
+      uint32_t sv[128];
+      __syncwarp();
+      tmem_ld_x32(s_addr, sv);
+      tmem_ld_x32(s_addr + 32, sv + 32);
+      tmem_ld_x32(s_addr + 64, sv + 64);
+      tmem_ld_x32(s_addr + 96, sv + 96);
+      tmem_ld_wait();
+      if (kv_valid < 128) {  // ragged last tile: keys beyond seq do not exist
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float s = (c * 32 + e < kv_valid) ? __uint_as_float(v[e]) : -INFINITY;
-          mx = fmaxf(mx, s);
-        }
+        for (int e = 0; e < 128; ++e)
+          if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
       }
+      float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+#pragma unroll
+      for (int e = 2; e < 128; e += 2) mx = fmax3(mx, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
       const float m_new = fmaxf(m_run, mx * sl2);
       const bool need = (m_new - m_run) > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -236,21 +274,17 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           tmem_st_wait();
         }
       }
-      // pass 2: probabilities
-#pragma unroll 1
+      // probabilities: p = exp2(s * scale_log2 - m_run), packed two at a time
+      const uint64_t nm2 = pack2(-m_run, -m_run);
+      uint64_t lsum2 = pack2(0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld_x32(s_addr + c * 32, v);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float s0 = (c * 32 + e < kv_valid) ? __uint_as_float(v[e]) : -INFINITY;
-          const float s1 = (c * 32 + e + 1 < kv_valid) ? __uint_as_float(v[e + 1]) : -INFINITY;
-          const float p0 = fast_exp2(s0 * sl2 - m_run);
-          const float p1 = fast_exp2(s1 * sl2 - m_run);
-          l_run += p0 + p1;
+          const float2 t = unpack2(ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2));
+          const float p0 = fast_exp2(t.x), p1 = fast_exp2(t.y);
+          lsum2 = fadd2(lsum2, pack2(p0, p1));
           pk[e >> 1] = pack_bf16(p0, p1);
         }
         if (P_TMEM) {
@@ -264,6 +298,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
           }
         }
+      }
+      {
+        const float2 ls = unpack2(lsum2);
+        l_run += ls.x + ls.y;
       }
       if (P_TMEM) {
         tmem_st_wait();

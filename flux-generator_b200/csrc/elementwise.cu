@@ -115,18 +115,29 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) acc[b] = 0.f;
     const __nv_bfloat16* wr = p.W + (long long)n * p.ldw;
-    for (int k = lane * 8; k < p.K; k += 256) {
-      float w[8];
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + k));
-      float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-      w[0] = a.x; w[1] = a.y; w[2] = bb.x; w[3] = bb.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y;
+    // 4 independent 16-byte weight loads in flight per lane (the kernel is a pure weight stream)
+    for (int k0 = lane * 8; k0 < p.K; k0 += 1024) {
+      uint4 u[4];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b < p.batch) {
-          float x[8];
-          load8(s_in + b * p.K + k, x);
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + i * 256;
+        u[i] = (k < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[b] += w[j] * x[j];
+      for (int i = 0; i < 4; ++i) {
+        const int k = k0 + i * 256;
+        if (k >= p.K) break;
+        float w[8];
+        float2 a = unpack_bf16(u[i].x), bb = unpack_bf16(u[i].y), c = unpack_bf16(u[i].z), d = unpack_bf16(u[i].w);
+        w[0] = a.x; w[1] = a.y; w[2] = bb.x; w[3] = bb.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b < p.batch) {
+            float x[8];
+            load8(s_in + b * p.K + k, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[b] += w[j] * x[j];
+          }
         }
       }
     }
@@ -246,17 +257,24 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
   }
 }
 
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* x, const double* sums,
+// (sum, sumsq) in double -> (mean, rstd) in float, once per (batch, group)
+__global__ void groupnorm_finalize_kernel(const double* sums, float2* stats, int n_groups, double n, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_groups) return;
+  const double mean = sums[2 * i] / n;
+  const double var = fmax(sums[2 * i + 1] / n - mean * mean, 0.0);
+  stats[i] = make_float2((float)mean, rsqrtf((float)var + eps));
+}
+
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* x, const float2* stats,
                                                               const __nv_bfloat16* weight, const __nv_bfloat16* bias,
-                                                              __nv_bfloat16* out, long long hw, int C, float eps,
-                                                              int do_silu) {
+                                                              __nv_bfloat16* out, long long hw, int C, int do_silu) {
   const int b = blockIdx.y;
   const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel vector index in image
   const long long nvec = hw * (C / 8);
   if (vec >= nvec) return;
   const int c0 = int(vec % (C / 8)) * 8;
   const int gs = C / 32;
-  const double n = (double)hw * gs;
   float v[8], w[8], bb[8], o[8];
   const long long off = (long long)b * hw * C + vec * 8;
   load8(x + off, v);
@@ -264,12 +282,8 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   load8(bias + c0, bb);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / gs;
-    const double su = sums[((long long)b * 32 + g) * 2], sq = sums[((long long)b * 32 + g) * 2 + 1];
-    const double mean = su / n;
-    const double var = fmax(sq / n - mean * mean, 0.0);
-    const float rstd = rsqrtf((float)var + eps);
-    float y = (v[j] - (float)mean) * rstd * w[j] + bb[j];
+    const float2 st = __ldg(&stats[b * 32 + (c0 + j) / gs]);
+    float y = (v[j] - st.x) * st.y * w[j] + bb[j];
     if (do_silu) y = silu(__bfloat162float(__float2bfloat16(y)));
     o[j] = y;
   }
@@ -492,13 +506,21 @@ extern "C" int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, in
   return launched("groupnorm_stats_kernel");
 }
 
-extern "C" int fx_groupnorm_apply(const void* x, const double* sums, const void* weight, const void* bias, void* out,
-                                  int32_t batch, int64_t hw, int32_t C, float eps, int32_t do_silu, fx_stream stream) {
-  FX_REQUIRE(x && sums && weight && bias && out && batch > 0 && hw > 0 && C % 32 == 0 && C % 8 == 0, "fx_groupnorm_apply: bad arguments");
+extern "C" int fx_groupnorm_finalize(const double* sums, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
+                                     fx_stream stream) {
+  FX_REQUIRE(sums && stats && batch > 0 && hw > 0 && C % 32 == 0, "fx_groupnorm_finalize: bad arguments");
+  const int n = batch * 32;
+  groupnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, (float2*)stats, n, (double)hw * (C / 32), eps);
+  return launched("groupnorm_finalize_kernel");
+}
+
+extern "C" int fx_groupnorm_apply(const void* x, const float* stats, const void* weight, const void* bias, void* out,
+                                  int32_t batch, int64_t hw, int32_t C, int32_t do_silu, fx_stream stream) {
+  FX_REQUIRE(x && stats && weight && bias && out && batch > 0 && hw > 0 && C % 32 == 0 && C % 8 == 0, "fx_groupnorm_apply: bad arguments");
   const long long nvec = hw * (C / 8);
   dim3 grid((unsigned)((nvec + 255) / 256), batch);
-  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sums, (const __nv_bfloat16*)weight,
-                                                              (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, hw, C, eps, do_silu);
+  groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float2*)stats, (const __nv_bfloat16*)weight,
+                                                              (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, hw, C, do_silu);
   return launched("groupnorm_apply_kernel");
 }
 

@@ -2,8 +2,8 @@
 //   A  [batch][rows][K]   bf16, K contiguous (activations; or NHWC image read through a 4-D TMA box
 //                         for the 3x3 convolution mode -- implicit GEMM, no im2col buffer)
 //   W  [N][K]             bf16, K contiguous (nn.Linear layout / OHWI conv weights flattened)
-// One CTA per SM; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2..5 =
-// epilogue (TMEM -> registers -> global).  smem ring of 128B-swizzled K-major tiles filled by TMA;
+// One CTA per SM; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2..9 =
+// epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each owning half the columns).  smem ring of 128B-swizzled K-major tiles filled by TMA;
 // accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "sm100.cuh"
@@ -12,7 +12,7 @@ namespace fx {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 enum : int { EPI_GENERIC = 0, EPI_QKV = 1 };
 
@@ -137,7 +137,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
 }
 
 template <int BN, int EPI, bool CONV>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(200)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -162,7 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -239,7 +239,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else {
     // ================= epilogue warps =================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp owns
     const int r = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -267,8 +268,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const long long out_off = (long long)b * p.out_bs + row * p.ldo;
         const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
         const bool vec_ok = ((p.ldo | p.ldr | p.gate_bs) & 7) == 0;
+        constexpr int CH = BN / 64;  // 32-column chunks per warp
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * CH; c < (half + 1) * CH; ++c) {
           const int n0 = tn * BN + c * 32;
           if (n0 >= p.N) break;
           uint32_t v[32];
@@ -283,98 +285,82 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
         }
       } else {
-        // ---- QKV(+MLP) epilogue: 128-column groups
+        // ---- QKV(+MLP) epilogue: this warp owns one 128-column group; the whole group sits in registers
         const int D3 = 3 * p.heads * 128;
         const long long pos = (long long)p.seq_off + row;
-#pragma unroll 1
-        for (int hc = 0; hc < BN / 128; ++hc) {
-          const int g0 = tn * BN + hc * 128;
-          if (g0 >= p.N) break;
-          if (g0 >= D3) {
-            // mlp region -> gelu -> `out` at column (g0 - 3D)
-            const long long out_off = (long long)b * p.out_bs + pos * p.ldo - D3;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              __syncwarp();
-              tmem_ld_x32(taddr + hc * 128 + c * 32, v);
-              tmem_ld_wait();
-              if (valid) {
+        const int g0 = tn * BN + half * 128;
+        if (g0 < p.N) {
+          uint32_t v[128];
+          __syncwarp();
+          tmem_ld_x32(taddr + half * 128, v);
+          tmem_ld_x32(taddr + half * 128 + 32, v + 32);
+          tmem_ld_x32(taddr + half * 128 + 64, v + 64);
+          tmem_ld_x32(taddr + half * 128 + 96, v + 96);
+          tmem_ld_wait();
+          if (valid) {
+            if (g0 >= D3) {
+              // mlp region -> +bias, gelu -> `out` at column (g0 - 3D)
+              const long long out_off = (long long)b * p.out_bs + pos * p.ldo - D3;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
                 float f[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[c * 32 + i]);
                 epi_generic_chunk(p, f, b, out_off, 0, g0 + c * 32, true);
               }
-            }
-            continue;
-          }
-          const int hidx = g0 >> 7;
-          const int which = hidx / p.heads;  // 0 q, 1 k, 2 v
-          const int head = hidx - which * p.heads;
-          __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
-                               (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
-          float rr = 1.0f;
-          if (which < 2) {
-            float ss = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              __syncwarp();
-              tmem_ld_x32(taddr + hc * 128 + c * 32, v);
-              tmem_ld_wait();
-              float t[8];
+            } else {
+              const int hidx = g0 >> 7;
+              const int which = hidx / p.heads;  // 0 q, 1 k, 2 v
+              const int head = hidx - which * p.heads;
+              __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
+                                   (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
+              float ss = 0.f;
+              if (p.bias) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                if (p.bias) ld_bf16x8(p.bias + g0 + c * 32 + i, t);
+                for (int i = 0; i < 128; i += 8) {
+                  float t[8];
+                  ld_bf16x8(p.bias + g0 + i, t);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x = __uint_as_float(v[i + j]) + (p.bias ? t[j] : 0.f);
-                  ss += x * x;
+                  for (int j = 0; j < 8; ++j) {
+                    const float x = __uint_as_float(v[i + j]) + t[j];
+                    v[i + j] = __float_as_uint(x);
+                    ss += x * x;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 128; ++i) ss += __uint_as_float(v[i]) * __uint_as_float(v[i]);
+              }
+              if (which < 2) {
+                const float rr = rsqrtf(ss * (1.0f / 128.0f) + p.rms_eps);
+                const __nv_bfloat16* nw = which == 0 ? p.qnorm_w : p.knorm_w;
+                const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe + pos * 64);
+#pragma unroll
+                for (int i = 0; i < 128; i += 8) {
+                  float t[8], f[8];
+                  ld_bf16x8(nw + i, t);
+                  const uint4 u = __ldg(pe4 + (i >> 3));
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 cs = unpack_bf16(w[j]);  // (cos, sin)
+                    const float x0 = __uint_as_float(v[i + 2 * j]) * rr * t[2 * j];
+                    const float x1 = __uint_as_float(v[i + 2 * j + 1]) * rr * t[2 * j + 1];
+                    f[2 * j] = x0 * cs.x - x1 * cs.y;
+                    f[2 * j + 1] = x0 * cs.y + x1 * cs.x;
+                  }
+                  st_bf16x8(dst + i, f);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 128; i += 8) {
+                  float f[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[i + j]);
+                  st_bf16x8(dst + i, f);
                 }
               }
             }
-            rr = rsqrtf(ss * (1.0f / 128.0f) + p.rms_eps);
-          }
-          const __nv_bfloat16* nw = which == 0 ? p.qnorm_w : p.knorm_w;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            __syncwarp();
-            tmem_ld_x32(taddr + hc * 128 + c * 32, v);
-            tmem_ld_wait();
-            if (!valid) continue;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              float t[8];
-              if (p.bias) ld_bf16x8(p.bias + g0 + c * 32 + i, t);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[i + j] = __uint_as_float(v[i + j]) + (p.bias ? t[j] : 0.f);
-            }
-            if (which < 2) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                float t[8];
-                ld_bf16x8(nw + c * 32 + i, t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[i + j] = f[i + j] * rr * t[j];
-              }
-              const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe + pos * 64 + c * 16);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(pe4 + i);
-                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 cs = unpack_bf16(w[j]);  // (cos, sin)
-                  const float x0 = f[i * 8 + j * 2], x1 = f[i * 8 + j * 2 + 1];
-                  f[i * 8 + j * 2] = x0 * cs.x - x1 * cs.y;
-                  f[i * 8 + j * 2 + 1] = x0 * cs.y + x1 * cs.x;
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) st_bf16x8(dst + c * 32 + i, f + i);
           }
         }
       }

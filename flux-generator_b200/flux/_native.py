@@ -79,7 +79,8 @@ SYMBOLS = {
     "fx_patchify": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "fx_unpatchify_scale": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp]),
     "fx_groupnorm_stats": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp]),
-    "fx_groupnorm_apply": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_f32, c_i32, c_vp]),
+    "fx_groupnorm_finalize": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_f32, c_vp]),
+    "fx_groupnorm_apply": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp]),
     "fx_upsample2x": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "fx_softmax_rows": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_f32, c_vp]),
     "fx_transpose": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp]),

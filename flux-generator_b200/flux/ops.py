@@ -230,8 +230,10 @@ def groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
         out = torch.empty_like(x)
     l = N.lib()
     N.check(l.fx_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, hw, Cc, N.stream()))
-    N.check(l.fx_groupnorm_apply(x.data_ptr(), sums.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                 B, hw, Cc, eps, int(silu), N.stream()))
+    stats = torch.empty((B, 32, 2), device=x.device, dtype=torch.float32)
+    N.check(l.fx_groupnorm_finalize(sums.data_ptr(), stats.data_ptr(), B, hw, Cc, eps, N.stream()))
+    N.check(l.fx_groupnorm_apply(x.data_ptr(), stats.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                 B, hw, Cc, int(silu), N.stream()))
     return out
 
 

@@ -161,10 +161,13 @@ int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32_t h, int32
 
 /* ---------------------------------------------------------------- VAE decoder pieces
  * GroupNorm(32 groups, eps, affine) [+ SiLU] on NHWC bf16 (flux/autoencoder.py:29-35,62-78,88-94).
- * stats: `sums` is double [batch][32][2] (sum, sum of squares), zeroed by the caller. */
+ * stats: `sums` is double [batch][32][2] (sum, sum of squares), zeroed by the caller; finalize turns it
+ * into float [batch][32][2] (mean, rstd); apply normalises with those. */
 int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, int64_t hw, int32_t C, fx_stream stream);
-int fx_groupnorm_apply(const void* x, const double* sums, const void* weight, const void* bias, void* out,
-                       int32_t batch, int64_t hw, int32_t C, float eps, int32_t silu, fx_stream stream);
+int fx_groupnorm_finalize(const double* sums, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
+                          fx_stream stream);
+int fx_groupnorm_apply(const void* x, const float* stats, const void* weight, const void* bias, void* out,
+                       int32_t batch, int64_t hw, int32_t C, int32_t silu, fx_stream stream);
 /* upsample_nearest(x, (2,2)) on NHWC (flux/autoencoder.py:122) */
 int fx_upsample2x(const void* x, void* out, int32_t batch, int32_t H, int32_t W, int32_t C, fx_stream stream);
 /* P = softmax(scale * S) row-wise, S fp32 [rows][ld_s] -> P bf16 [rows][ld_p]  (VAE mid attention,
