@@ -2,7 +2,7 @@
 //   A  [batch][rows][K]   bf16, K contiguous (activations; or NHWC image read through a 4-D TMA box
 //                         for the 3x3 convolution mode -- implicit GEMM, no im2col buffer)
 //   W  [N][K]             bf16, K contiguous (nn.Linear layout / OHWI conv weights flattened)
-// One CTA per SM; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2..9 =
+// One CTA per SM; warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 4..11 =
 // epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each owning half the columns).  smem ring of 128B-swizzled K-major tiles filled by TMA;
 // accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
@@ -12,7 +12,7 @@ namespace fx {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle span
-constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int GEMM_THREADS = 384;  // warp 0 TMA, warp 1 MMA, (2,3 idle), warps 4..11 epilogue (two per TMEM lane quarter)
 
 enum : int { EPI_GENERIC = 0, EPI_QKV = 1 };
 
@@ -137,7 +137,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
 }
 
 template <int BN, int EPI, bool CONV>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -175,6 +175,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The register file is partitioned per SM sub-partition (16K registers each, 3 warps here): the QKV
+  // epilogue keeps a whole 128-column head in registers, so warpgroup 0 hands registers to the epilogue.
+  if (warp < 4) {
+  if (EPI == EPI_QKV) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -237,10 +241,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  }
   } else {
     // ================= epilogue warps =================
+    if (EPI == EPI_QKV) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp owns
+    const int half = (warp - 4) >> 2;    // which half of the tile's columns this warp owns
     const int r = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
