@@ -1,6 +1,8 @@
 // Host launchers for the tcgen05 GEMM family (fx_gemm, fx_gemm_qkv, fx_conv3x3).
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "api_common.cuh"
@@ -22,23 +24,55 @@ static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   p.group_m = p.tiles_m < 16 ? p.tiles_m : 16;
 }
 
-template <int BN, int EPI, bool CONV>
+template <int BN, int EPI, bool CONV, int NCTA = 1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, EPI, CONV>;
+  using Cfg = GemmCfg<BN, NCTA>;
+  auto kern = gemm_kernel<BN, EPI, CONV, NCTA>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, p);
+  const int units = num_sms() / NCTA;  // persistent: one CTA (or CTA pair) per SM (pair)
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, p);
+  if (e != cudaSuccess) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaGetLastError();
+    return fail(FX_ERR_CUDA, "gemm_kernel launch: %s", cudaGetErrorString(e));
+  }
   return launched("gemm_kernel");
 }
 
+// CTA pairs (256 x 256 tiles, cta_group::2) for the wide dense GEMMs; FX_GEMM_NCTA=1 forces single-CTA tiles.
+static int want_ncta(int bn) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FX_GEMM_NCTA");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2) return bn == 256 ? forced : 1;
+  return bn == 256 ? 2 : 1;
+}
+
 template <int EPI, bool CONV>
-static int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+static int launch_bn(int bn, int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  if constexpr (!CONV) {
+    if (bn == 256 && ncta == 2) return launch<256, EPI, CONV, 2>(ta, tw, p, st);
+  }
   if (bn == 256) return launch<256, EPI, CONV>(ta, tw, p, st);
   if (bn == 128) return launch<128, EPI, CONV>(ta, tw, p, st);
   return launch<64, EPI, CONV>(ta, tw, p, st);
@@ -65,7 +99,8 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
   const int bn = pick_bn(a->N);
-  fill_tiling(p, (a->rows + GEMM_BM - 1) / GEMM_BM, bn);
+  const int ncta = want_ncta(bn);
+  fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), bn);
   CUtensorMap ta, tw;
   {
     const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
@@ -77,11 +112,11 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {GEMM_BK, (uint32_t)bn};
+    const uint32_t box[2] = {GEMM_BK, (uint32_t)(bn / ncta)};
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  return launch_bn<EPI_GENERIC, false>(bn, ta, tw, p, (cudaStream_t)stream);
+  return launch_bn<EPI_GENERIC, false>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
 }
 
 extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
@@ -103,7 +138,8 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   p.qnorm_w = (const __nv_bfloat16*)a->q_scale; p.knorm_w = (const __nv_bfloat16*)a->k_scale;
   p.pe = (const uint32_t*)a->pe;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
-  fill_tiling(p, (a->rows + GEMM_BM - 1) / GEMM_BM, 256);
+  const int ncta = want_ncta(256);
+  fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);
   CUtensorMap ta, tw;
   {
     const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
@@ -115,10 +151,11 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {GEMM_BK, 256};
+    const uint32_t box[2] = {GEMM_BK, (uint32_t)(256 / ncta)};
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
+  if (ncta == 2) return launch<256, EPI_QKV, false, 2>(ta, tw, p, (cudaStream_t)stream);
   return launch<256, EPI_QKV, false>(ta, tw, p, (cudaStream_t)stream);
 }
 
@@ -153,7 +190,7 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  return launch_bn<EPI_GENERIC, true>(bn, ta, tw, p, (cudaStream_t)stream);
+  return launch_bn<EPI_GENERIC, true>(bn, 1, ta, tw, p, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------

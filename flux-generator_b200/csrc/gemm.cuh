@@ -38,14 +38,17 @@ struct GemmParams {
   int conv_H, conv_W, conv_tiles_x, conv_tiles_y, cin_blocks;
 };
 
-template <int BN>
+template <int BN, int NCTA = 1>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  // NCTA = 2: a CTA pair computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 A
+  // rows and HALF of the B tile, so the same 192 KB of shared memory buffers 50% more MMA work.
+  static constexpr int STAGES = NCTA == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = (BN / NCTA) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // after the barriers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 256 * 4 /*epilogue staging*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void gemm_tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
@@ -71,43 +74,38 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// One 32-column chunk of the generic epilogue for one accumulator row.
-__device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f, int b, long long out_off,
-                                                  long long res_off, int n0, bool fast) {
+// One 32-column chunk of the generic epilogue for one accumulator row.  Tile-uniform vectors (bias, gate)
+// come from this warp's shared-memory staging area `sb` / `sg` (floats, already bounds-checked: bias 0 /
+// gate 1 past N); the row's residual values may have been prefetched into `rr` before the accumulator
+// was ready (rr_ok), so that no long-latency load sits between the TMEM read and the store.
+__device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f, const float* sb, const float* sg,
+                                                  const uint4* rr, bool rr_ok, long long out_off, long long res_off,
+                                                  int n0, bool fast) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(sb + i);
+    f[i] += t.x; f[i + 1] += t.y; f[i + 2] += t.z; f[i + 3] += t.w;
+  }
+  if (p.act != 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
+  }
+  if (p.gate) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(sg + i);
+      f[i] *= t.x; f[i + 1] *= t.y; f[i + 2] *= t.z; f[i + 3] *= t.w;
+    }
+  }
   if (fast) {
-    if (p.bias) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        float t[8];
-        ld_bf16x8(p.bias + n0 + i, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[i + j] += t[j];
-      }
-    }
-    if (p.act != 0) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], p.act);
-    }
-    if (p.gate) {
-      const __nv_bfloat16* g = p.gate + (long long)b * p.gate_bs + n0;
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        float t[8];
-        ld_bf16x8(g + i, t);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[i + j] *= t[j];
-      }
-    }
     if (p.resid) {
       const __nv_bfloat16* r = p.resid + res_off + n0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        float t[8];
-        const uint4 u = *reinterpret_cast<const uint4*>(r + i);  // plain load: may alias `out`
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = rr_ok ? rr[i] : *reinterpret_cast<const uint4*>(r + i * 8);  // plain load: may alias `out`
         float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
-        t[0] = a.x; t[1] = a.y; t[2] = bb.x; t[3] = bb.y; t[4] = c.x; t[5] = c.y; t[6] = d.x; t[7] = d.y;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[i + j] += t[j];
+        f[i * 8] += a.x; f[i * 8 + 1] += a.y; f[i * 8 + 2] += bb.x; f[i * 8 + 3] += bb.y;
+        f[i * 8 + 4] += c.x; f[i * 8 + 5] += c.y; f[i * 8 + 6] += d.x; f[i * 8 + 7] += d.y;
       }
     }
     if (p.out_f32) {
@@ -126,9 +124,6 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
       const int n = n0 + i;
       if (n >= p.N) continue;
       float v = f[i];
-      if (p.bias) v += __bfloat162float(p.bias[n]);
-      if (p.act != 0) v = apply_act(v, p.act);
-      if (p.gate) v *= __bfloat162float(p.gate[(long long)b * p.gate_bs + n]);
       if (p.resid) v += __bfloat162float(p.resid[res_off + n]);
       if (p.out_f32) reinterpret_cast<float*>(p.out)[out_off + n] = v;
       else reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + n] = __float2bfloat16(v);
@@ -136,11 +131,21 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
   }
 }
 
-template <int BN, int EPI, bool CONV>
+// Stage `n` tile-uniform bf16 values src[n0 .. n0+n) as floats into this warp's shared-memory slot
+// (fill value past `limit` or when src is null).  One coalesced load per warp, no cross-warp barrier.
+__device__ __forceinline__ void stage_vec(float* dst, const __nv_bfloat16* src, int n0, int n, int limit, float fill,
+                                          int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = (src != nullptr && n0 + i < limit) ? __bfloat162float(__ldg(src + n0 + i)) : fill;
+}
+
+template <int BN, int EPI, bool CONV, int NCTA = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  static_assert(NCTA == 1 || !CONV, "the CTA-pair path covers the dense GEMMs only");
+  using Cfg = GemmCfg<BN, NCTA>;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int first_tile = blockIdx.x / NCTA, tile_stride = gridDim.x / NCTA;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -162,29 +167,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 8 * NCTA);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc2(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync();  // peer barriers must be initialised before any remote arrive / TMA credit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // The register file is partitioned per SM sub-partition (16K registers each, 3 warps here): the QKV
   // epilogue keeps a whole 128-column head in registers, so warpgroup 0 hands registers to the epilogue.
   if (warp < 4) {
-  if (EPI == EPI_QKV) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
         int tm, tn;
         gemm_tile_coords(p, tile, tm, tn);
         const int b = tm / p.tiles_m_per_batch;
@@ -198,6 +209,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          if (NCTA == 2) {
+            // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
+            tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * GEMM_BK, tn * BN + int(cta_rank) * (BN / 2));
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {
             const int tap = kb / p.cin_blocks;
@@ -207,19 +224,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * GEMM_BM, b);
           }
           tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * GEMM_BK, tn * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * NCTA, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -232,25 +250,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NCTA == 2) umma2_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if (NCTA == 2) tc_commit2(&empty_bar[stage]);
+          else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);
+        if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
+        else tc_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
   } else {
     // ================= epilogue warps =================
-    if (EPI == EPI_QKV) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;    // which half of the tile's columns this warp owns
     const int r = quarter * 32 + lane;
+    float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - 4) * 256;  // bias   (<= 128 floats)
+    float* sg = sb + 128;                                                           // gate / norm weight
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
       int tm, tn;
       gemm_tile_coords(p, tile, tm, tn);
       const int b = tm / p.tiles_m_per_batch;
@@ -263,31 +286,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         valid = (y < p.conv_H) && (x < p.conv_W);
         row = (long long)y * p.conv_W + x;
       } else {
-        row = (long long)tmb * GEMM_BM + r;
+        row = (long long)tmb * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
         valid = row < p.rows;
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
 
       if (EPI == EPI_GENERIC) {
+        constexpr int CH = BN / 64;        // 32-column chunks per warp
+        constexpr int WN = BN / 2;         // columns per warp
+        const int nw0 = tn * BN + half * WN;
         const long long out_off = (long long)b * p.out_bs + row * p.ldo;
         const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
-        const bool vec_ok = ((p.ldo | p.ldr | p.gate_bs) & 7) == 0;
-        constexpr int CH = BN / 64;  // 32-column chunks per warp
-#pragma unroll 1
-        for (int c = half * CH; c < (half + 1) * CH; ++c) {
-          const int n0 = tn * BN + c * 32;
-          if (n0 >= p.N) break;
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld_x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (valid) {
-            float f[32];
+        const bool vec_ok = ((p.ldo | p.ldr) & 7) == 0;
+        // ---- everything that does not depend on the accumulator happens BEFORE the wait
+        __syncwarp();
+        stage_vec(sb, p.bias, nw0, WN, p.N, 0.f, lane);
+        if (p.gate) stage_vec(sg, p.gate + (long long)b * p.gate_bs, nw0, WN, p.N, 1.f, lane);
+        uint4 rr[CH][4];
+        const bool rr_ok = p.resid != nullptr && valid && vec_ok && (nw0 + WN <= p.N);
+        if (rr_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            epi_generic_chunk(p, f, b, out_off, res_off, n0, vec_ok && (n0 + 32 <= p.N));
+          for (int c = 0; c < CH; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rr[c][i] = *reinterpret_cast<const uint4*>(p.resid + res_off + nw0 + c * 32 + i * 8);
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int n0 = nw0 + c * 32;
+          if (n0 < p.N) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_x32(taddr + half * WN + c * 32, v);
+            tmem_ld_wait();
+            if (valid) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+              epi_generic_chunk(p, f, sb + c * 32, sg + c * 32, rr[c], rr_ok, out_off, res_off, n0,
+                                vec_ok && (n0 + 32 <= p.N));
+            }
           }
         }
       } else {
@@ -295,7 +336,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int D3 = 3 * p.heads * 128;
         const long long pos = (long long)p.seq_off + row;
         const int g0 = tn * BN + half * 128;
-        if (g0 < p.N) {
+        const bool active = g0 < p.N;
+        const int hidx = g0 >> 7;
+        const int which = (g0 >= D3) ? 3 : hidx / p.heads;  // 0 q, 1 k, 2 v, 3 mlp
+        // ---- before the accumulator wait: bias / norm weight to smem, this row's RoPE table to registers
+        uint4 pe_r[16];
+        __syncwarp();
+        if (active) {
+          stage_vec(sb, p.bias, g0, 128, p.N, 0.f, lane);
+          if (which < 2) {
+            stage_vec(sg, which == 0 ? p.qnorm_w : p.knorm_w, 0, 128, 128, 1.f, lane);
+            if (valid) {
+              const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe + pos * 64);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pe_r[i] = __ldg(pe4 + i);
+            }
+          }
+        }
+        __syncwarp();
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (active) {
           uint32_t v[128];
           __syncwarp();
           tmem_ld_x32(taddr + half * 128, v);
@@ -304,7 +365,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           tmem_ld_x32(taddr + half * 128 + 96, v + 96);
           tmem_ld_wait();
           if (valid) {
-            if (g0 >= D3) {
+            if (which == 3) {
               // mlp region -> +bias, gelu -> `out` at column (g0 - 3D)
               const long long out_off = (long long)b * p.out_bs + pos * p.ldo - D3;
 #pragma unroll
@@ -312,40 +373,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[c * 32 + i]);
-                epi_generic_chunk(p, f, b, out_off, 0, g0 + c * 32, true);
+                epi_generic_chunk(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true);
               }
             } else {
-              const int hidx = g0 >> 7;
-              const int which = hidx / p.heads;  // 0 q, 1 k, 2 v
               const int head = hidx - which * p.heads;
               __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
                                    (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
               float ss = 0.f;
-              if (p.bias) {
 #pragma unroll
-                for (int i = 0; i < 128; i += 8) {
-                  float t[8];
-                  ld_bf16x8(p.bias + g0 + i, t);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float x = __uint_as_float(v[i + j]) + t[j];
-                    v[i + j] = __float_as_uint(x);
-                    ss += x * x;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 128; ++i) ss += __uint_as_float(v[i]) * __uint_as_float(v[i]);
+              for (int i = 0; i < 128; i += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(sb + i);
+                const float x0 = __uint_as_float(v[i]) + t.x, x1 = __uint_as_float(v[i + 1]) + t.y;
+                const float x2 = __uint_as_float(v[i + 2]) + t.z, x3 = __uint_as_float(v[i + 3]) + t.w;
+                v[i] = __float_as_uint(x0); v[i + 1] = __float_as_uint(x1);
+                v[i + 2] = __float_as_uint(x2); v[i + 3] = __float_as_uint(x3);
+                ss += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
               }
               if (which < 2) {
                 const float rr = rsqrtf(ss * (1.0f / 128.0f) + p.rms_eps);
-                const __nv_bfloat16* nw = which == 0 ? p.qnorm_w : p.knorm_w;
-                const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe + pos * 64);
 #pragma unroll
                 for (int i = 0; i < 128; i += 8) {
-                  float t[8], f[8];
-                  ld_bf16x8(nw + i, t);
-                  const uint4 u = __ldg(pe4 + (i >> 3));
+                  float f[8];
+                  const float4 t0 = *reinterpret_cast<const float4*>(sg + i);
+                  const float4 t1 = *reinterpret_cast<const float4*>(sg + i + 4);
+                  const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                  const uint4 u = pe_r[i >> 3];
                   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -373,16 +425,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync();  // neither CTA may exit (or free TMEM) while its peer still uses it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
