@@ -170,7 +170,9 @@ __device__ __forceinline__ void cluster_sync() {
 }
 // arrive on the mbarrier at the same offset in the LEADER CTA's shared memory
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+  // relaxed: the arrive only publishes "TMEM has been read" (ordered by tcgen05.fence::before_thread_sync);
+  // a release here would drain every outstanding global store of the epilogue first (MEMBAR.ALL.CTA)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
 // TMA loads whose completion bytes are credited to the LEADER CTA's mbarrier
@@ -262,6 +264,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);
+}
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100)
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2f(uint64_t v) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
+  return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

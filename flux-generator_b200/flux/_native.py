@@ -94,7 +94,8 @@ SYMBOLS = {
 
 
 def lib_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # FLUX_B200_LIB: an alternative build of the same library (A/B micro-benchmarks only)
+    return os.environ.get("FLUX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load():

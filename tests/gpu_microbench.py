@@ -1,0 +1,73 @@
+"""Sustained-regime micro-benchmarks of the hot kernels at the BASELINE shapes (batch 8, 1024x1024).
+Each op loops for >= SECONDS so the clocks settle under the power cap; prints TFLOP/s.
+Usage: python tests/gpu_microbench.py [ops...]   (FLUX_B200_LIB selects an alternative build of the library)"""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flux-generator_b200"))
+from flux import ops  # noqa: E402
+
+dev, bf = "cuda", torch.bfloat16
+SECONDS = float(os.environ.get("MB_SECONDS", "1.5"))
+B, L, S, D, H, M = 8, 4096, 256, 3072, 24, 12288
+N = L + S
+
+
+def sustained(fn, flops):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    n = 0
+    while time.time() - t0 < SECONDS:  # launches are async: queue depth stays bounded by the sync below
+        for _ in range(10):
+            fn()
+        n += 10
+        if n % 50 == 0:
+            torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return ms, flops / ms / 1e9
+
+
+def main(which):
+    g = torch.Generator(device=dev).manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).to(bf)  # noqa: E731
+    x = r(B, N, D)
+    xm = r(B, N, D)
+    cat = r(B, N, D + M)
+    q, k, v = r(B, H, N, 128), r(B, H, N, 128), r(B, H, N, 128)
+    w1, b1 = r(3 * D + M, D, sc=D ** -0.5), r(3 * D + M, sc=0.1)
+    w2, b2 = r(D, D + M, sc=(D + M) ** -0.5), r(D, sc=0.1)
+    wfc1, bfc1 = r(M, D, sc=D ** -0.5), r(M, sc=0.1)
+    qs, ks = r(128), r(128)
+    pe = r(N, 64, 2)
+    gate = r(B, D, sc=0.1)
+    shift, scale = r(B, D, sc=0.1), r(B, D, sc=0.1)
+    f32buf = torch.empty(B, L, M, device=dev, dtype=torch.float32) if 'fc1_f32out' in which else None
+    tests = {
+        "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
+        "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
+        "fc1": (lambda: ops.gemm(xm[:, S:], wfc1, bfc1, act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
+        "fc1_bias": (lambda: ops.gemm(xm[:, S:], wfc1, bfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
+        "fc1_gelu": (lambda: ops.gemm(xm[:, S:], wfc1, act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
+        "fc1_f32out": (lambda: ops.gemm(xm[:, S:], wfc1, out=f32buf), 2.0 * B * L * M * D),
+        "fc1_plain": (lambda: ops.gemm(xm[:, S:], wfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
+        "attn": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5), 4.0 * B * H * N * N * 128),
+        "rownorm": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm), 0.0),
+        "cublas_l1": (lambda: torch.matmul(xm.view(-1, D), w1.T), 2.0 * B * N * (3 * D + M) * D),
+    }
+    for name in which or list(tests):
+        fn, fl = tests[name]
+        ms, tf = sustained(fn, fl)
+        extra = f" = {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s" if name == "rownorm" else f" = {tf:.0f} TFLOP/s"
+        print(f"{name:10s} {ms:8.3f} ms{extra}", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
