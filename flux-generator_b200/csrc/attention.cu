@@ -46,6 +46,26 @@ __device__ __forceinline__ float2 unpack2(uint64_t v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
   return d;
 }
+// exp2 on the FMA pipe for a pair of values (Cody-Waite split + cubic minimax of 2^f on [-0.5, 0.5], max
+// relative error 7.5e-5 -- far below the bf16 rounding of P).  MUFU.EX2 sustains only 4 lanes/clk per
+// sub-partition, exactly as many cycles as the two MMAs of a tile take, so a share of the exponentials
+// is moved off the MUFU pipe (same idea as FlashAttention-4's software exp2).
+__device__ __forceinline__ void exp2_emu2(uint64_t t2, float& p0, float& p1) {
+  float2 t = unpack2f(t2);
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  t2 = pack2f(t.x, t.y);
+  const uint64_t magic = pack2f(12582912.0f, 12582912.0f);  // 1.5 * 2^23: low mantissa bits <- round(t)
+  const uint64_t r2 = fadd2(t2, magic);
+  const uint64_t f2 = fadd2(r2, pack2f(-12582912.0f, -12582912.0f));
+  const uint64_t x2 = ffma2(f2, pack2f(-1.0f, -1.0f), t2);  // t - round(t) in [-0.5, 0.5]
+  uint64_t q2 = ffma2(pack2f(0.0551716648f, 0.0551716648f), x2, pack2f(0.2426111251f, 0.2426111251f));
+  q2 = ffma2(q2, x2, pack2f(0.6932609677f, 0.6932609677f));
+  q2 = ffma2(q2, x2, pack2f(0.9999280572f, 0.9999280572f));
+  const float2 q = unpack2f(q2), r = unpack2f(r2);
+  p0 = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+  p1 = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -55,6 +75,11 @@ template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+#ifndef FX_ATTN_EMU_MASK
+#define FX_ATTN_EMU_MASK 0x00u  // bit i set: pair i of every 8 uses the software exp2 (A/B: no gain yet, softmax is latency-bound)
+#endif
+constexpr uint32_t EMU_MASK = FX_ATTN_EMU_MASK;
 
 template <bool P_TMEM>
 struct AttnCfg {
@@ -278,8 +303,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          const float2 t = unpack2(ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2));
-          const float p0 = fast_exp2(t.x), p1 = fast_exp2(t.y);
+          const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
+          float p0, p1;
+          if (EMU_MASK & (1u << ((e >> 1) & 7))) {  // compile-time pattern: which pairs go to the FMA pipe
+            exp2_emu2(t2, p0, p1);
+          } else {
+            const float2 t = unpack2(t2);
+            p0 = fast_exp2(t.x);
+            p1 = fast_exp2(t.y);
+          }
           lsum2 = fadd2(lsum2, pack2(p0, p1));
           pk[e >> 1] = pack_bf16(p0, p1);
         }
