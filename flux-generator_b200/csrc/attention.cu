@@ -375,6 +375,287 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// attn2_kernel: same math, decoupled schedule.  The key/value stream is consumed in 64-key steps; every
+// query tile owns TWO 64-column S buffers in TMEM, and S(n+2) = Q K(n+2)^T is issued right after
+// P(n) V(n), i.e. always one step AHEAD of the softmax.  The softmax warpgroups therefore never wait for the
+// "P ready -> PV -> QK -> S ready" round trip of attn_kernel: they are throughput-bound, not latency-bound.
+//   TMEM: S[i][b] at columns (2 i + b) * 64 (P[i][b] aliases its first 32 columns), O[i] at 256 + 128 i.
+// ------------------------------------------------------------------------------------------
+struct Attn2Cfg {
+  static constexpr int KV_STAGES = 5;
+  static constexpr int Q_OFF = 0;
+  static constexpr int KV_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int BAR_OFF = KV_OFF + KV_STAGES * ATT_TILE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = Attn2Cfg;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* kv_full = bars + 1;          // NS
+  uint64_t* kv_empty = kv_full + NS;     // NS
+  uint64_t* s_full = kv_empty + NS;      // [tile][buffer] = 4
+  uint64_t* p_full = s_full + 4;         // [tile][buffer] = 4
+  uint64_t* pv_done = p_full + 4;        // [tile] = 2
+  uint64_t* o_full = pv_done + 2;        // [tile] = 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int bh = blockIdx.z * p.heads + blockIdx.y;
+  const int T = p.kv_tiles;                 // 128-key tiles
+  const int NSTEP = (p.seq + 63) / 64;      // 64-key steps
+
+  if (warp == ATT_WARP_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == ATT_WARP_MMA) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= ATT_CTRL0 && warp < ATT_CTRL0 + 4) {
+    if (warp == ATT_WARP_TMA) {
+      if (lane == 0) {
+        // ---------------- TMA producer: Q (both tiles), then K0 V0 K1 V1 ... (128-key tiles)
+        mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+        for (int i = 0; i < 2; ++i)
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_3d(smem + Cfg::Q_OFF + i * ATT_TILE_BYTES + hf * 16384, &tmap_q, q_full, hf * 64, q0 + i * 128, bh);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < 2 * T; ++t) {
+          const CUtensorMap* m = (t & 1) ? &tmap_v : &tmap_k;
+          const int row = (t >> 1) * 128;
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
+          uint8_t* dst = smem + Cfg::KV_OFF + stage * ATT_TILE_BYTES;
+          tma_load_3d(dst, m, &kv_full[stage], 0, row, bh);
+          tma_load_3d(dst + 16384, m, &kv_full[stage], 64, row, bh);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == ATT_WARP_MMA) {
+      if (lane == 0) {
+        // ---------------- MMA issuer
+        constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+        const uint32_t q_base = smem_u32(smem + Cfg::Q_OFF);
+        const uint32_t kv_base = smem_u32(smem + Cfg::KV_OFF);
+        int stage = 0;
+        uint32_t phase = 0;
+        auto acquire = [&]() {
+          mbar_wait(&kv_full[stage], phase);
+          const int s = stage;
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          return s;
+        };
+        // S[i][n&1] = Q_i . K(step n)^T  (64 keys: rows 64*(n&1).. of the 128-key tile in `kslot`)
+        auto issue_qk = [&](int i, int n, int kslot) {
+          const uint32_t k_addr = kv_base + kslot * ATT_TILE_BYTES + (n & 1) * 8192;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+            umma_ss(tmem + i * 128 + (n & 1) * 64, make_smem_desc_sw128(q_base + i * ATT_TILE_BYTES + off, 16, 1024),
+                    make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0);
+          }
+          tc_commit(&s_full[i * 2 + (n & 1)]);
+        };
+        // O_i (+)= P[i][n&1] . V(step n)
+        auto issue_pv = [&](int i, int n, int vslot) {
+          const uint32_t v_addr = kv_base + vslot * ATT_TILE_BYTES + (n & 1) * 4 * 2048;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tmem + 256 + i * 128, tmem + i * 128 + (n & 1) * 64 + ks * 8,
+                    make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024), idesc_pv, (n > 0 || ks != 0) ? 1u : 0u);
+          tc_commit(&pv_done[i]);
+        };
+        mbar_wait(q_full, 0);
+        int kslot = acquire();  // K(0)
+        tc_fence_after();
+        for (int n = 0; n < 2 && n < NSTEP; ++n)
+          for (int i = 0; i < 2; ++i) issue_qk(i, n, kslot);
+        tc_commit(&kv_empty[kslot]);  // K(0) has no further readers (steps 0 and 1 are both issued)
+        int vslot = 0, knext = 0;
+        for (int n = 0; n < NSTEP; ++n) {
+          const bool more = n + 2 < NSTEP;
+          if ((n & 1) == 0) {
+            vslot = acquire();               // V(n/2)
+            if (more) knext = acquire();     // K(n/2 + 1): feeds steps n+2 and n+3
+          }
+          for (int i = 0; i < 2; ++i) {
+            mbar_wait(&p_full[i * 2 + (n & 1)], (n >> 1) & 1);
+            tc_fence_after();
+            issue_pv(i, n, vslot);
+            if (more) issue_qk(i, n + 2, knext);
+          }
+          if ((n & 1) == 1 || n == NSTEP - 1) tc_commit(&kv_empty[vslot]);                       // V(n/2) done
+          if (more && (((n + 2) & 1) == 1 || n + 2 == NSTEP - 1)) tc_commit(&kv_empty[knext]);  // K tile done
+        }
+        tc_commit(&o_full[0]);
+        tc_commit(&o_full[1]);
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warpgroups
+    const int i = (warp - ATT_SM0) >> 2;  // query tile 0/1
+    const int quarter = warp & 3;         // TMEM lane quarter
+    const int r = quarter * 32 + lane;
+    const int q_row = q0 + i * 128 + r;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const uint32_t o_addr = tmem + lane_base + 256 + i * 128;
+    const float sl2 = p.scale_log2;
+    const uint64_t sl2_2 = pack2(sl2, sl2);
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int n = 0; n < NSTEP; ++n) {
+      const int b = n & 1;
+      const uint32_t s_addr = tmem + lane_base + i * 128 + b * 64;
+      const int kv_valid = min(64, p.seq - n * 64);
+      mbar_wait(&s_full[i * 2 + b], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[64];
+      __syncwarp();
+      tmem_ld_x32(s_addr, sv);
+      tmem_ld_x32(s_addr + 32, sv + 32);
+      tmem_ld_wait();
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int e = 0; e < 64; ++e)
+          if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
+      }
+      float mx0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+      float mx1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+#pragma unroll
+      for (int e = 4; e < 64; e += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
+      }
+      const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * sl2);
+      const bool need = (m_new - m_run) > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+        if (need) {
+          m_run = m_new;
+          l_run *= alpha;
+        }
+        if (n > 0) {
+          // O_i must be quiescent: P(n-1) V(n-1) was issued BEFORE S(n+1) but possibly after S(n) was ready
+          mbar_wait(&pv_done[i], (n - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld_x32(o_addr + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_x32(o_addr + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const uint64_t nm2 = pack2(-m_run, -m_run);
+      uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const uint64_t ta = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
+          const uint64_t tb = ffma2(pack2(__uint_as_float(sv[c * 32 + e + 2]), __uint_as_float(sv[c * 32 + e + 3])), sl2_2, nm2);
+          float pa0, pa1, pb0, pb1;
+          if (EMU_MASK & (1u << ((e >> 2) & 7))) {
+            exp2_emu2(ta, pa0, pa1);
+          } else {
+            const float2 t = unpack2(ta);
+            pa0 = fast_exp2(t.x);
+            pa1 = fast_exp2(t.y);
+          }
+          {
+            const float2 t = unpack2(tb);
+            pb0 = fast_exp2(t.x);
+            pb1 = fast_exp2(t.y);
+          }
+          ls0 = fadd2(ls0, pack2(pa0, pa1));
+          ls1 = fadd2(ls1, pack2(pb0, pb1));
+          pk[e >> 1] = pack_bf16(pa0, pa1);
+          pk[(e >> 1) + 1] = pack_bf16(pb0, pb1);
+        }
+        tmem_st_x16(s_addr + c * 16, pk);
+      }
+      {
+        const float2 a = unpack2(fadd2(ls0, ls1));
+        l_run += a.x + a.y;
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[i * 2 + b]);
+    }
+
+    // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
+    mbar_wait(&o_full[i], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    __nv_bfloat16* dst = p.out + (long long)blockIdx.z * p.out_bs + (long long)q_row * p.ld_out + blockIdx.y * 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld_x32(o_addr + c * 32, v);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + e) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == ATT_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Small generic attention (text encoders; head_dim 64; seq <= 512): one warp per (b, h, query).
 // ------------------------------------------------------------------------------------------
 struct AttnSmallParams {
@@ -496,6 +777,19 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box))) return rc;
   if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box))) return rc;
   if (a->variant == 1) return launch_attn<false>(a, tq, tk, tv, p, (cudaStream_t)stream);
+  if (a->variant == 3) {
+    // decoupled 64-key-step schedule (attn2_kernel): correct, but measured slower than attn_kernel
+    // (861 vs 1026 TFLOP/s sustained at B=8, H=24, N=4352): the doubled per-step overheads outweigh the
+    // shorter critical path.  Kept selectable for the next round's work on the softmax pipeline.
+    static bool attr_done = false;
+    if (!attr_done) {
+      FX_CUDA(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg::SMEM_BYTES));
+      attr_done = true;
+    }
+    dim3 grid((a->seq + 255) / 256, a->heads, a->batch);
+    attn2_kernel<<<grid, ATT_THREADS, Attn2Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    return launched("attn2_kernel");
+  }
   return launch_attn<true>(a, tq, tk, tv, p, (cudaStream_t)stream);
 }
 

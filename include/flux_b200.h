@@ -101,7 +101,7 @@ typedef struct fx_attn_args {
   void* out; int64_t ld_out; int64_t out_bs;
   float scale;
   int32_t batch, heads, seq;
-  int32_t variant;             /* 0 = default; other values select bring-up variants (tests) */
+  int32_t variant;             /* 0 = default (P via TMEM); 1 = P via shared memory; 3 = decoupled 64-key-step schedule (tests / A-B) */
 } fx_attn_args;
 int fx_attention(const fx_attn_args* a, fx_stream stream);
 
