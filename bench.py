@@ -210,6 +210,9 @@ class KernelTimer:
         wrap("gemm_qkv", gemm_flops)
         wrap("attention", attn_flops)
         wrap("conv3x3", conv_flops)
+        for name in ("rownorm", "gemv", "groupnorm", "upsample2x", "softmax_rows", "transpose", "finish_image",
+                     "unpatchify_scale", "patchify", "euler_step", "timestep_embedding"):
+            wrap(name, lambda *a, **k: 0.0)  # HBM-bound helpers: time only
 
     def summary(self) -> dict:
         out = {}

@@ -32,38 +32,49 @@ struct RowNormParams {
   float eps; int mode, batch, rows, D;
 };
 
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// The row stays packed (bf16) in registers and is unpacked in each of the three passes: 48 instead of 96
+// data registers for D = 3072, so two 8-row blocks fit per SM instead of one (the kernel is a pure
+// HBM stream: more rows in flight = more bandwidth).
 template <int ITERS>  // ITERS = ceil(D / 256); D % 8 == 0
-__global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(256, 2) rownorm_kernel(const RowNormParams p) {
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gw >= (long long)p.batch * p.rows) return;
   const int b = int(gw / p.rows);
   const long long r = gw - (long long)b * p.rows;
   const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
-  float v[ITERS * 8];
+  uint4 raw[ITERS];
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int c = i * 256 + lane * 8;
-    if (c < p.D) load8(xr + c, v + i * 8);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[i * 8 + j] = 0.f;
-    }
+    raw[i] = (c < p.D) ? *reinterpret_cast<const uint4*>(xr + c) : make_uint4(0, 0, 0, 0);
   }
   float mean = 0.f;
   if (p.mode != 2) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < ITERS * 8; ++i) s += v[i];
+    for (int i = 0; i < ITERS; ++i) {
+      float v[8];
+      unpack8(raw[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[j];
+    }
     mean = warp_sum(s) / float(p.D);
   }
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     if (i * 256 + lane * 8 < p.D) {
+      float v[8];
+      unpack8(raw[i], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v[i * 8 + j] - mean;
+        const float d = v[j] - mean;
         ss += d * d;
       }
     }
@@ -75,12 +86,13 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const RowNormParams p) {
   for (int i = 0; i < ITERS; ++i) {
     const int c = i * 256 + lane * 8;
     if (c >= p.D) continue;
-    float a[8], s[8], o[8];
+    float v[8], a[8], s[8], o[8];
+    unpack8(raw[i], v);
     load8(p.p0 + pb + c, a);
     if (p.mode != 2) load8(p.p1 + pb + c, s);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float y = (v[i * 8 + j] - mean) * rstd;
+      const float y = (v[j] - mean) * rstd;
       if (p.mode == 0) o[j] = (1.0f + s[j]) * y + a[j];  // p0 = shift, p1 = scale
       else if (p.mode == 1) o[j] = y * a[j] + s[j];      // p0 = weight, p1 = bias
       else o[j] = y * a[j];                              // p0 = weight
@@ -109,47 +121,57 @@ __global__ void __launch_bounds__(256) gemv_kernel(const GemvParams p) {
     s_in[idx] = __float2bfloat16(x);  // bf16 like the reference's nn.silu output
   }
   __syncthreads();
+  // Each warp owns GEMV_R consecutive output rows: one shared-memory read of the activations feeds
+  // GEMV_R weight rows (the kernel streams weights from HBM; smem traffic was the co-limiter at R = 1).
+  constexpr int R = 4;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int n = blockIdx.x * (blockDim.x >> 5) + warp; n < p.N; n += warps_total) {
-    float acc[8];
+  for (int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * R; n0 < p.N; n0 += warps_total * R) {
+    float acc[R][8];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[b] = 0.f;
-    const __nv_bfloat16* wr = p.W + (long long)n * p.ldw;
-    // 4 independent 16-byte weight loads in flight per lane (the kernel is a pure weight stream)
-    for (int k0 = lane * 8; k0 < p.K; k0 += 1024) {
-      uint4 u[4];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + i * 256;
-        u[i] = (k < p.K) ? __ldg(reinterpret_cast<const uint4*>(wr + k)) : make_uint4(0, 0, 0, 0);
+      for (int b = 0; b < 8; ++b) acc[r][b] = 0.f;
+    for (int k = lane * 8; k < p.K; k += 256) {
+      uint4 u[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        u[r] = (n0 + r < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.W + (long long)(n0 + r) * p.ldw + k)) : make_uint4(0, 0, 0, 0);
+      float w[R][8];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float2 a = unpack_bf16(u[r].x), bb = unpack_bf16(u[r].y), c = unpack_bf16(u[r].z), d = unpack_bf16(u[r].w);
+        w[r][0] = a.x; w[r][1] = a.y; w[r][2] = bb.x; w[r][3] = bb.y; w[r][4] = c.x; w[r][5] = c.y; w[r][6] = d.x; w[r][7] = d.y;
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + i * 256;
-        if (k >= p.K) break;
-        float w[8];
-        float2 a = unpack_bf16(u[i].x), bb = unpack_bf16(u[i].y), c = unpack_bf16(u[i].z), d = unpack_bf16(u[i].w);
-        w[0] = a.x; w[1] = a.y; w[2] = bb.x; w[3] = bb.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y;
+      for (int b = 0; b < 8; ++b) {
+        if (b < p.batch) {
+          float x[8];
+          load8(s_in + b * p.K + k, x);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (b < p.batch) {
-            float x[8];
-            load8(s_in + b * p.K + k, x);
+          for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[b] += w[j] * x[j];
-          }
+            for (int j = 0; j < 8; ++j) acc[r][b] += w[r][j] * x[j];
         }
       }
     }
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[b] = warp_sum(acc[b]);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[r][b] = warp_sum(acc[r][b]);
     if (lane == 0) {
-      const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
-      for (int b = 0; b < p.batch; ++b) {
-        float v = acc[b] + bias;
-        if (p.silu_out) v = silu(__bfloat162float(__float2bfloat16(v)));
-        if (p.add) v = __bfloat162float(__float2bfloat16(v)) + __bfloat162float(p.add[b * p.ld_add + n]);
-        p.out[b * p.ld_out + n] = __float2bfloat16(v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int n = n0 + r;
+        if (n >= p.N) break;
+        const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b >= p.batch) continue;
+          float v = acc[r][b] + bias;
+          if (p.silu_out) v = silu(__bfloat162float(__float2bfloat16(v)));
+          if (p.add) v = __bfloat162float(__float2bfloat16(v)) + __bfloat162float(p.add[b * p.ld_add + n]);
+          p.out[b * p.ld_out + n] = __float2bfloat16(v);
+        }
       }
     }
   }
@@ -452,7 +474,7 @@ extern "C" int fx_gemv(const fx_gemv_args* a, fx_stream stream) {
     GemvParams p{(const __nv_bfloat16*)a->in + b0 * a->ld_in, a->ld_in, (const __nv_bfloat16*)a->W, a->ldw,
                  (const __nv_bfloat16*)a->bias, a->add ? (const __nv_bfloat16*)a->add + b0 * a->ld_add : nullptr, a->ld_add,
                  (__nv_bfloat16*)a->out + b0 * a->ld_out, a->ld_out, nb, a->N, a->K, a->silu_in, a->silu_out};
-    const int warps_needed = a->N;
+    const int warps_needed = (a->N + 3) / 4;
     int blocks = (warps_needed + 7) / 8;
     const int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
