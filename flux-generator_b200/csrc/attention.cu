@@ -25,6 +25,7 @@ constexpr int ATT_TILE_BYTES = 128 * 128 * 2;  // one 128x128 bf16 tile = two 16
 
 struct AttnParams {
   int seq, heads, kv_tiles;
+  int sequence;  // 1: the two softmax warpgroups take turns on the exp phase (MUFU is shared per sub-partition)
   float scale_log2;
   __nv_bfloat16* out;
   long long ld_out, out_bs;
@@ -106,7 +107,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   uint64_t* s_full = kv_empty + NS;    // 2
   uint64_t* p_full = s_full + 2;       // 2
   uint64_t* o_full = p_full + 2;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* seq_bar = o_full + 2;      // 2: exp-phase turn taking between the softmax warpgroups
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seq_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +129,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_full[i], 1);
+      mbar_init(&seq_bar[i], 4);
     }
     fence_barrier_init();
   }
@@ -271,8 +274,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
       }
       float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+      float mxb = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
-      for (int e = 2; e < 128; e += 2) mx = fmax3(mx, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+      for (int e = 4; e < 128; e += 4) {  // two independent chains
+        mx = fmax3(mx, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+        mxb = fmax3(mxb, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
+      }
+      mx = fmaxf(mx, mxb);
       const float m_new = fmaxf(m_run, mx * sl2);
       const bool need = (m_new - m_run) > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
@@ -295,9 +303,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           tmem_st_wait();
         }
       }
-      // probabilities: p = exp2(s * scale_log2 - m_run), packed two at a time
+      // probabilities: p = exp2(s * scale_log2 - m_run), packed two at a time.  The two warpgroups take
+      // turns (the MUFU of a sub-partition serves one warp of each), and the row sum is accumulated AFTER
+      // P has been handed to the MMA warp -- neither sits on the critical path S -> P -> PV.
+      if (p.sequence) mbar_wait(&seq_bar[i], (i == 0) ? ((j & 1) ^ 1) : (j & 1));
       const uint64_t nm2 = pack2(-m_run, -m_run);
-      uint64_t lsum2 = pack2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
@@ -312,7 +322,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             p0 = fast_exp2(t.x);
             p1 = fast_exp2(t.y);
           }
-          lsum2 = fadd2(lsum2, pack2(p0, p1));
+          sv[c * 32 + e] = __float_as_uint(p0);
+          sv[c * 32 + e + 1] = __float_as_uint(p1);
           pk[e >> 1] = pack_bf16(p0, p1);
         }
         if (P_TMEM) {
@@ -327,9 +338,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           }
         }
       }
-      {
-        const float2 ls = unpack2(lsum2);
-        l_run += ls.x + ls.y;
+      if (p.sequence) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&seq_bar[i ^ 1]);  // the other warpgroup's turn
       }
       if (P_TMEM) {
         tmem_st_wait();
@@ -339,6 +350,16 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[i]);
+      {
+        uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 128; e += 4) {
+          ls0 = fadd2(ls0, pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+          ls1 = fadd2(ls1, pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+        }
+        const float2 ls = unpack2(fadd2(ls0, ls1));
+        l_run += ls.x + ls.y;
+      }
     }
 
     // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
@@ -766,6 +787,7 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   FX_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v), "fx_attention: q/k/v must be 16-byte aligned");
   AttnParams p{};
   p.seq = a->seq; p.heads = a->heads; p.kv_tiles = (a->seq + 127) / 128;
+  p.sequence = (a->variant == 4) ? 0 : 1;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out; p.out_bs = a->out_bs;
   CUtensorMap tq, tk, tv;

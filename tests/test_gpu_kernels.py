@@ -114,7 +114,7 @@ def test_conv3x3(B, H, W, Cin, Cout):
         ops.conv3x3(rnd(1, 4, 4, 16), rnd(8, 144), None)  # Cin must be a multiple of 64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("B,H,S", [(1, 1, 128), (2, 3, 512), (1, 2, 320), (1, 1, 77), (1, 2, 1280), (1, 1, 1)])
 def test_attention(variant, B, H, S):
     q, k, v = rnd(B, H, S, 128, seed=21), rnd(B, H, S, 128, seed=22), rnd(B, H, S, 128, seed=23)
