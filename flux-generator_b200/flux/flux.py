@@ -49,6 +49,10 @@ class FluxPipeline:
                                               vocab_size=min(self.t5.config.vocab_size, 32100))
         self.sampler = FluxSampler(name)
         self._cond_cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._bcast_cache: Dict[tuple, tuple] = {}
+        self._ids_cache: Dict[tuple, torch.Tensor] = {}
+        import os
+        self.use_graph = os.environ.get("FLUX_B200_GRAPH", "1") not in ("0", "")
 
     def ensure_models_are_loaded(self):
         torch.cuda.synchronize(self.device)
@@ -67,10 +71,13 @@ class FluxPipeline:
     def _prepare_latent_images(self, x: torch.Tensor):
         b, h, w, c = x.shape
         packed = ops.patchify(x.to(device=self.device, dtype=bf16))
-        i = torch.zeros((h // 2, w // 2), dtype=torch.int32)
-        j, k = torch.meshgrid(torch.arange(h // 2, dtype=torch.int32), torch.arange(w // 2, dtype=torch.int32),
-                              indexing="ij")
-        x_ids = torch.stack([i, j, k], dim=-1).reshape(1, h * w // 4, 3).repeat(b, 1, 1).to(self.device)
+        x_ids = self._ids_cache.get((b, h, w))
+        if x_ids is None:
+            i = torch.zeros((h // 2, w // 2), dtype=torch.int32)
+            j, k = torch.meshgrid(torch.arange(h // 2, dtype=torch.int32), torch.arange(w // 2, dtype=torch.int32),
+                                  indexing="ij")
+            x_ids = torch.stack([i, j, k], dim=-1).reshape(1, h * w // 4, 3).repeat(b, 1, 1).to(self.device)
+            self._ids_cache = {(b, h, w): x_ids}
         return packed, x_ids
 
     def _prepare_conditioning(self, n_images, t5_tokens, clip_tokens):
@@ -83,13 +90,19 @@ class FluxPipeline:
             vec1 = self.clip(clip_tokens).pooled_output
             hit = (txt1, vec1)
             self._cond_cache[key] = hit
-        txt, vec = hit
-        if len(txt) == 1 and n_images > 1:
-            txt = txt.expand(n_images, *txt.shape[1:]).contiguous()
-        txt_ids = torch.zeros((n_images, txt.shape[1], 3), dtype=torch.int32, device=self.device)
-        if len(vec) == 1 and n_images > 1:
-            vec = vec.expand(n_images, *vec.shape[1:]).contiguous()
-        return txt, txt_ids, vec
+        # the broadcast copies are cached too: the flow model keys its txt_in cache and its CUDA graph on them
+        bkey = (key, n_images)
+        bhit = self._bcast_cache.get(bkey)
+        if bhit is None:
+            txt, vec = hit
+            if len(txt) == 1 and n_images > 1:
+                txt = txt.expand(n_images, *txt.shape[1:]).contiguous()
+            txt_ids = torch.zeros((n_images, txt.shape[1], 3), dtype=torch.int32, device=self.device)
+            if len(vec) == 1 and n_images > 1:
+                vec = vec.expand(n_images, *vec.shape[1:]).contiguous()
+            bhit = (txt, txt_ids, vec)
+            self._bcast_cache = {bkey: bhit}
+        return bhit
 
     # ------------------------------------------------------------------ flux/flux.py:87-126
     def _denoising_loop(self, x_t, x_ids, txt, txt_ids, vec, num_steps: int = 35, guidance: float = 4.0,
@@ -105,8 +118,8 @@ class FluxPipeline:
         for i in range(num_steps):
             t = timesteps[i]
             t_prev = timesteps[i + 1]
-            pred = self.flow.forward(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec,
-                                     timesteps=scalar(t), guidance=guidance)
+            fwd = self.flow.forward_graphed if self.use_graph else self.flow.forward
+            pred = fwd(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=scalar(t), guidance=guidance)
             x_t = ops.euler_step(x_t.clone(), pred, t_prev - t)  # sampler.step (flux/sampler.py:56-57)
             yield x_t
 

@@ -146,6 +146,7 @@ class Flux:
             if missing:
                 raise ValueError(f"Missing {len(missing)} parameters, e.g. {missing[:3]}")
         self._txt_cache = None
+        self._graphs = {}
         return self
 
     def _shapes_dict(self):
@@ -290,6 +291,38 @@ class Flux:
         ops.rownorm(x_img, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, S:])
         ops.gemm(xm[:, S:], self._w("final_layer.linear"), self._b("final_layer.linear"), out=ws["pred"])
         return ws["pred"]
+
+    def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
+                        timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """forward() replayed from a CUDA graph (captured once per shape and conditioning tensors): removes the
+        ~450 host launches per step, which dominate the small configurations (512x512, batch 1).  `img`,
+        `timesteps` and `guidance` are copied into static buffers; txt / y / ids are captured by address."""
+        key = (tuple(img.shape), txt.data_ptr(), txt._version, y.data_ptr(), y._version, img_ids.data_ptr(),
+               txt_ids.data_ptr(), guidance is not None)
+        g = self._graphs.get(key) if hasattr(self, "_graphs") else None
+        if g is None:
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            st = dict(img=torch.empty_like(img, dtype=bf16), t=torch.empty_like(timesteps, dtype=bf16),
+                      g=None if guidance is None else torch.empty_like(guidance, dtype=bf16), keep=(txt, y, img_ids, txt_ids))
+            st["img"].copy_(img)
+            st["t"].copy_(timesteps)
+            if guidance is not None:
+                st["g"].copy_(guidance)
+            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"])  # warm-up: caches, attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"])
+            st["graph"] = graph
+            self._graphs = {key: st}  # one resident graph: shapes change rarely
+            g = st
+        g["img"].copy_(img)
+        g["t"].copy_(timesteps)
+        if guidance is not None:
+            g["g"].copy_(guidance)
+        g["graph"].replay()
+        return g["pred"]
 
     def __call__(self, img, img_ids, txt, txt_ids, timesteps, y, guidance=None) -> torch.Tensor:
         """Flux.__call__ (flux/model.py:99-136): returns a fresh [B, L, in_channels] bf16 tensor."""

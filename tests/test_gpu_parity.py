@@ -163,6 +163,24 @@ def test_pipeline_end_to_end_vs_golden(variant):
     assert d.mean() <= 2 / 255 and np.quantile(d, 0.999) <= 8 / 255
 
 
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    cfg = small_configs()[0]
+    model, _, p = build_flow(cfg, True)
+    g = torch.Generator().manual_seed(10)
+    B, L, S = 2, 24, 16
+    txt = torch.randn(B, S, cfg["context_in_dim"], generator=g).to(bf).to(dev)
+    y = torch.randn(B, cfg["vec_in_dim"], generator=g).to(bf).to(dev)
+    ids = O.prepare_latent_images(torch.zeros(B, 8, 12, 16))[1].to(dev)
+    tids = torch.zeros(B, S, 3, dtype=torch.int32, device=dev)
+    gd = torch.full((B,), 3.5, dtype=bf, device=dev)
+    for step, tval in enumerate((1.0, 0.75, 0.5)):  # replay with new inputs each step
+        img = torch.randn(B, L, 64, generator=g).to(bf).to(dev)
+        ts = torch.full((B,), tval, dtype=bf, device=dev)
+        eager = model.forward(img, ids, txt, tids, ts, y, gd).clone()
+        graphed = model.forward_graphed(img, ids, txt, tids, ts, y, gd).clone()
+        assert torch.equal(eager, graphed), f"step {step}"
+
+
 def test_batch_invariance_and_determinism():
     """An image does not depend on what else is in the batch (sharding over GPUs is exact), and
     repeated runs are bit-identical."""
