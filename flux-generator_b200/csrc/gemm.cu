@@ -21,7 +21,16 @@ static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   p.num_tiles = p.tiles_m * p.tiles_n;
   // raster: GROUP_M m-tiles x all n-tiles per group; a wave of ~148 CTAs then touches
   // group_m A-tiles and ~148/group_m W-slabs -> both operands are re-read from L2, not HBM.
-  p.group_m = p.tiles_m < 16 ? p.tiles_m : 16;
+  // Narrow outputs (N = 3072: 12 column tiles) run all their column tiles of ~6 row tiles in one wave, so every
+  // A k-slice is fetched once per wave; wide outputs keep 16 row tiles per group (measured, sustained regime:
+  // linear2 1136 -> 1159 TFLOP/s with small groups, linear1 / fc1 best at 16).  FX_GEMM_GROUP_M overrides.
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FX_GEMM_GROUP_M");
+    forced = e ? atoi(e) : 0;
+  }
+  int gm = forced > 0 ? forced : (p.tiles_n <= 16 ? 6 : 16);
+  p.group_m = p.tiles_m < gm ? p.tiles_m : gm;
 }
 
 template <int BN, int EPI, bool CONV, int NCTA = 1>
