@@ -199,3 +199,35 @@ def test_batch_invariance_and_determinism():
     assert torch.equal(full, again)
     one = model(img[1:2], ids[1:2], txt[1:2].contiguous(), tids[1:2], ts[1:2], y[1:2])
     assert torch.equal(one[0], full[1])
+
+
+def test_cli_end_to_end_writes_images(tmp_path, monkeypatch):
+    """txt2image.py surface on the GPU (small synthetic models): grid PNG with the reference's 4-px border
+    layout (txt2image.py:139-144) and --save-raw naming (txt2image.py:129-136)."""
+    import flux
+    import txt2image
+    from PIL import Image
+    fcfg, acfg, t5c, clc = small_configs()
+    real = flux.FluxPipeline
+
+    def small(name, **kw):
+        return real(name, flow_params=specs.FluxParams(**fcfg, guidance_embed="dev" in name),
+                    ae_params=specs.AutoEncoderParams(**acfg), t5_config=specs.T5Config(**t5c),
+                    clip_config=specs.CLIPTextModelConfig(**clc), **kw)
+
+    monkeypatch.setattr(flux, "FluxPipeline", small)
+    out = tmp_path / "grid.png"
+    txt2image.main(["a cat", "--synthetic", "--n-images", "4", "--n-rows", "2", "--image-size", "64x96", "--steps", "2",
+                    "--seed", "3", "--output", str(out), "--verbose"])
+    im = Image.open(out)
+    assert im.size == (2 * (96 + 8), 2 * (64 + 8))  # (W, H): 2 columns x 2 rows of 4-px padded images
+    raw = tmp_path / "img.png"
+    txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
+                    "--output", str(raw), "--model", "dev", "--guidance", "3.5"])
+    a, b = Image.open(tmp_path / "img.0.png"), Image.open(tmp_path / "img.1.png")
+    assert a.size == (96, 64) and b.size == (96, 64)  # rounded UP to multiples of 16 (txt2image.py:14-25)
+    assert a.tobytes() != b.tobytes()  # different prior per image
+    # same seed, same images: the run is deterministic
+    txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
+                    "--output", str(tmp_path / "again.png"), "--model", "dev", "--guidance", "3.5"])
+    assert Image.open(tmp_path / "again.0.png").tobytes() == a.tobytes()
