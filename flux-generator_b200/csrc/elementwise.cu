@@ -241,51 +241,62 @@ __global__ void unpatchify_scale_kernel(const __nv_bfloat16* packed, __nv_bfloat
 }
 
 // ------------------------------------------------------------------ GroupNorm (32 groups) on NHWC
-// stats: each block reduces a slab of rows; thread owns 8 consecutive channels.
-__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* x, double* sums, long long hw, int C,
-                                                              int rows_per_block) {
-  __shared__ float s_sum[32], s_sq[32];
-  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
+// stats: each block reduces a slab of 256 rows; thread owns 8 consecutive channels.  No atomics anywhere:
+// per-block partial sums are combined in a fixed order, so results are bit-reproducible run to run.
+constexpr int GN_ROWS_PER_BLOCK = 256;
+
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* x, float* partials, long long hw, int C) {
+  __shared__ float sm[256][17];  // [thread][8 sums | 8 sums of squares], padded
   const int b = blockIdx.y;
   const int tpr = C / 8;                 // threads per row
   const int rpi = 256 / tpr;             // rows per iteration
   const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  const long long r1 = min(hw, r0 + rows_per_block);
+  const long long r0 = (long long)blockIdx.x * GN_ROWS_PER_BLOCK;
+  const long long r1 = min(hw, r0 + GN_ROWS_PER_BLOCK);
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  if (tr < rpi) {
-    const __nv_bfloat16* base = x + (long long)b * hw * C + tc * 8;
-    for (long long r = r0 + tr; r < r1; r += rpi) {
-      float v[8];
-      load8(base + r * C, v);
+  const __nv_bfloat16* base = x + (long long)b * hw * C + tc * 8;
+  for (long long r = r0 + tr; r < r1; r += rpi) {
+    float v[8];
+    load8(base + r * C, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
-    }
+    for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
   }
-  const int gs = C / 32;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (tc * 8 + j) / gs;
-    atomicAdd(&s_sum[g], s[j]);
-    atomicAdd(&s_sq[g], q[j]);
-  }
+  for (int j = 0; j < 8; ++j) { sm[threadIdx.x][j] = s[j]; sm[threadIdx.x][8 + j] = q[j]; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    atomicAdd(&sums[((long long)b * 32 + threadIdx.x) * 2], (double)s_sum[threadIdx.x]);
-    atomicAdd(&sums[((long long)b * 32 + threadIdx.x) * 2 + 1], (double)s_sq[threadIdx.x]);
+  if (threadIdx.x < 64) {  // (group, statistic): fixed summation order over rows then channels
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+    const int gs = C / 32;
+    float acc = 0.f;
+    for (int t = 0; t < rpi; ++t)
+      for (int c = g * gs; c < (g + 1) * gs; ++c) acc += sm[t * tpr + (c >> 3)][st * 8 + (c & 7)];
+    partials[(((long long)b * gridDim.x + blockIdx.x) * 32 + g) * 2 + st] = acc;
   }
 }
 
-// (sum, sumsq) in double -> (mean, rstd) in float, once per (batch, group)
-__global__ void groupnorm_finalize_kernel(const double* sums, float2* stats, int n_groups, double n, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_groups) return;
-  const double mean = sums[2 * i] / n;
-  const double var = fmax(sums[2 * i + 1] / n - mean * mean, 0.0);
-  stats[i] = make_float2((float)mean, rsqrtf((float)var + eps));
+// per-block partials -> (mean, rstd) in float; one warp per (batch, group), fixed order, double accumulation
+__global__ void groupnorm_finalize_kernel(const float* partials, float2* stats, int n_groups, int nblk, double n, float eps) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_groups) return;
+  const int b = wid >> 5, g = wid & 31;
+  double su = 0.0, sq = 0.0;
+  for (int k = lane; k < nblk; k += 32) {
+    const float* pp = partials + (((long long)b * nblk + k) * 32 + g) * 2;
+    su += (double)pp[0];
+    sq += (double)pp[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    su += __shfl_xor_sync(0xffffffffu, su, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if (lane == 0) {
+    const double mean = su / n;
+    const double var = fmax(sq / n - mean * mean, 0.0);
+    stats[wid] = make_float2((float)mean, rsqrtf((float)var + eps));
+  }
 }
 
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* x, const float2* stats,
@@ -518,21 +529,26 @@ extern "C" int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32
   return launched("unpatchify_scale_kernel");
 }
 
-extern "C" int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, int64_t hw, int32_t C, fx_stream stream) {
-  FX_REQUIRE(x && sums && batch > 0 && hw > 0, "fx_groupnorm_stats: bad arguments");
+extern "C" int64_t fx_groupnorm_partials_count(int32_t batch, int64_t hw) {
+  return (int64_t)batch * ((hw + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK) * 64;
+}
+
+extern "C" int fx_groupnorm_stats(const void* x, float* partials, int32_t batch, int64_t hw, int32_t C, fx_stream stream) {
+  FX_REQUIRE(x && partials && batch > 0 && hw > 0, "fx_groupnorm_stats: bad arguments");
   FX_REQUIRE(C % 32 == 0 && C >= 64 && C <= 2048 && (C / 8) <= 256 && 256 % (C / 8) == 0,
              "fx_groupnorm_stats: unsupported channel count %d", C);
-  const int rows_per_block = 256;
-  dim3 grid((unsigned)((hw + rows_per_block - 1) / rows_per_block), batch);
-  groupnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, sums, hw, C, rows_per_block);
+  dim3 grid((unsigned)((hw + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK), batch);
+  groupnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, partials, hw, C);
   return launched("groupnorm_stats_kernel");
 }
 
-extern "C" int fx_groupnorm_finalize(const double* sums, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
+extern "C" int fx_groupnorm_finalize(const float* partials, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
                                      fx_stream stream) {
-  FX_REQUIRE(sums && stats && batch > 0 && hw > 0 && C % 32 == 0, "fx_groupnorm_finalize: bad arguments");
+  FX_REQUIRE(partials && stats && batch > 0 && hw > 0 && C % 32 == 0, "fx_groupnorm_finalize: bad arguments");
   const int n = batch * 32;
-  groupnorm_finalize_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, (float2*)stats, n, (double)hw * (C / 32), eps);
+  const int nblk = (int)((hw + GN_ROWS_PER_BLOCK - 1) / GN_ROWS_PER_BLOCK);
+  groupnorm_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, (float2*)stats, n, nblk,
+                                                                                 (double)hw * (C / 32), eps);
   return launched("groupnorm_finalize_kernel");
 }
 

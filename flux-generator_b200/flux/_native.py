@@ -78,6 +78,7 @@ SYMBOLS = {
     "fx_euler_step": (C.c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),
     "fx_patchify": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "fx_unpatchify_scale": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp]),
+    "fx_groupnorm_partials_count": (C.c_int64, [c_i32, c_i64]),
     "fx_groupnorm_stats": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp]),
     "fx_groupnorm_finalize": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_f32, c_vp]),
     "fx_groupnorm_apply": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp]),

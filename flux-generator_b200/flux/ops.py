@@ -225,10 +225,10 @@ def groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     _chk(x)
     B, Cc = x.shape[0], x.shape[-1]
     hw = x.numel() // (B * Cc)
-    sums = torch.zeros((B, 32, 2), device=x.device, dtype=torch.float64)
+    l = N.lib()
+    sums = torch.empty((int(l.fx_groupnorm_partials_count(B, hw)),), device=x.device, dtype=torch.float32)
     if out is None:
         out = torch.empty_like(x)
-    l = N.lib()
     N.check(l.fx_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, hw, Cc, N.stream()))
     stats = torch.empty((B, 32, 2), device=x.device, dtype=torch.float32)
     N.check(l.fx_groupnorm_finalize(sums.data_ptr(), stats.data_ptr(), B, hw, Cc, eps, N.stream()))

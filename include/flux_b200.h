@@ -161,10 +161,12 @@ int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32_t h, int32
 
 /* ---------------------------------------------------------------- VAE decoder pieces
  * GroupNorm(32 groups, eps, affine) [+ SiLU] on NHWC bf16 (flux/autoencoder.py:29-35,62-78,88-94).
- * stats: `sums` is double [batch][32][2] (sum, sum of squares), zeroed by the caller; finalize turns it
- * into float [batch][32][2] (mean, rstd); apply normalises with those. */
-int fx_groupnorm_stats(const void* x, double* sums, int32_t batch, int64_t hw, int32_t C, fx_stream stream);
-int fx_groupnorm_finalize(const double* sums, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
+ * stats writes per-block partial sums (float, fx_groupnorm_partials_count(batch, hw) elements: no atomics,
+ * bit-reproducible); finalize reduces them in a fixed order to float [batch][32][2] (mean, rstd); apply
+ * normalises with those. */
+int64_t fx_groupnorm_partials_count(int32_t batch, int64_t hw);
+int fx_groupnorm_stats(const void* x, float* partials, int32_t batch, int64_t hw, int32_t C, fx_stream stream);
+int fx_groupnorm_finalize(const float* partials, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
                           fx_stream stream);
 int fx_groupnorm_apply(const void* x, const float* stats, const void* weight, const void* bias, void* out,
                        int32_t batch, int64_t hw, int32_t C, int32_t silu, fx_stream stream);

@@ -166,7 +166,7 @@ def test_two_rank_gloo_sharding_and_broadcast(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), ROOT],
+                        "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), str(script), ROOT],
                        capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
