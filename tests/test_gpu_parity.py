@@ -91,6 +91,11 @@ def test_flow_full_width_vs_oracle():
                          txt.float(), tids, ts, y.float(), gd)
     out = model(img.to(dev), ids.to(dev), txt.to(dev), tids.to(dev), ts.to(dev), y.to(dev), gd.to(dev))
     assert rel_l2(out, ref) <= 2e-2 and cosine(out, ref) >= 0.9995
+    # calibration: an op-by-op bf16 execution -- what the reference's MLX graph does -- sits this far
+    # from the fp32 oracle; the fused kernels (fp32 inside, bf16 at kernel boundaries) must not be further away
+    emu = O.flux_forward(sd, O.FluxParams(depth=1, depth_single_blocks=1, guidance_embed=True), img.float(), ids,
+                         txt.float(), tids, ts, y.float(), gd, mode=O.Mode("bf16"))
+    assert rel_l2(out, ref) <= 1.5 * rel_l2(emu, ref) + 1e-3, (rel_l2(out, ref), rel_l2(emu, ref))
 
 
 def test_vae_decode_vs_golden():
@@ -161,6 +166,26 @@ def test_pipeline_end_to_end_vs_golden(variant):
     img = pipe.decode(lats[-1], (h, w))
     d = np.abs(img.cpu().numpy() - g["image"])
     assert d.mean() <= 2 / 255 and np.quantile(d, 0.999) <= 8 / 255
+
+
+def test_argument_errors_surface_as_value_errors():
+    """bad shapes / alignment are rejected by the library before any launch (FX_ERR_INVALID -> ValueError)."""
+    a = torch.zeros(4, 0, 64, device=dev, dtype=bf)
+    with pytest.raises(ValueError):
+        ops.gemm(a, torch.zeros(8, 64, device=dev, dtype=bf))                      # empty rows
+    with pytest.raises(ValueError):
+        ops.attention(*(torch.zeros(1, 1, 8, 64, device=dev, dtype=bf),) * 3, torch.zeros(1, 8, 64, device=dev, dtype=bf), 1.0)
+    with pytest.raises(ValueError):
+        ops.rownorm(torch.zeros(2, 4, 12, device=dev, dtype=bf), 2, torch.ones(12, device=dev, dtype=bf), None, 1e-6)  # D % 8
+    with pytest.raises(ValueError):
+        ops.attention_small(*(torch.zeros(1, 600, 64, device=dev, dtype=bf),) * 3, 1, 1.0)   # seq > 512
+    with pytest.raises(ValueError):
+        ops.gemm(torch.zeros(8, 64, device=dev, dtype=torch.float32), torch.zeros(8, 64, device=dev, dtype=bf))  # dtype
+    q = torch.zeros(1, 2, 16, 128, device=dev, dtype=bf)
+    with pytest.raises(ValueError):  # rows beyond seq_total
+        ops.gemm_qkv(torch.zeros(1, 32, 64, device=dev, dtype=bf), torch.zeros(768, 64, device=dev, dtype=bf), None,
+                     torch.ones(128, device=dev, dtype=bf), torch.ones(128, device=dev, dtype=bf),
+                     torch.zeros(16, 64, 2, device=dev, dtype=bf), q, q.clone(), q.clone(), 0)
 
 
 def test_cuda_graph_replay_is_bit_identical_to_eager():
