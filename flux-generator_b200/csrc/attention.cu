@@ -105,8 +105,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   uint64_t* kv_full = bars + 1;        // NS
   uint64_t* kv_empty = kv_full + NS;   // NS
   uint64_t* s_full = kv_empty + NS;    // 2
-  uint64_t* p_full = s_full + 2;       // 2
-  uint64_t* o_full = p_full + 2;       // 2
+  uint64_t* p_full = s_full + 2;       // [tile][half] = 4: P is handed over in two 64-key halves
+  uint64_t* o_full = p_full + 4;       // 2
   uint64_t* seq_bar = o_full + 2;      // 2: exp-phase turn taking between the softmax warpgroups
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seq_bar + 2);
 
@@ -127,7 +127,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&seq_bar[i], 4);
     }
@@ -184,9 +185,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
                   make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0);
         }
       };
-      auto issue_pv = [&](int i, uint32_t v_addr, bool acc) {
+      // the P.V product is issued in two halves of 64 keys: the first four MMAs start as soon as the first half
+      // of P exists, while the softmax warps are still exponentiating the second half
+      auto issue_pv = [&](int i, uint32_t v_addr, bool acc, int hf) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = hf * 4; ks < hf * 4 + 4; ++ks) {
           const uint64_t vd = make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024);
           if (P_TMEM) {
             umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, vd, idesc_pv, (acc || ks != 0) ? 1u : 0u);
@@ -219,16 +222,22 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         const uint32_t k_addr = kv_base + ks_ * ATT_TILE_BYTES;
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
-        issue_pv(0, v_addr, j > 0);
+        issue_pv(0, v_addr, j > 0, 0);
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(0, v_addr, j > 0, 1);
         if (more) {
           mbar_wait(&kv_full[ks_], phase);  // K(j+1)
           tc_fence_after();
           issue_qk(0, k_addr);
           tc_commit(&s_full[0]);
         }
-        mbar_wait(&p_full[1], j & 1);
+        mbar_wait(&p_full[2], j & 1);
         tc_fence_after();
-        issue_pv(1, v_addr, j > 0);
+        issue_pv(1, v_addr, j > 0, 0);
+        mbar_wait(&p_full[3], j & 1);
+        tc_fence_after();
+        issue_pv(1, v_addr, j > 0, 1);
         tc_commit(&kv_empty[vs]);
         if (more) {
           issue_qk(1, k_addr);
@@ -337,19 +346,21 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
           }
         }
+        if (c & 1) {  // a 64-key half of P is complete: hand it to the MMA warp
+          if (c == 3 && p.sequence) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&seq_bar[i ^ 1]);  // the other warpgroup's turn on the MUFU
+          }
+          if (P_TMEM) {
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[2 * i + (c >> 1)]);
+        }
       }
-      if (p.sequence) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&seq_bar[i ^ 1]);  // the other warpgroup's turn
-      }
-      if (P_TMEM) {
-        tmem_st_wait();
-        tc_fence_before();
-      } else {
-        fence_proxy_async_smem();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i]);
       {
         uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
 #pragma unroll
