@@ -240,6 +240,52 @@ __global__ void unpatchify_scale_kernel(const __nv_bfloat16* packed, __nv_bfloat
   z[idx] = __float2bfloat16(v);
 }
 
+// ------------------------------------------------------------------ Gaussian prior, written packed
+// FluxSampler.sample_prior + _prepare_latent_images in one pass (flux/sampler.py:44-45, flux/flux.py:53-58):
+// counter-based Philox4x32-10 keyed by (seed, GLOBAL image index) and counted by the NHWC element index, so an
+// image's noise does not depend on the batch it is generated in nor on how the batch is sharded over GPUs.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void prior_kernel(__nv_bfloat16* out, int b, int h, int w, int c, uint32_t seed_lo, uint32_t seed_hi, int first_index) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call = 4 consecutive NHWC elements
+  const long long per_image = (long long)h * w * c / 4;
+  if (q >= (long long)b * per_image) return;
+  const int bi = int(q / per_image);
+  const long long qi = q - (long long)bi * per_image;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)qi, (uint32_t)(qi >> 32), (uint32_t)(first_index + bi), 0u, seed_lo, seed_hi, r);
+  float n[4];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {  // Box-Muller on two uniform pairs
+    const float u1 = ((r[2 * k] >> 8) + 1) * (1.0f / 16777216.0f);    // (0, 1]
+    const float u2 = (r[2 * k + 1] >> 8) * (1.0f / 16777216.0f);      // [0, 1)
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    n[2 * k] = rad * cs;
+    n[2 * k + 1] = rad * sn;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long e = qi * 4 + k;                  // NHWC element ((y*w + x)*c + ch)
+    const int ch = int(e % c);
+    const long long pix = e / c;
+    const int x = int(pix % w), y = int(pix / w);
+    const long long tok = (long long)(y >> 1) * (w >> 1) + (x >> 1);
+    out[((long long)bi * (h / 2) * (w / 2) + tok) * (4 * c) + ch * 4 + (y & 1) * 2 + (x & 1)] = __float2bfloat16(n[k]);
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm (32 groups) on NHWC
 // stats: each block reduces a slab of 256 rows; thread owns 8 consecutive channels.  No atomics anywhere:
 // per-block partial sums are combined in a fixed order, so results are bit-reproducible run to run.
@@ -517,6 +563,16 @@ extern "C" int fx_patchify(const void* x, void* out, int32_t b, int32_t h, int32
   const long long n = (long long)b * h * w * c;
   patchify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, b, h, w, c);
   return launched("patchify_kernel");
+}
+
+extern "C" int fx_prior_packed(void* out, int32_t b, int32_t h, int32_t w, int32_t c, uint64_t seed, int32_t first_index,
+                               fx_stream stream) {
+  FX_REQUIRE(out && b > 0 && h > 0 && w > 0 && c > 0, "fx_prior_packed: bad arguments");
+  FX_REQUIRE(h % 2 == 0 && w % 2 == 0 && c % 4 == 0, "fx_prior_packed: latent size (%d, %d) must be even, channels %% 4 == 0", h, w);
+  const long long n = (long long)b * h * w * c / 4;
+  prior_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, b, h, w, c, (uint32_t)seed,
+                                                                          (uint32_t)(seed >> 32), first_index);
+  return launched("prior_kernel");
 }
 
 extern "C" int fx_unpatchify_scale(const void* packed, void* z, int32_t b, int32_t h, int32_t w, int32_t c, int32_t c_pad,

@@ -77,6 +77,7 @@ SYMBOLS = {
     "fx_timestep_embedding": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp]),
     "fx_euler_step": (C.c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),
     "fx_patchify": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "fx_prior_packed": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, C.c_uint64, c_i32, c_vp]),
     "fx_unpatchify_scale": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp]),
     "fx_groupnorm_partials_count": (C.c_int64, [c_i32, c_i64]),
     "fx_groupnorm_stats": (C.c_int, [c_vp, c_vp, c_i32, c_i64, c_i32, c_vp]),

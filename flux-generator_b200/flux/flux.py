@@ -71,6 +71,9 @@ class FluxPipeline:
     def _prepare_latent_images(self, x: torch.Tensor):
         b, h, w, c = x.shape
         packed = ops.patchify(x.to(device=self.device, dtype=bf16))
+        return packed, self._latent_ids(b, h, w)
+
+    def _latent_ids(self, b: int, h: int, w: int) -> torch.Tensor:
         x_ids = self._ids_cache.get((b, h, w))
         if x_ids is None:
             i = torch.zeros((h // 2, w // 2), dtype=torch.int32)
@@ -78,7 +81,7 @@ class FluxPipeline:
                                   indexing="ij")
             x_ids = torch.stack([i, j, k], dim=-1).reshape(1, h * w // 4, 3).repeat(b, 1, 1).to(self.device)
             self._ids_cache = {(b, h, w): x_ids}
-        return packed, x_ids
+        return x_ids
 
     def _prepare_conditioning(self, n_images, t5_tokens, clip_tokens):
         key = (tuple(t5_tokens.flatten().tolist()), tuple(clip_tokens.flatten().tolist()))
@@ -126,9 +129,15 @@ class FluxPipeline:
     def generate_latents(self, text: str, n_images: int = 1, num_steps: int = 35, guidance: float = 4.0,
                          latent_size: Tuple[int, int] = (64, 64), seed=None, x_T: Optional[torch.Tensor] = None):
         if x_T is None:
-            x_T = self.sampler.sample_prior((n_images, *latent_size, 16), dtype=self.dtype,
-                                            key=0 if seed is None else seed, first_index=self.first_image_index)
-        x_T, x_ids = self._prepare_latent_images(x_T)
+            # prior drawn on the device straight into the packed layout (sample_prior + patchify fused)
+            h, w = latent_size
+            if h % 2 or w % 2:
+                raise ValueError(f"latent size {latent_size} must be even")
+            x_T = ops.prior_packed(n_images, latent_size, 16, 0 if seed is None else seed, self.first_image_index,
+                                   device=self.device)
+            x_ids = self._latent_ids(n_images, h, w)
+        else:
+            x_T, x_ids = self._prepare_latent_images(x_T)
         t5_tokens, clip_tokens = self.tokenize(text)
         txt, txt_ids, vec = self._prepare_conditioning(n_images, t5_tokens, clip_tokens)
         yield (x_T, x_ids, txt, txt_ids, vec)

@@ -205,6 +205,16 @@ def patchify(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def prior_packed(n_images: int, latent_size, channels: int = 16, seed: int = 0, first_index: int = 0,
+                 device="cuda") -> torch.Tensor:
+    """Standard-normal prior written directly in the packed [B, L, 4c] layout (Philox keyed by global image index)."""
+    h, w = latent_size
+    out = torch.empty((n_images, h * w // 4, 4 * channels), device=device, dtype=bf16)
+    N.check(N.lib().fx_prior_packed(out.data_ptr(), n_images, h, w, channels, int(seed) & 0xFFFFFFFFFFFFFFFF, first_index,
+                                    N.stream()))
+    return out
+
+
 def unpatchify_scale(packed: torch.Tensor, latent_size, c_pad: int, scale_factor: float,
                      shift_factor: float) -> torch.Tensor:
     _chk(packed)

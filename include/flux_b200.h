@@ -153,6 +153,12 @@ int fx_euler_step(void* x, const void* pred, float dt, int64_t n, fx_stream stre
 /* ---------------------------------------------------------------- latent packing
  * _prepare_latent_images (flux/flux.py:53-58): [b][h][w][c] -> [b][hw/4][4c], feature c*4+dy*2+dx */
 int fx_patchify(const void* x, void* out, int32_t b, int32_t h, int32_t w, int32_t c, fx_stream stream);
+/* FluxSampler.sample_prior fused with the packing above (flux/sampler.py:44-45): standard-normal bf16 noise
+ * written as [b][hw/4][4c]; Philox4x32-10 keyed by (seed, first_index + image) and counted by the NHWC element
+ * index, so an image's prior is independent of batch composition and GPU sharding.  (MLX's threefry stream
+ * is not reproducible offline; callers that need specific noise pass x_T instead.) */
+int fx_prior_packed(void* out, int32_t b, int32_t h, int32_t w, int32_t c, uint64_t seed, int32_t first_index,
+                    fx_stream stream);
 /* FluxPipeline.decode's inverse + AutoEncoder.decode's affine (flux/flux.py:159-160,
  * flux/autoencoder.py:353): packed [b][hw/4][4c] -> z [b][h][w][c_pad] = x/scale + shift, channels
  * c..c_pad-1 zero (conv_in reads 64-channel blocks). */

@@ -204,3 +204,44 @@ def test_groupnorm_softmax_attention_small():
     assert rel_l2(ops.attention_small(q, k, v, H, 1.0, bias=bias), ref) <= 5e-3
     ref = F.scaled_dot_product_attention(hd(q), hd(k), hd(v), is_causal=True).transpose(1, 2).reshape(Bq, S, -1)
     assert rel_l2(ops.attention_small(q, k, v, H, 0.125, causal=True), ref) <= 5e-3
+
+
+def _philox4x32_10(ctr, key):
+    import numpy as np
+    c = [np.uint32(v) for v in ctr]
+    k = [np.uint32(v) for v in key]
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * np.uint64(c[0])
+        p1 = np.uint64(0xCD9E8D57) * np.uint64(c[2])
+        hi0, lo0 = np.uint32(p0 >> np.uint64(32)), np.uint32(p0 & np.uint64(0xFFFFFFFF))
+        hi1, lo1 = np.uint32(p1 >> np.uint64(32)), np.uint32(p1 & np.uint64(0xFFFFFFFF))
+        c = [hi1 ^ c[1] ^ k[0], lo1, hi0 ^ c[3] ^ k[1], lo0]
+        k = [np.uint32((int(k[0]) + 0x9E3779B9) & 0xFFFFFFFF), np.uint32((int(k[1]) + 0xBB67AE85) & 0xFFFFFFFF)]
+    return [int(v) for v in c]
+
+
+def test_prior_kernel_philox_known_answers_and_sharding():
+    """Device prior (sample_prior + patchify fused): counter-based, so (a) values follow from a CPU Philox4x32-10,
+    (b) an image's noise does not depend on batch size or on which rank generates it, (c) ~N(0, 1)."""
+    import math
+    assert _philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]  # Random123 KAT
+    h, w, seed = 8, 12, 1234
+    full = ops.prior_packed(5, (h, w), 16, seed, 0)
+    z = ops.unpatchify_scale(full, (h, w), 16, 1.0, 0.0)           # back to NHWC [5, h, w, 16]
+    for (bi, e) in ((0, 0), (3, 101), (4, h * w * 16 - 4)):         # element groups of 4 = one Philox call
+        r = _philox4x32_10([e // 4, 0, bi, 0], [seed, 0])
+        exp = []
+        for kk in range(2):
+            u1 = ((r[2 * kk] >> 8) + 1) / 16777216.0
+            u2 = (r[2 * kk + 1] >> 8) / 16777216.0
+            rad = math.sqrt(-2.0 * math.log(u1))
+            exp += [rad * math.cos(2 * math.pi * u2), rad * math.sin(2 * math.pi * u2)]
+        got = z[bi].flatten()[e:e + 4].float().cpu()
+        assert torch.allclose(got, torch.tensor(exp).to(bf).float(), atol=2e-2, rtol=2e-2), (bi, e, got, exp)
+    assert torch.equal(ops.prior_packed(2, (h, w), 16, seed, 3), full[3:5])      # rank holding images 3..4
+    assert torch.equal(ops.prior_packed(5, (h, w), 16, seed, 0), full)           # deterministic
+    assert not torch.equal(ops.prior_packed(1, (h, w), 16, seed + 1, 0), full[:1])
+    big = ops.prior_packed(4, (128, 128), 16, 7, 0).float()
+    assert abs(big.mean().item()) < 5e-3 and abs(big.std().item() - 1.0) < 5e-3
+    with pytest.raises(ValueError):
+        ops.prior_packed(1, (7, 8), 16, 0, 0)
