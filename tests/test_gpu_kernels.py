@@ -228,7 +228,7 @@ def test_prior_kernel_philox_known_answers_and_sharding():
     h, w, seed = 8, 12, 1234
     full = ops.prior_packed(5, (h, w), 16, seed, 0)
     z = ops.unpatchify_scale(full, (h, w), 16, 1.0, 0.0)           # back to NHWC [5, h, w, 16]
-    for (bi, e) in ((0, 0), (3, 101), (4, h * w * 16 - 4)):         # element groups of 4 = one Philox call
+    for (bi, e) in ((0, 0), (3, 100), (4, h * w * 16 - 4)):         # element groups of 4 = one Philox call
         r = _philox4x32_10([e // 4, 0, bi, 0], [seed, 0])
         exp = []
         for kk in range(2):
