@@ -166,11 +166,15 @@ def test_two_rank_gloo_sharding_and_broadcast(tmp_path):
     import socket
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER)
-    with socket.socket() as sk:  # a port that is free right now
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
-                       capture_output=True, text=True, timeout=240)
+    r = None
+    for attempt in range(3):  # the rendezvous port is picked free-right-now; retry if something grabbed it meanwhile
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script), ROOT],
+                           capture_output=True, text=True, timeout=240)
+        if r.returncode == 0:
+            break
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
