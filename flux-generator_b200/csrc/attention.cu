@@ -36,17 +36,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the softmax inner loop
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float2 unpack2(uint64_t v) {
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(v));
-  return d;
-}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { return pack2f(lo, hi); }
+__device__ __forceinline__ float2 unpack2(uint64_t v) { return unpack2f(v); }
 // exp2 on the FMA pipe for a pair of values (Cody-Waite split + cubic minimax of 2^f on [-0.5, 0.5], max
 // relative error 7.5e-5 -- far below the bf16 rounding of P).  MUFU.EX2 sustains only 4 lanes/clk per
 // sub-partition, exactly as many cycles as the two MMAs of a tile take, so a share of the exponentials
