@@ -79,9 +79,7 @@ static int want_ncta(int bn) {
 
 template <int EPI, bool CONV>
 static int launch_bn(int bn, int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-  if constexpr (!CONV) {
-    if (bn == 256 && ncta == 2) return launch<256, EPI, CONV, 2>(ta, tw, p, st);
-  }
+  if (bn == 256 && ncta == 2) return launch<256, EPI, CONV, 2>(ta, tw, p, st);
   if (bn == 256) return launch<256, EPI, CONV>(ta, tw, p, st);
   if (bn == 128) return launch<128, EPI, CONV>(ta, tw, p, st);
   return launch<64, EPI, CONV>(ta, tw, p, st);
@@ -177,12 +175,13 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   p.cin_blocks = a->Cin / GEMM_BK;
   p.k_blocks = 9 * p.cin_blocks;
   p.conv_H = a->H; p.conv_W = a->Wd;
-  p.conv_tiles_x = (a->Wd + 15) / 16;
+  const int bn = pick_bn(a->Cout);
+  const int ncta = want_ncta(bn);  // CTA pair: two horizontally adjacent 8x16-pixel patches form one 256-row tile
+  p.conv_tiles_x = (a->Wd + 16 * ncta - 1) / (16 * ncta);
   p.conv_tiles_y = (a->H + 7) / 8;
   p.bias = (const __nv_bfloat16*)a->bias;
   p.out = a->out; p.ldo = a->Cout; p.out_bs = (long long)a->H * a->Wd * a->Cout; p.out_f32 = a->out_f32;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = p.out_bs;
-  const int bn = pick_bn(a->Cout);
   fill_tiling(p, p.conv_tiles_x * p.conv_tiles_y, bn);
   CUtensorMap ta, tw;
   {
@@ -195,11 +194,11 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   {
     const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)a->Cout};
     const uint64_t strides[1] = {(uint64_t)p.K * 2};
-    const uint32_t box[2] = {GEMM_BK, (uint32_t)bn};
+    const uint32_t box[2] = {GEMM_BK, (uint32_t)(bn / ncta)};
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  return launch_bn<EPI_GENERIC, true>(bn, 1, ta, tw, p, (cudaStream_t)stream);
+  return launch_bn<EPI_GENERIC, true>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------

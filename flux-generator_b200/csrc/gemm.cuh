@@ -171,7 +171,6 @@ template <int BN, int EPI, bool CONV, int NCTA = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
-  static_assert(NCTA == 1 || !CONV, "the CTA-pair path covers the dense GEMMs only");
   using Cfg = GemmCfg<BN, NCTA>;
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int first_tile = blockIdx.x / NCTA, tile_stride = gridDim.x / NCTA;
@@ -230,9 +229,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int b = tm / p.tiles_m_per_batch;
         const int tmb = tm - b * p.tiles_m_per_batch;
         int cy = 0, cx = 0;
-        if (CONV) {
+        if (CONV) {  // conv_tiles_x counts tiles of the CTA (pair): 16 * NCTA pixels wide
           cy = (tmb / p.conv_tiles_x) * 8;
-          cx = (tmb % p.conv_tiles_x) * 16;
+          cx = (tmb % p.conv_tiles_x) * (16 * NCTA) + int(cta_rank) * 16;
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -241,7 +240,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (NCTA == 2) {
             // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
+            if (CONV) {
+              const int tap = kb / p.cin_blocks;
+              const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
+              tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
+            } else {
+              tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
+            }
             tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * GEMM_BK, tn * BN + int(cta_rank) * (BN / 2));
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -311,7 +316,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       long long row;  // row index inside the batch (pixel index for conv)
       if (CONV) {
         const int y = (tmb / p.conv_tiles_x) * 8 + (r >> 4);
-        const int x = (tmb % p.conv_tiles_x) * 16 + (r & 15);
+        const int x = (tmb % p.conv_tiles_x) * (16 * NCTA) + int(cta_rank) * 16 + (r & 15);
         valid = (y < p.conv_H) && (x < p.conv_W);
         row = (long long)y * p.conv_W + x;
       } else {
