@@ -73,13 +73,14 @@ static int want_ncta(int bn) {
     const char* e = getenv("FX_GEMM_NCTA");
     forced = e ? atoi(e) : 0;
   }
-  if (forced == 1 || forced == 2) return bn == 256 ? forced : 1;
-  return bn == 256 ? 2 : 1;
+  if (forced == 1 || forced == 2) return bn >= 128 ? forced : 1;
+  return bn >= 128 ? 2 : 1;
 }
 
 template <int EPI, bool CONV>
 static int launch_bn(int bn, int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
   if (bn == 256 && ncta == 2) return launch<256, EPI, CONV, 2>(ta, tw, p, st);
+  if (bn == 128 && ncta == 2) return launch<128, EPI, CONV, 2>(ta, tw, p, st);
   if (bn == 256) return launch<256, EPI, CONV>(ta, tw, p, st);
   if (bn == 128) return launch<128, EPI, CONV>(ta, tw, p, st);
   return launch<64, EPI, CONV>(ta, tw, p, st);

@@ -161,6 +161,11 @@ def stage_conv():
     b = torch.zeros(256, device=dev, dtype=bf)
     ms = tm(lambda: ops.conv3x3(x, w, b), iters=3, warm=1)
     print(f"conv 512x512 256->256: {ms:.3f} ms = {2.0 * 512 * 512 * 256 * 256 * 9 / ms / 1e9:.0f} TFLOP/s")
+    x = torch.randn(1, 1024, 1024, 128, device=dev, dtype=bf)
+    w = torch.randn(128, 9 * 128, device=dev, dtype=bf) * 0.02
+    b = torch.zeros(128, device=dev, dtype=bf)
+    ms = tm(lambda: ops.conv3x3(x, w, b), iters=3, warm=1)
+    print(f"conv 1024x1024 128->128: {ms:.3f} ms = {2.0 * 1024 * 1024 * 128 * 128 * 9 / ms / 1e9:.0f} TFLOP/s")
 
 
 def stage_attn(variant):
