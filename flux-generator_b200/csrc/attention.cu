@@ -32,9 +32,13 @@ struct AttnParams {
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
+#ifdef FX_ATTN_NOEXP  // timing ablation only (wrong numerics): no MUFU work
+  return x * 0.0078125f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) { return pack2f(lo, hi); }
 __device__ __forceinline__ float2 unpack2(uint64_t v) { return unpack2f(v); }
@@ -69,9 +73,43 @@ template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 #ifndef FX_ATTN_EMU_MASK
-#define FX_ATTN_EMU_MASK 0x00u  // bit i set: pair i of every 8 uses the software exp2 (A/B: no gain yet, softmax is latency-bound)
+#define FX_ATTN_EMU_MASK 0x11u  // bit i set: pair i of every 8 uses the software exp2 (25 %: 3471 -> 3303 clocks per key tile)
 #endif
 constexpr uint32_t EMU_MASK = FX_ATTN_EMU_MASK;
+
+// FX_ATTN_PROBE (profiling builds only): one CTA records SM-clock timestamps of its pipeline events into
+// a global buffer [role 3][step 64][event 8]; roles: 0 MMA issuer, 1/2 softmax warpgroup 0/1 (first warp).
+// waits of the MMA warp: all 32 lanes poll (warp-uniform control flow).  A/B in the sustained, power-capped
+// regime: one polling lane + __syncwarp was 2 % slower; FX_ATTN_MMA_ONEWAIT selects it.
+#ifdef FX_ATTN_MMA_ONEWAIT
+#define MMA_WAIT(bar, ph) do { if (lane == 0) mbar_wait(bar, ph); __syncwarp(); } while (0)
+#else
+#define MMA_WAIT(bar, ph) mbar_wait(bar, ph)
+#endif
+#ifdef FX_ATTN_MMAONLY  // timing ablation: tensor pipe alone (no softmax, P never waited for)
+#define P_WAIT(bar, ph) do {} while (0)
+#else
+#define P_WAIT(bar, ph) MMA_WAIT(bar, ph)
+#endif
+#ifdef FX_ATTN_PROBE
+__device__ long long* g_attn_probe = nullptr;
+__device__ __forceinline__ long long probe_clock() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ long long probe_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROBE(role, step, ev)                                                                         \
+  do {                                                                                                \
+    if (probe_on && (step) < 64) g_attn_probe[((role) * 64 + (step)) * 8 + (ev)] = probe_clock();     \
+  } while (0)
+#else
+#define PROBE(role, step, ev) do {} while (0)
+#endif
 
 template <bool P_TMEM>
 struct AttnCfg {
@@ -106,6 +144,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   const int q0 = blockIdx.x * 256;
   const int bh = blockIdx.z * p.heads + blockIdx.y;
   const int T = p.kv_tiles;
+#ifdef FX_ATTN_PROBE
+  const bool probe_on = g_attn_probe && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 1 && lane == 0;
+#endif
 
   if (warp == ATT_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -125,6 +166,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     }
     fence_barrier_init();
   }
+#ifdef FX_ATTN_PROBE
+  if (probe_on && warp == ATT_WARP_MMA) {
+    g_attn_probe[(0 * 64 + 63) * 8 + 0] = probe_clock();
+    g_attn_probe[(0 * 64 + 63) * 8 + 2] = probe_gtime();
+  }
+#endif
   if (warp == ATT_WARP_MMA) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -151,6 +198,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         const CUtensorMap* m = (t & 1) ? &tmap_v : &tmap_k;
         const int row = (t >> 1) * 128;
         mbar_wait(&kv_empty[stage], phase ^ 1);
+#ifdef FX_ATTN_NOTMA  // timing ablation: K/V tiles are loaded once, later ring slots are only re-armed
+        if (t >= NS) {
+          mbar_arrive(&kv_full[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          continue;
+        }
+#endif
         mbar_arrive_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
         uint8_t* dst = smem + Cfg::KV_OFF + stage * ATT_TILE_BYTES;
         tma_load_3d(dst, m, &kv_full[stage], 0, row, bh);
@@ -159,86 +213,116 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       }
     }
   } else if (warp == ATT_WARP_MMA) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
+    // ---------------- MMA issuer.  The whole warp runs this loop with warp-uniform control flow and one
+    // elected lane issues the tcgen05 instructions: the compiler then keeps descriptors in uniform registers
+    // (no per-instruction ELECT / BRA.U.ANY loop), and every descriptor is "precomputed low word + constant".
+    // The issuing thread was the kernel's bottleneck before this (probe: ~105 clocks per MMA against a
+    // 64-clock tensor-pipe floor, P always ready before the issuer asked for it).
+    {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
-      const uint32_t q_base = smem_u32(smem + Cfg::Q_OFF);
-      const uint32_t kv_base = smem_u32(smem + Cfg::KV_OFF);
-      const uint32_t p_base = smem_u32(smem + Cfg::P_OFF);
+      const uint32_t q_lo = (smem_u32(smem + Cfg::Q_OFF) >> 4) | (1u << 16);      // K-major: LBO field 1
+      const uint32_t k_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1u << 16);
+      const uint32_t v_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1024u << 16);  // MN-major: LBO = 16384 B
+      const uint32_t p_lo = (smem_u32(smem + Cfg::P_OFF) >> 4) | (1u << 16);
+      constexpr uint32_t TILE16 = ATT_TILE_BYTES >> 4;
       int stage = 0;
       uint32_t phase = 0;
-      auto issue_qk = [&](int i, uint32_t k_addr) {
+      auto issue_qk = [&](int i, int kslot) {
+#ifdef FX_ATTN_NOQK
+        return;
+#endif
+        const uint32_t a_lo = q_lo + i * TILE16, b_lo = k_lo0 + kslot * TILE16;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-          umma_ss(tmem + i * 128, make_smem_desc_sw128(q_base + i * ATT_TILE_BYTES + off, 16, 1024),
-                  make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0);
+          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;  // (half * 16384 + k16 * 32) >> 4
+          umma_ss(tmem + i * 128, make_desc(a_lo + off, kDescHiSw128), make_desc(b_lo + off, kDescHiSw128), idesc_qk, ks != 0);
         }
       };
       // the P.V product is issued in two halves of 64 keys: the first four MMAs start as soon as the first half
       // of P exists, while the softmax warps are still exponentiating the second half
-      auto issue_pv = [&](int i, uint32_t v_addr, bool acc, int hf) {
+      auto issue_pv = [&](int i, int vslot, bool acc, int hf) {
+#ifdef FX_ATTN_NOPV
+        return;
+#endif
+        const uint32_t b_lo = v_lo0 + vslot * TILE16;
 #pragma unroll
         for (int ks = hf * 4; ks < hf * 4 + 4; ++ks) {
-          const uint64_t vd = make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024);
+          const uint64_t vd = make_desc(b_lo + ks * 128, kDescHiSw128);  // 16 keys = 2048 B
           if (P_TMEM) {
             umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, vd, idesc_pv, (acc || ks != 0) ? 1u : 0u);
           } else {
-            const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-            umma_ss(tmem + 256 + i * 128, make_smem_desc_sw128(p_base + i * ATT_TILE_BYTES + off, 16, 1024), vd,
-                    idesc_pv, (acc || ks != 0) ? 1u : 0u);
+            const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;
+            umma_ss(tmem + 256 + i * 128, make_desc(p_lo + i * TILE16 + off, kDescHiSw128), vd, idesc_pv,
+                    (acc || ks != 0) ? 1u : 0u);
           }
         }
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[stage], phase);  // K(0)
+      MMA_WAIT(q_full, 0);
+      MMA_WAIT(&kv_full[stage], phase);  // K(0)
       tc_fence_after();
-      {
-        const uint32_t k_addr = kv_base + stage * ATT_TILE_BYTES;
-        issue_qk(0, k_addr);
+      if (elect_one()) {
+        issue_qk(0, stage);
         tc_commit(&s_full[0]);
-        issue_qk(1, k_addr);
+        issue_qk(1, stage);
         tc_commit(&s_full[1]);
         tc_commit(&kv_empty[stage]);
-        if (++stage == NS) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == NS) { stage = 0; phase ^= 1; }
       for (int j = 0; j < T; ++j) {
         const bool more = (j + 1 < T);
         const int vs = stage;
-        mbar_wait(&kv_full[vs], phase);  // V(j)
+        MMA_WAIT(&kv_full[vs], phase);  // V(j)
+        PROBE(0, j, 0);
         if (++stage == NS) { stage = 0; phase ^= 1; }
         const int ks_ = stage;
-        const uint32_t v_addr = kv_base + vs * ATT_TILE_BYTES;
-        const uint32_t k_addr = kv_base + ks_ * ATT_TILE_BYTES;
-        mbar_wait(&p_full[0], j & 1);
+        if (more) MMA_WAIT(&kv_full[ks_], phase);  // K(j+1): landed long ago (it trails V(j) in the ring)
+        P_WAIT(&p_full[0], j & 1);
+        PROBE(0, j, 1);
         tc_fence_after();
-        issue_pv(0, v_addr, j > 0, 0);
-        mbar_wait(&p_full[1], j & 1);
+        if (elect_one()) issue_pv(0, vs, j > 0, 0);
+        __syncwarp();
+        P_WAIT(&p_full[1], j & 1);
+        PROBE(0, j, 2);
+        PROBE(0, j, 3);
         tc_fence_after();
-        issue_pv(0, v_addr, j > 0, 1);
-        if (more) {
-          mbar_wait(&kv_full[ks_], phase);  // K(j+1)
-          tc_fence_after();
-          issue_qk(0, k_addr);
-          tc_commit(&s_full[0]);
+        if (elect_one()) {
+          issue_pv(0, vs, j > 0, 1);
+          if (more) {
+            issue_qk(0, ks_);
+            tc_commit(&s_full[0]);
+          }
         }
-        mbar_wait(&p_full[2], j & 1);
+        __syncwarp();
+        P_WAIT(&p_full[2], j & 1);
+        PROBE(0, j, 4);
         tc_fence_after();
-        issue_pv(1, v_addr, j > 0, 0);
-        mbar_wait(&p_full[3], j & 1);
+        if (elect_one()) issue_pv(1, vs, j > 0, 0);
+        __syncwarp();
+        P_WAIT(&p_full[3], j & 1);
+        PROBE(0, j, 5);
         tc_fence_after();
-        issue_pv(1, v_addr, j > 0, 1);
-        tc_commit(&kv_empty[vs]);
+        if (elect_one()) {
+          issue_pv(1, vs, j > 0, 1);
+          tc_commit(&kv_empty[vs]);
+          if (more) {
+            issue_qk(1, ks_);
+            tc_commit(&s_full[1]);
+            tc_commit(&kv_empty[ks_]);
+          }
+        }
+        __syncwarp();
         if (more) {
-          issue_qk(1, k_addr);
-          tc_commit(&s_full[1]);
-          tc_commit(&kv_empty[ks_]);
           if (++stage == NS) { stage = 0; phase ^= 1; }
         }
+        PROBE(0, j, 6);
       }
-      tc_commit(&o_full[0]);
-      tc_commit(&o_full[1]);
+      if (elect_one()) {
+        tc_commit(&o_full[0]);
+        tc_commit(&o_full[1]);
+      }
+      __syncwarp();
     }
   }
   } else {
@@ -256,9 +340,43 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
     float m_run = -INFINITY, l_run = 0.f;
 
     const uint64_t sl2_2 = pack2(sl2, sl2);
+#ifdef FX_ATTN_PROBE
+    const bool probe_on_sm = probe_on && quarter == 0;
+#define SPROBE(j, ev) do { if (probe_on_sm && (j) < 64) g_attn_probe[((1 + i) * 64 + (j)) * 8 + (ev)] = probe_clock(); } while (0)
+#else
+#define SPROBE(j, ev) do {} while (0)
+#endif
+#ifdef FX_ATTN_MMAONLY
+#ifdef FX_ATTN_FREELD  // contention generator: unsynchronised TMEM reads of S (and writes of P) while the MMAs run
     for (int j = 0; j < T; ++j) {
+      uint32_t sv[128];
+      __syncwarp();
+      tmem_ld_x32(s_addr, sv);
+      tmem_ld_x32(s_addr + 32, sv + 32);
+      tmem_ld_x32(s_addr + 64, sv + 64);
+      tmem_ld_x32(s_addr + 96, sv + 96);
+      tmem_ld_wait();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int e = 0; e < 128; ++e) acc ^= sv[e];
+      if (acc == 0x12345u) l_run += 1.f;
+#ifdef FX_ATTN_FREEST
+      tmem_st_x16(s_addr, sv);
+      tmem_st_x16(s_addr + 16, sv + 16);
+      tmem_st_x16(s_addr + 32, sv + 32);
+      tmem_st_x16(s_addr + 48, sv + 48);
+      tmem_st_wait();
+#endif
+      for (int w = 0; w < FX_ATTN_FREELD; ++w) __nanosleep(100);
+    }
+#endif
+    for (int j = 0; j < 0; ++j) {
+#else
+    for (int j = 0; j < T; ++j) {
+#endif
       const int kv_valid = min(128, p.seq - j * 128);
       mbar_wait(&s_full[i], j & 1);
+      SPROBE(j, 0);
       tc_fence_after();
       // the whole S row (128 fp32) lives in registers: one TMEM read per tile
       uint32_t sv[128];
@@ -268,11 +386,47 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       tmem_ld_x32(s_addr + 64, sv + 64);
       tmem_ld_x32(s_addr + 96, sv + 96);
       tmem_ld_wait();
+      SPROBE(j, 1);
       if (kv_valid < 128) {  // ragged last tile: keys beyond seq do not exist
 #pragma unroll
         for (int e = 0; e < 128; ++e)
           if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
       }
+      // p = exp2(s * scale_log2 - m_run) for one 32-key chunk, packed two at a time
+      auto exp_chunk = [&](int c, uint32_t* dst, uint32_t* pk, uint64_t nm2) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
+          float p0, p1;
+          if (EMU_MASK & (1u << ((e >> 1) & 7))) {  // compile-time pattern: which pairs go to the FMA pipe
+            exp2_emu2(t2, p0, p1);
+          } else {
+            const float2 t = unpack2(t2);
+            p0 = fast_exp2(t.x);
+            p1 = fast_exp2(t.y);
+          }
+          dst[e] = __float_as_uint(p0);
+          dst[e + 1] = __float_as_uint(p1);
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+      };
+      // The running maximum is LAZY (it only moves when a tile exceeds it by more than 2^8), so the first
+      // chunk's exponentials are issued speculatively against the current m_run while the row maximum of the
+      // tile is still being reduced on the ALU pipe: the ~400-clock max chain leaves the S -> P -> PV critical
+      // path.  Only when some row's maximum did grow (the first tiles of a row, then almost never) is the
+      // chunk recomputed after the rescale.  The two warpgroups take turns on the exp phase (the MUFU of a
+      // sub-partition serves one warp of each); the row sum is accumulated AFTER P has been handed over.
+      SPROBE(j, 2);
+      if (p.sequence) mbar_wait(&seq_bar[i], (i == 0) ? ((j & 1) ^ 1) : (j & 1));
+      SPROBE(j, 3);
+      uint64_t nm2 = pack2(-m_run, -m_run);
+      uint32_t pa[32], pk0[16];
+#ifndef FX_ATTN_NOSPEC
+      exp_chunk(0, pa, pk0, nm2);
+#endif
+#ifdef FX_ATTN_NOMAX  // timing ablation only (wrong numerics)
+      float mx = __uint_as_float(sv[0]);
+#else
       float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
       float mxb = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
 #pragma unroll
@@ -281,8 +435,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         mxb = fmax3(mxb, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
       }
       mx = fmaxf(mx, mxb);
+#endif
       const float m_new = fmaxf(m_run, mx * sl2);
       const bool need = (m_new - m_run) > 8.0f;
+      bool redo = false;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
         if (need) {
@@ -302,29 +458,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           }
           tmem_st_wait();
         }
+        nm2 = pack2(-m_run, -m_run);
+        redo = true;
       }
-      // probabilities: p = exp2(s * scale_log2 - m_run), packed two at a time.  The two warpgroups take
-      // turns (the MUFU of a sub-partition serves one warp of each), and the row sum is accumulated AFTER
-      // P has been handed to the MMA warp -- neither sits on the critical path S -> P -> PV.
-      if (p.sequence) mbar_wait(&seq_bar[i], (i == 0) ? ((j & 1) ^ 1) : (j & 1));
-      const uint64_t nm2 = pack2(-m_run, -m_run);
+#ifdef FX_ATTN_NOSPEC
+      exp_chunk(0, pa, pk0, nm2);
+#else
+      if (redo) exp_chunk(0, pa, pk0, nm2);
+#endif
+#pragma unroll
+      for (int e = 0; e < 32; ++e) sv[e] = pa[e];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
+        if (c == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
-          float p0, p1;
-          if (EMU_MASK & (1u << ((e >> 1) & 7))) {  // compile-time pattern: which pairs go to the FMA pipe
-            exp2_emu2(t2, p0, p1);
-          } else {
-            const float2 t = unpack2(t2);
-            p0 = fast_exp2(t.x);
-            p1 = fast_exp2(t.y);
-          }
-          sv[c * 32 + e] = __float_as_uint(p0);
-          sv[c * 32 + e + 1] = __float_as_uint(p1);
-          pk[e >> 1] = pack_bf16(p0, p1);
+          for (int e = 0; e < 16; ++e) pk[e] = pk0[e];
+        } else {
+          exp_chunk(c, sv + c * 32, pk, nm2);
         }
         if (P_TMEM) {
           tmem_st_x16(s_addr + c * 16, pk);
@@ -350,8 +501,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[2 * i + (c >> 1)]);
+          SPROBE(j, 4 + (c >> 1));
         }
       }
+#ifdef FX_ATTN_NOSUM  // timing ablation only (wrong numerics)
+      l_run += __uint_as_float(sv[0]);
+#else
       {
         uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
 #pragma unroll
@@ -362,6 +517,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         const float2 ls = unpack2(fadd2(ls0, ls1));
         l_run += ls.x + ls.y;
       }
+#endif
+      SPROBE(j, 6);
     }
 
     // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
@@ -391,6 +548,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+#ifdef FX_ATTN_PROBE
+  if (probe_on && warp == ATT_WARP_MMA) {
+    g_attn_probe[(0 * 64 + 63) * 8 + 1] = probe_clock();
+    g_attn_probe[(0 * 64 + 63) * 8 + 3] = probe_gtime();
+  }
+#endif
   if (warp == ATT_WARP_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -816,6 +979,14 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   }
   return launch_attn<true>(a, tq, tk, tv, p, (cudaStream_t)stream);
 }
+
+#ifdef FX_ATTN_PROBE
+extern "C" int fx_dbg_attn_probe(void* buf) {  // profiling builds only: device buffer of 3*64*8 int64
+  long long* b = (long long*)buf;
+  FX_CUDA(cudaMemcpyToSymbol(fx::g_attn_probe, &b, sizeof(b)));
+  return FX_OK;
+}
+#endif
 
 extern "C" int fx_attention_small(const fx_attn_small_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention_small: null pointer");

@@ -33,10 +33,10 @@ static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   p.group_m = p.tiles_m < gm ? p.tiles_m : gm;
 }
 
-template <int BN, int EPI, bool CONV, int NCTA = 1>
+template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, NCTA>;
-  auto kern = gemm_kernel<BN, EPI, CONV, NCTA>;
+  auto kern = gemm_kernel<BN, EPI, CONV, NCTA, F8>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -88,6 +88,33 @@ static int launch_bn(int bn, int ncta, const CUtensorMap& ta, const CUtensorMap&
 
 static int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
 
+// FP8 (e4m3) operands: only the wide CTA-pair tiles are instantiated (the quantised path covers the big
+// Linear layers of the MMDiT blocks, all N >= 3072)
+template <int EPI>
+static int launch_f8(int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  if (ncta == 2) return launch<256, EPI, false, 2, true>(ta, tw, p, st);
+  return launch<256, EPI, false, 1, true>(ta, tw, p, st);
+}
+
+// A [batch][rows][K] and W [N][K] tensor maps; esz = bytes per element (2 bf16, 1 e4m3); the box is always
+// 128 bytes of K by (128 | bn / ncta) rows
+static int make_operand_maps(CUtensorMap* ta, CUtensorMap* tw, const void* A, int64_t lda, int64_t a_bs, const void* W,
+                             int64_t ldw, int batch, int rows, int N, int K, int bn, int ncta, int esz) {
+  const bool u8 = esz == 1;
+  const uint32_t bk = 128 / esz;
+  {
+    const uint64_t dims[3] = {(uint64_t)K, (uint64_t)rows, (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)lda * esz, (uint64_t)(batch > 1 ? a_bs : lda * (int64_t)rows) * esz};
+    const uint32_t box[3] = {bk, GEMM_BM, 1};
+    int rc = make_tmap_bf16(ta, A, 3, dims, strides, box, u8);
+    if (rc) return rc;
+  }
+  const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+  const uint64_t strides[1] = {(uint64_t)ldw * esz};
+  const uint32_t box[2] = {bk, (uint32_t)(bn / ncta)};
+  return make_tmap_bf16(tw, W, 2, dims, strides, box, u8);
+}
+
 }  // namespace fx
 
 using namespace fx;
@@ -96,12 +123,15 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->A && a->W && a->out, "fx_gemm: null pointer");
   FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm: empty problem (batch %d rows %d N %d K %d)",
              a->batch, a->rows, a->N, a->K);
-  FX_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->a_bs % 8 == 0,
-             "fx_gemm: K, lda, ldw, a_bs must be multiples of 8 elements (TMA 16-byte strides)");
+  const int esz = a->fp8 ? 1 : 2;
+  FX_REQUIRE(a->K % (16 / esz) == 0 && a->lda % (16 / esz) == 0 && a->ldw % (16 / esz) == 0 && a->a_bs % (16 / esz) == 0,
+             "fx_gemm: K, lda, ldw, a_bs must be multiples of 16 bytes (TMA strides)");
   FX_REQUIRE(aligned16(a->A) && aligned16(a->W), "fx_gemm: A and W must be 16-byte aligned");
+  FX_REQUIRE(!a->fp8 || (a->a_scale && a->w_scale && a->N > 128), "fx_gemm: fp8 needs a_scale, w_scale and N > 128");
   GemmParams p{};
   p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
-  p.k_blocks = (a->K + GEMM_BK - 1) / GEMM_BK;
+  p.k_blocks = (a->K * esz + 127) / 128;
+  p.a_scale = a->a_scale; p.a_scale_bs = a->a_scale_bs; p.w_scale = a->w_scale;
   p.bias = (const __nv_bfloat16*)a->bias;
   p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
@@ -110,20 +140,9 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   const int ncta = want_ncta(bn);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), bn);
   CUtensorMap ta, tw;
-  {
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a->batch > 1 ? a->a_bs : a->lda * (int64_t)a->rows) * 2};
-    const uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
-    int rc = make_tmap_bf16(&ta, a->A, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {GEMM_BK, (uint32_t)(bn / ncta)};
-    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
-    if (rc) return rc;
-  }
+  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, bn, ncta, esz);
+  if (rc) return rc;
+  if (a->fp8) return launch_f8<EPI_GENERIC>(ncta, ta, tw, p, (cudaStream_t)stream);
   return launch_bn<EPI_GENERIC, false>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
 }
 
@@ -134,12 +153,15 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   FX_REQUIRE(a->N >= D3 && a->N % 128 == 0, "fx_gemm_qkv: N (%d) must be >= 3*heads*128 and a multiple of 128", a->N);
   FX_REQUIRE(a->N == D3 || a->mlp_out, "fx_gemm_qkv: mlp_out required when N > 3*heads*128");
   FX_REQUIRE(a->seq_off >= 0 && a->seq_off + a->rows <= a->seq_total, "fx_gemm_qkv: rows exceed seq_total");
-  FX_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->a_bs % 8 == 0 && a->ld_mlp % 8 == 0 &&
-                 a->mlp_bs % 8 == 0,
-             "fx_gemm_qkv: strides must be multiples of 8 elements");
+  const int esz = a->fp8 ? 1 : 2;
+  FX_REQUIRE(a->K % (16 / esz) == 0 && a->lda % (16 / esz) == 0 && a->ldw % (16 / esz) == 0 && a->a_bs % (16 / esz) == 0 &&
+                 a->ld_mlp % 8 == 0 && a->mlp_bs % 8 == 0,
+             "fx_gemm_qkv: strides must be multiples of 16 bytes");
+  FX_REQUIRE(!a->fp8 || (a->a_scale && a->w_scale), "fx_gemm_qkv: fp8 needs a_scale and w_scale");
   GemmParams p{};
   p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
-  p.k_blocks = (a->K + GEMM_BK - 1) / GEMM_BK;
+  p.k_blocks = (a->K * esz + 127) / 128;
+  p.a_scale = a->a_scale; p.a_scale_bs = a->a_scale_bs; p.w_scale = a->w_scale;
   p.bias = (const __nv_bfloat16*)a->bias;
   p.out = a->mlp_out; p.ldo = a->ld_mlp; p.out_bs = a->mlp_bs; p.out_f32 = 0; p.act = FX_ACT_GELU_TANH;
   p.heads = a->heads; p.seq_total = a->seq_total; p.seq_off = a->seq_off; p.rms_eps = a->rms_eps;
@@ -149,20 +171,9 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   const int ncta = want_ncta(256);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);
   CUtensorMap ta, tw;
-  {
-    const uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->rows, (uint64_t)a->batch};
-    const uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)(a->batch > 1 ? a->a_bs : a->lda * (int64_t)a->rows) * 2};
-    const uint32_t box[3] = {GEMM_BK, GEMM_BM, 1};
-    int rc = make_tmap_bf16(&ta, a->A, 3, dims, strides, box);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
-    const uint64_t strides[1] = {(uint64_t)a->ldw * 2};
-    const uint32_t box[2] = {GEMM_BK, (uint32_t)(256 / ncta)};
-    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
-    if (rc) return rc;
-  }
+  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, 256, ncta, esz);
+  if (rc) return rc;
+  if (a->fp8) return launch_f8<EPI_QKV>(ncta, ta, tw, p, (cudaStream_t)stream);
   if (ncta == 2) return launch<256, EPI_QKV, false, 2>(ta, tw, p, (cudaStream_t)stream);
   return launch<256, EPI_QKV, false>(ta, tw, p, (cudaStream_t)stream);
 }

@@ -1,4 +1,4 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A . W^T)
+// Persistent warp-specialised bf16 (or FP8 e4m3, template F8) GEMM for sm_100a:  out = epilogue(A . W^T)
 //   A  [batch][rows][K]   bf16, K contiguous (activations; or NHWC image read through a 4-D TMA box
 //                         for the 3x3 convolution mode -- implicit GEMM, no im2col buffer)
 //   W  [N][K]             bf16, K contiguous (nn.Linear layout / OHWI conv weights flattened)
@@ -11,7 +11,7 @@
 namespace fx {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle span (FP8: 128 e4m3 elements in the same 128 B)
 constexpr int GEMM_THREADS = 384;  // warps 0..7 epilogue (two per TMEM lane quarter), warp 8 TMA, warp 9 MMA, (10, 11 idle)
 // The warp scheduler favours higher warp ids: the single-thread TMA / MMA issuers sit ABOVE the epilogue
 // warps so that a compute-heavy epilogue (GELU, RoPE) can never starve the tensor pipe of instructions.
@@ -41,6 +41,11 @@ struct GemmParams {
   const __nv_bfloat16 *qnorm_w, *knorm_w;
   const uint32_t* pe;  // [seq_total][64] (cos, sin) bf16 pairs
   __nv_bfloat16 *q, *k, *v;  // [batch][heads][seq_total][128]
+  // ---- FP8 mode (F8): A, W are e4m3 with per-row / per-output-channel dequantisation scales,
+  //      acc * a_scale[b][row] * w_scale[n] enters the epilogue in place of the raw accumulator
+  const float* a_scale;
+  long long a_scale_bs;
+  const float* w_scale;
   // ---- 3x3 conv mode (A is [batch][H][W][C] NHWC, pad 1, stride 1)
   int conv_H, conv_W, conv_tiles_x, conv_tiles_y, cin_blocks;
 };
@@ -55,7 +60,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // after the barriers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 256 * 4 /*epilogue staging*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 384 * 4 /*epilogue staging*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void gemm_tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
@@ -85,13 +90,24 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
 // come from this warp's shared-memory staging area `sb` / `sg` (floats, already bounds-checked: bias 0 /
 // gate 1 past N); the row's residual values may have been prefetched into `rr` before the accumulator
 // was ready (rr_ok), so that no long-latency load sits between the TMEM read and the store.
+template <bool F8 = false>
 __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f, const float* sb, const float* sg,
                                                   const uint4* rr, bool rr_ok, long long out_off, long long res_off,
-                                                  int n0, bool fast) {
+                                                  int n0, bool fast, const float* sw = nullptr, float rs = 1.f) {
+  if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(sb + i);
+      const float4 w = *reinterpret_cast<const float4*>(sw + i);
+      f[i] = fmaf(f[i], rs * w.x, t.x); f[i + 1] = fmaf(f[i + 1], rs * w.y, t.y);
+      f[i + 2] = fmaf(f[i + 2], rs * w.z, t.z); f[i + 3] = fmaf(f[i + 3], rs * w.w, t.w);
+    }
+  } else {
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
     const float4 t = *reinterpret_cast<const float4*>(sb + i);
     f[i] += t.x; f[i + 1] += t.y; f[i + 2] += t.z; f[i + 3] += t.w;
+  }
   }
   if (p.act == 1) {
 #ifdef FX_GELU_SCALAR
@@ -166,8 +182,11 @@ __device__ __forceinline__ void stage_vec(float* dst, const __nv_bfloat16* src, 
                                           int lane) {
   for (int i = lane; i < n; i += 32) dst[i] = (src != nullptr && n0 + i < limit) ? __bfloat162float(__ldg(src + n0 + i)) : fill;
 }
+__device__ __forceinline__ void stage_vec_f32(float* dst, const float* src, int n0, int n, int limit, float fill, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = (src != nullptr && n0 + i < limit) ? __ldg(src + n0 + i) : fill;
+}
 
-template <int BN, int EPI, bool CONV, int NCTA = 1>
+template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
@@ -185,6 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int KE = F8 ? 2 * GEMM_BK : GEMM_BK;  // K elements per 128-byte stage row
 
   if (warp == GEMM_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -245,9 +265,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
               tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
             } else {
-              tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
+              tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
             }
-            tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * GEMM_BK, tn * BN + int(cta_rank) * (BN / 2));
+            tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN + int(cta_rank) * (BN / 2));
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {
@@ -255,9 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
             tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
           } else {
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, tmb * GEMM_BM, b);
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * GEMM_BM, b);
           }
-          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * GEMM_BK, tn * BN);
+          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -266,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   } else if (warp == GEMM_WARP_MMA) {
     // ================= MMA issuer =================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM * NCTA, BN, 0, 0);
+      constexpr uint32_t idesc = F8 ? make_idesc_f8(GEMM_BM * NCTA, BN) : make_idesc_bf16(GEMM_BM * NCTA, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -284,8 +304,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (NCTA == 2) umma2_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (F8) {
+              if (NCTA == 2) umma2_ss_f8(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss_f8(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
+              if (NCTA == 2) umma2_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           if (NCTA == 2) tc_commit2(&empty_bar[stage]);
           else tc_commit(&empty_bar[stage]);
@@ -303,8 +328,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - GEMM_EPI0) >> 2;  // which half of the tile's columns this warp owns
     const int r = quarter * 32 + lane;
-    float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - GEMM_EPI0) * 256;  // bias (<= 128 floats)
+    float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - GEMM_EPI0) * 384;  // bias (<= 128 floats)
     float* sg = sb + 128;                                                           // gate / norm weight
+    float* sw = sb + 256;                                                           // FP8: per-column weight scales
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
@@ -339,6 +365,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         __syncwarp();
         stage_vec(sb, p.bias, nw0, WN, p.N, 0.f, lane);
         if (p.gate) stage_vec(sg, p.gate + (long long)b * p.gate_bs, nw0, WN, p.N, 1.f, lane);
+        float rs = 1.f;
+        if (F8) {
+          stage_vec_f32(sw, p.w_scale, nw0, WN, p.N, 0.f, lane);
+          if (valid) rs = __ldg(p.a_scale + (long long)b * p.a_scale_bs + row);
+        }
         const bool rr_ok = p.resid != nullptr && valid && vec_ok && (nw0 + WN <= p.N);
         uint4 rcur[4], rnxt[4];
         if (rr_ok) {
@@ -364,8 +395,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-            epi_generic_chunk(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0,
-                              vec_ok && (n0 + 32 <= p.N));
+            epi_generic_chunk<F8>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0,
+                                  vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
@@ -382,8 +413,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // ---- before the accumulator wait: bias / norm weight to smem, first RoPE chunk to registers
         uint4 pcur[4], pnxt[4];
         __syncwarp();
+        float rs = 1.f;
         if (active) {
           stage_vec(sb, p.bias, g0, 128, p.N, 0.f, lane);
+          if (F8) {
+            stage_vec_f32(sw, p.w_scale, g0, 128, p.N, 0.f, lane);
+            if (valid) rs = __ldg(p.a_scale + (long long)b * p.a_scale_bs + row);
+          }
           if (which < 2) {
             stage_vec(sg, which == 0 ? p.qnorm_w : p.knorm_w, 0, 128, 128, 1.f, lane);
             if (valid) {
@@ -410,7 +446,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                epi_generic_chunk(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true);
+                epi_generic_chunk<F8>(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true, sw + c * 32, rs);
               }
             }
           } else {
@@ -429,8 +465,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
-                  const float x0 = __uint_as_float(v[i]) + t.x, x1 = __uint_as_float(v[i + 1]) + t.y;
-                  const float x2 = __uint_as_float(v[i + 2]) + t.z, x3 = __uint_as_float(v[i + 3]) + t.w;
+                  float x0, x1, x2, x3;
+                  if (F8) {
+                    const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
+                    x0 = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); x1 = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
+                    x2 = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); x3 = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
+                  } else {
+                    x0 = __uint_as_float(v[i]) + t.x; x1 = __uint_as_float(v[i + 1]) + t.y;
+                    x2 = __uint_as_float(v[i + 2]) + t.z; x3 = __uint_as_float(v[i + 3]) + t.w;
+                  }
                   ss += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
                 }
               }
@@ -451,8 +494,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
+                  if (F8) {
+                    const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
+                    f[i] = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); f[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
+                    f[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); f[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
+                  } else {
                   f[i] = __uint_as_float(v[i]) + t.x; f[i + 1] = __uint_as_float(v[i + 1]) + t.y;
                   f[i + 2] = __uint_as_float(v[i + 2]) + t.z; f[i + 3] = __uint_as_float(v[i + 3]) + t.w;
+                  }
                 }
                 if (which < 2) {
 #pragma unroll

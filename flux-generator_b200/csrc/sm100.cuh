@@ -121,6 +121,22 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
+// FP8 (e4m3 x e4m3 -> f32, kind::f8f6f4): K = 32 per instruction (32 bytes of each operand row, the same
+// byte geometry as K = 16 in bf16), twice the MACs per tensor-pipe cycle.
+__device__ __forceinline__ void umma_ss_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+//   idesc: c_format = f32 (1), a_format = b_format = 0 (E4M3), K-major operands
+__host__ __device__ constexpr uint32_t make_idesc_f8(int M, int N) {
+  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor bit layout): bf16 x bf16 -> f32.
 //   [4,6) c_format=1 (f32)  [7,10) a_format=1 (bf16)  [10,13) b_format=1 (bf16)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
@@ -143,6 +159,26 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= uint64_t(1) << 46;
   d |= uint64_t(2) << 61;
   return d;
+}
+
+// Descriptor from a precomputed low word ((smem_addr >> 4) | LBO field << 16) and a constant high word:
+// per-instruction operand advance is then ONE integer add on the low word.  kDescHiSw128: SBO = 1024 B,
+// descriptor version 1, 128-byte swizzle.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// one lane of a converged warp (the lowest): the thread that issues tcgen05.mma / commit / TMA
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
@@ -204,6 +240,15 @@ __device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_ss_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }

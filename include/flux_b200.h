@@ -57,6 +57,12 @@ typedef struct fx_gemm_args {
   const void* gate; int64_t gate_bs;               /* [batch][N] multiplier or NULL */
   const void* resid; int64_t ldr; int64_t resid_bs; /* [batch][rows][N] addend or NULL (may alias out) */
   int32_t batch, rows, N, K;
+  /* --quantize (txt2image.py:56,79-82; the reference's MLX 4-bit nn.quantize becomes FP8 here): when fp8 != 0,
+   * A and W hold e4m3 bytes produced by fx_quantize_rows / fx_rownorm(out_fp8); the accumulator is
+   * multiplied by a_scale[b][row] * w_scale[n] before the epilogue.  N > 128 (wide tiles only). */
+  int32_t fp8;
+  const float* a_scale; int64_t a_scale_bs;         /* [batch][rows] */
+  const float* w_scale;                             /* [N] */
 } fx_gemm_args;
 /* v = A.W^T + bias; v = act(v); v *= gate[b][n]; v += resid[b][r][n]   (each optional) */
 int fx_gemm(const fx_gemm_args* a, fx_stream stream);
@@ -76,6 +82,9 @@ typedef struct fx_qkv_args {
   void* mlp_out; int64_t ld_mlp; int64_t mlp_bs; /* [batch][seq_total][ld_mlp] (row = seq_off + r) or NULL */
   float rms_eps;
   int32_t batch, rows, N, K, heads, seq_total, seq_off;
+  int32_t fp8;                 /* as fx_gemm_args.fp8 */
+  const float* a_scale; int64_t a_scale_bs;
+  const float* w_scale;
 } fx_qkv_args;
 int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream);
 
@@ -206,6 +215,12 @@ int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, floa
  * [K][N] (MN-major); D float [128][N]. */
 int fx_dbg_umma_tile(const void* A, const void* B, float* D, int32_t K, int32_t N, int32_t b_mn_major,
                      int32_t a_tmem, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, fx_stream stream);
+
+/* Tensor-pipe issue-pattern micro-benchmark (profiling only): every SM's CTA has one thread issue `iters`
+ * steps of 32 tcgen05.mma (128x128x16) in one of a dozen fixed orders (the attention kernel's QK / PV
+ * sequence with and without commits, single-kind streams, N = 256, two issuing threads ...) on the attention
+ * kernel's shared-memory / TMEM layout; writes the SM-clock count of CTA 0 to clocks_out[0]. */
+int fx_dbg_mma_pattern(int32_t pattern, int32_t iters, int64_t* clocks_out, fx_stream stream);
 
 #ifdef __cplusplus
 }

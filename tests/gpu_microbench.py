@@ -8,7 +8,17 @@ import time
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flux-generator_b200"))
-from flux import ops  # noqa: E402
+from flux import _native, ops  # noqa: E402
+
+if os.environ.get("MB_ALLOW_MISSING"):  # A/B against an older build of the library that lacks newer debug symbols
+    for _k in [k for k in _native.SYMBOLS if k.startswith("fx_dbg_")]:
+        _native.SYMBOLS.pop(_k)
+try:
+    import pynvml
+    pynvml.nvmlInit()
+    _nv = pynvml.nvmlDeviceGetHandleByIndex(0)
+except Exception:  # noqa: BLE001
+    _nv = None
 
 dev, bf = "cuda", torch.bfloat16
 SECONDS = float(os.environ.get("MB_SECONDS", "1.5"))
@@ -29,7 +39,16 @@ def sustained(fn, flops):
         n += 10
         if n % 50 == 0:
             torch.cuda.current_stream().synchronize()
+            for _ in range(30):
+                fn()
+            n += 30
     e1.record()
+    global last_clock
+    last_clock = ""
+    if _nv is not None:  # sampled while the queue is still draining: clocks / power UNDER load
+        mhz = pynvml.nvmlDeviceGetClockInfo(_nv, pynvml.NVML_CLOCK_SM)
+        watts = pynvml.nvmlDeviceGetPowerUsage(_nv) / 1000.0
+        last_clock = f"  [{mhz} MHz, {watts:.0f} W]"
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     return ms, flops / ms / 1e9
@@ -68,7 +87,7 @@ def main(which):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
         extra = f" = {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s" if name == "rownorm" else f" = {tf:.0f} TFLOP/s"
-        print(f"{name:10s} {ms:8.3f} ms{extra}", flush=True)
+        print(f"{name:10s} {ms:8.3f} ms{extra}{last_clock}", flush=True)
 
 
 if __name__ == "__main__":
