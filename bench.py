@@ -341,6 +341,19 @@ def main_arm(args) -> None:
     e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
     e2e_value = B * world * args.steps / (max(e2e_ms, e2e_wall) * 1e-3)
 
+    # ---- --quantize leg (reported beside the bf16 headline, never in its place): the block Linears as FP8 e4m3
+    # tcgen05 GEMMs (W8A8, per-row scales, fp32 accumulate); same workload, device-resident inputs
+    quant = None
+    if not args.no_quantized:
+        pipe.flow.quantize()
+        split_events.clear()
+        q_ms, _, q_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
+        quant = {"dtype": "fp8_e4m3 (block Linears W8A8, per-row scales, fp32 accumulate; attention / proj / VAE bf16)",
+                 "value": B * world * args.steps / (q_ms * 1e-3), "unit": UNIT, "ms_per_step": q_ms / args.steps,
+                 "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events) / len(split_events) / STEPS_DENOISE,
+                 "clocks": q_clocks, "flag": "txt2image.py --quantize / Flux.quantize()",
+                 "parity": "tests/test_gpu_fp8.py (own tolerance; the bf16 line above is the headline)"}
+
     if rank == 0:
         pk = peaks()
         gem = {"launches": 0, "ms": 0.0, "tflop": 0.0}
@@ -367,6 +380,7 @@ def main_arm(args) -> None:
             "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks,
             # BASELINE metric's second half: per-denoise-step ms (one MMDiT forward + Euler update over the 8 images)
             "ms_per_denoise_step": denoise_ms, "ms_vae_decode_batch": decode_ms,
+            "quantized": quant,
         }
         if not args.no_cpu:
             threads = os.cpu_count() or 1
@@ -389,6 +403,7 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the MMDiT forward from a CUDA graph")
+    ap.add_argument("--no-quantized", action="store_true", help="skip the FP8 (--quantize) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -2,6 +2,8 @@
 // embedding, Euler step, latent packing, GroupNorm(+SiLU), nearest upsample, row softmax, transpose,
 // image finish, embedding gather, gated activation.  All vectorised to 16-byte accesses, bf16 in HBM,
 // fp32 in registers.
+#include <cuda_fp8.h>
+
 #include "api_common.cuh"
 #include "sm100.cuh"
 
@@ -18,6 +20,23 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* f) {
   u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// FP8 row quantisation (--quantize): q = e4m3(x * inv), inv = 448 / absmax (round-to-nearest-even, saturating);
+// dequantisation scale = absmax * (1/448); an all-zero row gets inv = scale = 1.  Every operation is a single
+// IEEE fp32 operation, so the CPU oracle reproduces bytes and scales exactly.
+__device__ __forceinline__ float fp8_row_scale(float amax) { return amax > 0.f ? amax * (1.0f / 448.0f) : 1.0f; }
+__device__ __forceinline__ float fp8_row_inv(float amax) { return amax > 0.f ? __fdiv_rn(448.0f, amax) : 1.0f; }
+__device__ __forceinline__ uint2 quant8(const float* f, float inv) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = __nv_cvt_float2_to_fp8x2(make_float2(__fmul_rn(f[2 * i], inv), __fmul_rn(f[2 * i + 1], inv)), __NV_SATFINITE, __NV_E4M3);
+  return make_uint2(w[0] | (w[1] << 16), w[2] | (w[3] << 16));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -30,6 +49,7 @@ struct RowNormParams {
   __nv_bfloat16* out; long long ldo, out_bs;
   const __nv_bfloat16 *p0, *p1; long long p_bs;
   float eps; int mode, batch, rows, D;
+  float* scale_out; long long scale_bs;  // F8OUT: out holds e4m3 bytes, scale_out[b][r] the row's dequantisation scale
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -40,7 +60,7 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 // The row stays packed (bf16) in registers and is unpacked in each of the three passes: 48 instead of 96
 // data registers for D = 3072, so two 8-row blocks fit per SM instead of one (the kernel is a pure
 // HBM stream: more rows in flight = more bandwidth).
-template <int ITERS>  // ITERS = ceil(D / 256); D % 8 == 0
+template <int ITERS, bool F8OUT = false>  // ITERS = ceil(D / 256); D % 8 == 0
 __global__ void __launch_bounds__(256, 2) rownorm_kernel(const RowNormParams p) {
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -82,6 +102,11 @@ __global__ void __launch_bounds__(256, 2) rownorm_kernel(const RowNormParams p) 
   const float rstd = rsqrtf(warp_sum(ss) / float(p.D) + p.eps);
   const long long pb = (p.mode == 0) ? b * p.p_bs : 0;
   __nv_bfloat16* orow = p.out + b * p.out_bs + r * p.ldo;
+  uint8_t* qrow = reinterpret_cast<uint8_t*>(p.out) + b * p.out_bs + r * p.ldo;
+  // F8OUT: the modulated row is kept packed (bf16, 48 more registers for D = 3072) while its absmax is reduced,
+  // then quantised -- exactly quantize_rows(rownorm(x)) in one kernel: one HBM read, a half-size write
+  uint4 keep[F8OUT ? ITERS : 1];
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int c = i * 256 + lane * 8;
@@ -97,7 +122,102 @@ __global__ void __launch_bounds__(256, 2) rownorm_kernel(const RowNormParams p) 
       else if (p.mode == 1) o[j] = y * a[j] + s[j];      // p0 = weight, p1 = bias
       else o[j] = y * a[j];                              // p0 = weight
     }
-    store8(orow + c, o);
+    if (!F8OUT) {
+      store8(orow + c, o);
+    } else {
+      uint4 u;
+      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+      u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+      keep[i] = u;
+      unpack8(u, o);  // the absmax of the ROUNDED values
+#pragma unroll
+      for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(o[j]));
+    }
+  }
+  if (F8OUT) {
+    amax = warp_max(amax);
+    if (lane == 0) p.scale_out[b * p.scale_bs + r] = fp8_row_scale(amax);
+    const float inv = fp8_row_inv(amax);
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int c = i * 256 + lane * 8;
+      if (c >= p.D) continue;
+      float o[8];
+      unpack8(keep[i], o);
+      *reinterpret_cast<uint2*>(qrow + c) = quant8(o, inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ FP8 row quantisation: one warp per row
+// x bf16 [batch][rows][K] -> q e4m3 [batch][rows][K] + scale fp32 [batch][rows].  Two passes over the row; the
+// second one hits L1 / L2 (a row is at most 30 KB), so HBM sees one bf16 read and one byte-wide write.
+struct QuantParams {
+  const __nv_bfloat16* x; long long ldx, x_bs;
+  uint8_t* q; long long ldq, q_bs;
+  float* scale; long long scale_bs;
+  int batch, rows, K;
+};
+__global__ void __launch_bounds__(256) quantize_rows_kernel(const QuantParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gw >= (long long)p.batch * p.rows) return;
+  const int b = int(gw / p.rows);
+  const long long r = gw - (long long)b * p.rows;
+  const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
+  float amax = 0.f;
+  for (int c = lane * 8; c < p.K; c += 256) {
+    float v[8];
+    load8(xr + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+  }
+  amax = warp_max(amax);
+  if (lane == 0) p.scale[b * p.scale_bs + r] = fp8_row_scale(amax);
+  const float inv = fp8_row_inv(amax);
+  uint8_t* qr = p.q + b * p.q_bs + r * p.ldq;
+  for (int c = lane * 8; c < p.K; c += 256) {
+    float v[8];
+    load8(xr + c, v);
+    *reinterpret_cast<uint2*>(qr + c) = quant8(v, inv);
+  }
+}
+
+// Long rows (the attention | GELU(mlp) operand of linear2 / mlp.2, K = 12288 / 15360): one 256-thread block per
+// row, the row held packed in registers between the absmax reduction and the conversion -> a single HBM pass.
+template <int ITERS>  // ITERS = ceil(K / 2048)
+__global__ void __launch_bounds__(256) quantize_rows_block_kernel(const QuantParams p) {
+  __shared__ float s_max[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / p.rows;
+  const long long r = blockIdx.x - (long long)b * p.rows;
+  const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
+  uint4 raw[ITERS];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 2048 + tid * 8;
+    raw[i] = (c < p.K) ? *reinterpret_cast<const uint4*>(xr + c) : make_uint4(0, 0, 0, 0);
+    float v[8];
+    unpack8(raw[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+  }
+  amax = warp_max(amax);
+  if (lane == 0) s_max[warp] = amax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) amax = fmaxf(amax, s_max[w]);
+  if (tid == 0) p.scale[b * p.scale_bs + r] = fp8_row_scale(amax);
+  const float inv = fp8_row_inv(amax);
+  uint8_t* qr = p.q + b * p.q_bs + r * p.ldq;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 2048 + tid * 8;
+    if (c >= p.K) continue;
+    float v[8];
+    unpack8(raw[i], v);
+    *reinterpret_cast<uint2*>(qr + c) = quant8(v, inv);
   }
 }
 
@@ -503,11 +623,23 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
   FX_REQUIRE(a->ldx % 8 == 0 && a->ldo % 8 == 0 && a->x_bs % 8 == 0 && a->out_bs % 8 == 0 && a->p_bs % 8 == 0,
              "fx_rownorm: strides must be multiples of 8 elements");
   if (a->batch <= 0 || a->rows <= 0) return FX_OK;
+  FX_REQUIRE(!a->out_fp8 || (a->scale_out && a->ldo % 16 == 0 && a->out_bs % 16 == 0),
+             "fx_rownorm: out_fp8 needs scale_out and 16-byte aligned output rows");
   RowNormParams p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, (__nv_bfloat16*)a->out, a->ldo, a->out_bs,
-                  (const __nv_bfloat16*)a->p0, (const __nv_bfloat16*)a->p1, a->p_bs, a->eps, a->mode, a->batch, a->rows, a->D};
+                  (const __nv_bfloat16*)a->p0, (const __nv_bfloat16*)a->p1, a->p_bs, a->eps, a->mode, a->batch, a->rows, a->D,
+                  a->scale_out, a->scale_bs};
   const long long rows = (long long)a->batch * a->rows;
   const int blocks = int((rows + 7) / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (a->out_fp8) {
+    switch ((a->D + 255) / 256) {
+#define FX_RN(I) case I: rownorm_kernel<I, true><<<blocks, 256, 0, st>>>(p); break;
+      FX_RN(1) FX_RN(2) FX_RN(3) FX_RN(4) FX_RN(5) FX_RN(6) FX_RN(7) FX_RN(8)
+      FX_RN(9) FX_RN(10) FX_RN(11) FX_RN(12) FX_RN(13) FX_RN(14) FX_RN(15) FX_RN(16)
+#undef FX_RN
+    }
+    return launched("rownorm_kernel");
+  }
   switch ((a->D + 255) / 256) {
 #define FX_RN(I) case I: rownorm_kernel<I><<<blocks, 256, 0, st>>>(p); break;
     FX_RN(1) FX_RN(2) FX_RN(3) FX_RN(4) FX_RN(5) FX_RN(6) FX_RN(7) FX_RN(8)
@@ -515,6 +647,28 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
 #undef FX_RN
   }
   return launched("rownorm_kernel");
+}
+
+extern "C" int fx_quantize_rows(const fx_quant_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->x && a->q && a->scale, "fx_quantize_rows: null pointer");
+  FX_REQUIRE(a->K > 0 && a->K % 8 == 0 && a->ldx % 8 == 0 && a->x_bs % 8 == 0 && a->ldq % 8 == 0 && a->q_bs % 8 == 0,
+             "fx_quantize_rows: K and strides must be multiples of 8 elements");
+  FX_REQUIRE(aligned16(a->x) && (reinterpret_cast<uintptr_t>(a->q) & 7) == 0, "fx_quantize_rows: unaligned pointers");
+  if (a->batch <= 0 || a->rows <= 0) return FX_OK;
+  QuantParams p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, (uint8_t*)a->q, a->ldq, a->q_bs, a->scale, a->scale_bs,
+                a->batch, a->rows, a->K};
+  const long long rows = (long long)a->batch * a->rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->K > 2048 && a->K <= 16384 && rows < (1ll << 31)) {
+    switch ((a->K + 2047) / 2048) {
+#define FX_QB(I) case I: quantize_rows_block_kernel<I><<<(unsigned)rows, 256, 0, st>>>(p); break;
+      FX_QB(2) FX_QB(3) FX_QB(4) FX_QB(5) FX_QB(6) FX_QB(7) FX_QB(8)
+#undef FX_QB
+    }
+    return launched("quantize_rows_block_kernel");
+  }
+  quantize_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(p);
+  return launched("quantize_rows_kernel");
 }
 
 extern "C" int fx_gemv(const fx_gemv_args* a, fx_stream stream) {

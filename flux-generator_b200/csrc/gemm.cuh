@@ -60,7 +60,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;  // after the barriers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 384 * 4 /*epilogue staging*/ + 1024 /*align*/;
+  static constexpr int STORE_OFF = EPI_OFF + 8 * 384 * 4;    // per-warp 32 x 64 B transposition buffers for coalesced stores
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 8 * 384 * 4 /*epilogue staging*/ +
+                                    8 * 2048 /*store transposition*/ + 1024 /*align*/;
 };
 
 __device__ __forceinline__ void gemm_tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
@@ -86,6 +88,33 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Coalesced store of one 32-column bf16 chunk of a warp's 32 accumulator rows.  In the tcgen05.ld layout a
+// thread owns a ROW, so a direct store makes every lane write 16 bytes into a different 128-byte line (32 half-
+// filled sectors per request: ncu showed the LSU / L1 store path, not the tensor pipe, bounding the FP8 kernels).
+// The chunk is transposed through a per-warp 2 KB shared-memory buffer (XOR-swizzled: conflict-free both ways)
+// so that each store instruction writes 8 rows x 64 contiguous bytes = 16 full sectors.
+//   f: this lane's 32 values (row = lane); base: address of (row 0 of the warp, first column of the chunk);
+//   ld: row stride in elements; vmask: bit r set = row r exists.
+__device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, const float* f, __nv_bfloat16* base,
+                                                        long long ld, uint32_t vmask) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(f[8 * j], f[8 * j + 1]); u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+  }
+  __syncwarp();
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const uint4 u = *reinterpret_cast<const uint4*>(wst + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+    if ((vmask >> r) & 1u) *reinterpret_cast<uint4*>(base + r * ld + ch * 8) = u;
+  }
+  __syncwarp();
+}
+
 // One 32-column chunk of the generic epilogue for one accumulator row.  Tile-uniform vectors (bias, gate)
 // come from this warp's shared-memory staging area `sb` / `sg` (floats, already bounds-checked: bias 0 /
 // gate 1 past N); the row's residual values may have been prefetched into `rr` before the accumulator
@@ -93,7 +122,8 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
 template <bool F8 = false>
 __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f, const float* sb, const float* sg,
                                                   const uint4* rr, bool rr_ok, long long out_off, long long res_off,
-                                                  int n0, bool fast, const float* sw = nullptr, float rs = 1.f) {
+                                                  int n0, bool fast, const float* sw = nullptr, float rs = 1.f,
+                                                  uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true) {
   if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -143,7 +173,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
     }
   }
   if (fast) {
-    if (p.resid) {
+    if (p.resid && valid) {
       const __nv_bfloat16* r = p.resid + res_off + n0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -154,16 +184,21 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
       }
     }
     if (p.out_f32) {
-      float* o = reinterpret_cast<float*>(p.out) + out_off + n0;
+      if (valid) {
+        float* o = reinterpret_cast<float*>(p.out) + out_off + n0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4)
-        *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-    } else {
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+      }
+    } else if (wst != nullptr) {  // warp-collective: every lane takes part, rows are masked
+      store_chunk32_coalesced(wst, lane, f, reinterpret_cast<__nv_bfloat16*>(p.out) + out_off - (long long)lane * p.ldo + n0,
+                              p.ldo, vmask);
+    } else if (valid) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + n0;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) st_bf16x8(o + i, f + i);
     }
-  } else {
+  } else if (valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {  // static indices keep f[] in registers
       const int n = n0 + i;
@@ -331,6 +366,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - GEMM_EPI0) * 384;  // bias (<= 128 floats)
     float* sg = sb + 128;                                                           // gate / norm weight
     float* sw = sb + 256;                                                           // FP8: per-column weight scales
+    // conv tiles map accumulator rows to 8x16 pixel patches (row -> address is not affine): direct stores there
+    uint8_t* wst = CONV ? nullptr : smem + Cfg::STORE_OFF + (warp - GEMM_EPI0) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
@@ -350,6 +387,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         valid = row < p.rows;
       }
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
 
       // NOTE on code size: the chunk loops below are deliberately NOT unrolled.  A fully unrolled epilogue is
       // ~200 KB of SASS that eight warps stream through once per tile -> instruction-cache misses
@@ -391,12 +429,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           __syncwarp();
           tmem_ld_x32(taddr + half * WN + c * 32, v);
           tmem_ld_wait();
-          if (valid) {
+          {
             float f[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
             epi_generic_chunk<F8>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0,
-                                  vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs);
+                                  vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs, wst, lane, vmask, valid);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
@@ -442,11 +480,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               __syncwarp();
               tmem_ld_x32(ta + c * 32, v);
               tmem_ld_wait();
-              if (valid) {
+              {
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                epi_generic_chunk<F8>(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true, sw + c * 32, rs);
+                epi_generic_chunk<F8>(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true, sw + c * 32, rs,
+                                      wst, lane, vmask, valid);
               }
             }
           } else {
@@ -489,7 +528,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               __syncwarp();
               tmem_ld_x32(ta + c * 32, v);
               tmem_ld_wait();
-              if (valid) {
+              {  // every lane computes (rows past the end hold zeros / stale table values and are masked at the store)
                 float f[32];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -520,8 +559,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                   }
                 }
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) st_bf16x8(dst + c * 32 + i, f + i);
+                store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask);
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];

@@ -22,7 +22,8 @@ class GemmArgs(C.Structure):
     _fields_ = [("A", c_vp), ("lda", c_i64), ("a_bs", c_i64), ("W", c_vp), ("ldw", c_i64), ("bias", c_vp),
                 ("out", c_vp), ("ldo", c_i64), ("out_bs", c_i64), ("out_f32", c_i32), ("act", c_i32),
                 ("gate", c_vp), ("gate_bs", c_i64), ("resid", c_vp), ("ldr", c_i64), ("resid_bs", c_i64),
-                ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32)]
+                ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32),
+                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp)]
 
 
 class QkvArgs(C.Structure):
@@ -30,7 +31,8 @@ class QkvArgs(C.Structure):
                 ("q_scale", c_vp), ("k_scale", c_vp), ("pe", c_vp), ("q", c_vp), ("k", c_vp), ("v", c_vp),
                 ("mlp_out", c_vp), ("ld_mlp", c_i64), ("mlp_bs", c_i64), ("rms_eps", c_f32),
                 ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32), ("heads", c_i32),
-                ("seq_total", c_i32), ("seq_off", c_i32)]
+                ("seq_total", c_i32), ("seq_off", c_i32),
+                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp)]
 
 
 class ConvArgs(C.Structure):
@@ -52,7 +54,12 @@ class AttnSmallArgs(C.Structure):
 class RowNormArgs(C.Structure):
     _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_bs", c_i64), ("out", c_vp), ("ldo", c_i64), ("out_bs", c_i64),
                 ("p0", c_vp), ("p1", c_vp), ("p_bs", c_i64), ("eps", c_f32), ("mode", c_i32), ("batch", c_i32),
-                ("rows", c_i32), ("D", c_i32)]
+                ("rows", c_i32), ("D", c_i32), ("out_fp8", c_i32), ("scale_out", c_vp), ("scale_bs", c_i64)]
+
+
+class QuantArgs(C.Structure):
+    _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_bs", c_i64), ("q", c_vp), ("ldq", c_i64), ("q_bs", c_i64),
+                ("scale", c_vp), ("scale_bs", c_i64), ("batch", c_i32), ("rows", c_i32), ("K", c_i32)]
 
 
 class GemvArgs(C.Structure):
@@ -73,6 +80,7 @@ SYMBOLS = {
     "fx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),
     "fx_attention_small": (C.c_int, [C.POINTER(AttnSmallArgs), c_vp]),
     "fx_rownorm": (C.c_int, [C.POINTER(RowNormArgs), c_vp]),
+    "fx_quantize_rows": (C.c_int, [C.POINTER(QuantArgs), c_vp]),
     "fx_gemv": (C.c_int, [C.POINTER(GemvArgs), c_vp]),
     "fx_timestep_embedding": (C.c_int, [c_vp, c_vp, c_i32, c_i32, c_vp]),
     "fx_euler_step": (C.c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),

@@ -104,6 +104,7 @@ class Flux:
         self._ws: Dict[Tuple[int, int, int], dict] = {}
         self._pe_cache: Dict[tuple, torch.Tensor] = {}
         self._txt_cache: Optional[tuple] = None
+        self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
 
     # ------------------------------------------------------------------ weights
     def sanitize(self, weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -147,7 +148,49 @@ class Flux:
                 raise ValueError(f"Missing {len(missing)} parameters, e.g. {missing[:3]}")
         self._txt_cache = None
         self._graphs = {}
+        if self._q8:  # weights changed under a quantised model: requantise
+            self._q8 = {}
+            self.quantize()
         return self
+
+    # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
+    def quantized_keys(self) -> List[str]:
+        """The Linears that run in FP8 when quantised: the four big projections of every block (97 % of the
+        step's FLOPs).  The reference's predicate is `isinstance(m, nn.Linear) and in_dim % 512 == 0` with MLX
+        4-bit groups (txt2image.py:79-82); attention `proj`, the embedders and the modulation GEMVs stay bf16."""
+        p = self.params
+        keys = []
+        for i in range(p.depth):
+            for s in ("img", "txt"):
+                keys += [f"double_blocks.{i}.{s}_attn.qkv", f"double_blocks.{i}.{s}_mlp.0", f"double_blocks.{i}.{s}_mlp.2"]
+        for i in range(p.depth_single_blocks):
+            keys += [f"single_blocks.{i}.linear1", f"single_blocks.{i}.linear2"]
+        return keys
+
+    def quantize(self) -> "Flux":
+        """Quantise the block Linears to FP8 e4m3 with one scale per output channel (fx_quantize_rows) and switch
+        forward() to the FP8 tcgen05 path: activations are row-quantised by the producing norm kernel (or one
+        extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16."""
+        keys = self.quantized_keys()
+        total = sum(self._shape(k + ".weight")[0] * self._shape(k + ".weight")[1] for k in keys)
+        rows = sum(self._shape(k + ".weight")[0] for k in keys)
+        buf = torch.empty(total, device=self.device, dtype=ops.fp8)
+        sc = torch.empty(rows, device=self.device, dtype=torch.float32)
+        o = r = 0
+        for k in keys:
+            n, kk = self._shape(k + ".weight")
+            q, s = buf[o:o + n * kk].view(n, kk), sc[r:r + n]
+            ops.quantize_rows(self._w(k), out=q, out_scale=s)
+            self._q8[k] = (q, s)
+            o += n * kk
+            r += n
+        self._graphs = {}
+        self._ws = {}  # the workspace gains the FP8 operand buffers
+        return self
+
+    @property
+    def quantized(self) -> bool:
+        return bool(self._q8)
 
     def _shapes_dict(self):
         self._shape(self._manifest[0][0])
@@ -181,6 +224,11 @@ class Flux:
             ws = dict(x=e(B, N, D), xm=e(B, N, D), q=e(B, H, N, 128), k=e(B, H, N, 128), v=e(B, H, N, 128),
                       cat=e(B, N, D + M), mod=e(B, self._mod_total), vec=e(B, D), h=e(B, D), h2=e(B, D),
                       pred=e(B, L, self.in_channels))
+            if self._q8:  # FP8 operand buffers + per-row scales
+                ws.update(xm8=torch.empty((B, N, D), device=dev, dtype=ops.fp8),
+                          cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
+                          xs=torch.empty((B, N), device=dev, dtype=torch.float32),
+                          cs=torch.empty((B, N), device=dev, dtype=torch.float32))
             self._ws = {key: ws}  # keep one shape resident
         return ws
 
@@ -258,7 +306,9 @@ class Flux:
         pe = self._pe(txt_ids, img_ids)
         scale = 128 ** -0.5
 
-        for i in range(p.depth):
+        if self._q8:
+            self._blocks_fp8(ws, S, pe, scale)
+        for i in range(0 if self._q8 else p.depth):
             pre = f"double_blocks.{i}."
             streams = (("img", x_img, xm[:, S:], cat[:, S:], S), ("txt", x_txt, xm[:, :S], cat[:, :S], 0))
             for name, xs, xms, _, off in streams:
@@ -277,7 +327,7 @@ class Flux:
                 ops.gemm(xms, self._w(mlp + "0"), self._b(mlp + "0"), act="gelu_tanh", out=cs[:, :, D:])
                 ops.gemm(cs[:, :, D:], self._w(mlp + "2"), self._b(mlp + "2"), gate=self._mod(ws, mk, 5), resid=xs, out=xs)
 
-        for i in range(p.depth_single_blocks):
+        for i in range(0 if self._q8 else p.depth_single_blocks):
             pre = f"single_blocks.{i}."
             mk = pre + "modulation.lin"
             ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
@@ -291,6 +341,52 @@ class Flux:
         ops.rownorm(x_img, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, S:])
         ops.gemm(xm[:, S:], self._w("final_layer.linear"), self._b("final_layer.linear"), out=ws["pred"])
         return ws["pred"]
+
+    def _blocks_fp8(self, ws: dict, S: int, pe: torch.Tensor, scale: float) -> None:
+        """The 19 + 38 blocks with FP8 operands for qkv / mlp.0 / mlp.2 / linear1 / linear2 (same dataflow as the
+        bf16 path in forward(); `proj` stays bf16).  A operands: the AdaLN row norm writes e4m3 + row scales directly;
+        the attention | GELU(mlp) buffer `cat` takes one fx_quantize_rows pass before mlp.2 / linear2."""
+        p = self.params
+        D = self.hidden_size
+        x, q, k, v, cat = ws["x"], ws["q"], ws["k"], ws["v"], ws["cat"]
+        xm, xm8, cat8, xs, cs = ws["xm"], ws["xm8"], ws["cat8"], ws["xs"], ws["cs"]
+        for i in range(p.depth):
+            pre = f"double_blocks.{i}."
+            streams = (("img", slice(S, None), S), ("txt", slice(0, S), 0))
+            for name, rows, off in streams:
+                mk = pre + name + "_mod.lin"
+                ak = pre + name + "_attn."
+                ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
+                w8, wsc = self._q8[ak + "qkv"]
+                ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
+                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS,
+                             a_scale=xs[:, rows], w_scale=wsc)
+            ops.attention(q, k, v, cat[:, :, :D], scale)
+            for name, rows, off in streams:
+                mk = pre + name + "_mod.lin"
+                ak = pre + name + "_attn."
+                mlp = pre + name + "_mlp."
+                xr = x[:, rows]
+                ops.gemm(cat[:, rows, :D], self._w(ak + "proj"), self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xr, out=xr)
+                ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
+                w8, wsc = self._q8[mlp + "0"]
+                ops.gemm(xm8[:, rows], w8, self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:], a_scale=xs[:, rows], w_scale=wsc)
+                ops.quantize_rows(cat[:, rows, D:], out=cat8[:, rows, D:], out_scale=cs[:, rows])
+                w8, wsc = self._q8[mlp + "2"]
+                ops.gemm(cat8[:, rows, D:], w8, self._b(mlp + "2"), gate=self._mod(ws, mk, 5), resid=xr, out=xr,
+                         a_scale=cs[:, rows], w_scale=wsc)
+        for i in range(p.depth_single_blocks):
+            pre = f"single_blocks.{i}."
+            mk = pre + "modulation.lin"
+            ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8, out_scale=xs)
+            w8, wsc = self._q8[pre + "linear1"]
+            ops.gemm_qkv(xm8, w8, self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
+                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
+                         a_scale=xs, w_scale=wsc)
+            ops.attention(q, k, v, cat[:, :, :D], scale)
+            ops.quantize_rows(cat, out=cat8, out_scale=cs)
+            w8, wsc = self._q8[pre + "linear2"]
+            ops.gemm(cat8, w8, self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x, a_scale=cs, w_scale=wsc)
 
     def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                         timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -15,6 +15,7 @@ from . import _native as N
 
 ACT = {"none": 0, None: 0, "gelu_tanh": 1, "quick_gelu": 2, "gelu": 3, "gelu_erf": 3}
 bf16 = torch.bfloat16
+fp8 = torch.float8_e4m3fn  # storage dtype of --quantize operands (1 byte per element)
 
 
 def _as3(t: torch.Tensor) -> Tuple[int, int, int, int, int]:
@@ -38,11 +39,29 @@ def _chk(t: torch.Tensor, dtype=bf16) -> torch.Tensor:
     return t
 
 
+def _fp8_operands(args, a: torch.Tensor, w: torch.Tensor, a_scale: Optional[torch.Tensor],
+                   w_scale: Optional[torch.Tensor], B: int, R: int) -> None:
+    """Fill the fp8 fields of GemmArgs / QkvArgs: a_scale fp32 [B, R] (or [R]), w_scale fp32 [N]."""
+    if a_scale is None or w_scale is None:
+        raise ValueError("fp8 operands need a_scale and w_scale")
+    _chk(a_scale, torch.float32), _chk(w_scale, torch.float32)
+    if a_scale.numel() != B * R or w_scale.numel() != w.shape[0] or not w_scale.is_contiguous():
+        raise ValueError("fp8 scale shapes do not match the operands")
+    if a_scale.stride(-1) != 1:
+        raise ValueError("a_scale rows must be contiguous")
+    args.fp8 = 1
+    args.a_scale, args.w_scale = a_scale.data_ptr(), w_scale.data_ptr()
+    args.a_scale_bs = a_scale.stride(0) if (a_scale.dim() == 2 and B > 1) else R
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          act=None, gate: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-         out_dtype: torch.dtype = bf16) -> torch.Tensor:
-    """out = resid + gate * act(a @ w.T + bias).  a [B,R,K] | [R,K]; w [N,K]; gate [B,N]; resid like out."""
-    _chk(a), _chk(w)
+         out_dtype: torch.dtype = bf16, a_scale: Optional[torch.Tensor] = None,
+         w_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = resid + gate * act(a @ w.T + bias).  a [B,R,K] | [R,K]; w [N,K]; gate [B,N]; resid like out.
+    a and w may both be float8_e4m3fn with per-row scales (a_scale [B,R], w_scale [N]): the --quantize path."""
+    is8 = a.dtype == fp8
+    _chk(a, fp8 if is8 else bf16), _chk(w, fp8 if is8 else bf16)
     B, R, K, lda, abs_ = _as3(a)
     Nn = w.shape[0]
     if w.shape[1] != K:
@@ -66,15 +85,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _, _, _, ldr, rbs = _as3(resid)
         args.resid, args.ldr, args.resid_bs = resid.data_ptr(), ldr, rbs
     args.batch, args.rows, args.N, args.K = B, R, Nn, K
+    if is8:
+        _fp8_operands(args, a, w, a_scale, w_scale, B, R)
     N.check(N.lib().fx_gemm(C.byref(args), N.stream()))
     return out
 
 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_scale: torch.Tensor,
              k_scale: torch.Tensor, pe: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
-             seq_off: int, mlp_out: Optional[torch.Tensor] = None, rms_eps: float = 1e-5) -> None:
-    """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16."""
-    _chk(a), _chk(w), _chk(q), _chk(k), _chk(v), _chk(pe)
+             seq_off: int, mlp_out: Optional[torch.Tensor] = None, rms_eps: float = 1e-5,
+             a_scale: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None) -> None:
+    """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16.
+    a / w may be float8_e4m3fn with a_scale / w_scale (see gemm)."""
+    is8 = a.dtype == fp8
+    _chk(a, fp8 if is8 else bf16), _chk(w, fp8 if is8 else bf16), _chk(q), _chk(k), _chk(v), _chk(pe)
     B, R, K, lda, abs_ = _as3(a)
     H, seq_total = q.shape[1], q.shape[2]
     args = N.QkvArgs()
@@ -89,6 +113,8 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_s
     args.rms_eps = rms_eps
     args.batch, args.rows, args.N, args.K = B, R, w.shape[0], K
     args.heads, args.seq_total, args.seq_off = H, seq_total, seq_off
+    if is8:
+        _fp8_operands(args, a, w, a_scale, w_scale, B, R)
     N.check(N.lib().fx_gemm_qkv(C.byref(args), N.stream()))
 
 
@@ -146,12 +172,14 @@ def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
 
 
 def rownorm(x: torch.Tensor, mode: int, p0: torch.Tensor, p1: Optional[torch.Tensor], eps: float,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """mode 0: (1+p1[b])*LN(x)+p0[b]; mode 1: LN(x)*p0+p1; mode 2: RMSNorm(x)*p0."""
+            out: Optional[torch.Tensor] = None, out_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode 0: (1+p1[b])*LN(x)+p0[b]; mode 1: LN(x)*p0+p1; mode 2: RMSNorm(x)*p0.
+    A float8_e4m3fn `out` (with out_scale fp32 [B,R]) gets the row-quantised result (--quantize)."""
     _chk(x)
     B, R, D, ldx, xbs = _as3(x)
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=bf16)
+    _chk(out, out.dtype)
     _, _, _, ldo, obs = _as3(out)
     args = N.RowNormArgs()
     args.x, args.ldx, args.x_bs = x.data_ptr(), ldx, xbs
@@ -159,8 +187,36 @@ def rownorm(x: torch.Tensor, mode: int, p0: torch.Tensor, p1: Optional[torch.Ten
     args.p0, args.p1 = p0.data_ptr(), N.ptr(p1)
     args.p_bs = p0.stride(0) if (mode == 0 and p0.dim() == 2) else 0
     args.eps, args.mode, args.batch, args.rows, args.D = eps, mode, B, R, D
+    if out.dtype == fp8:
+        if out_scale is None:
+            raise ValueError("fp8 rownorm output needs out_scale")
+        _chk(out_scale, torch.float32)
+        args.out_fp8, args.scale_out = 1, out_scale.data_ptr()
+        args.scale_bs = out_scale.stride(0) if (out_scale.dim() == 2 and B > 1) else R
     N.check(N.lib().fx_rownorm(C.byref(args), N.stream()))
     return out
+
+
+def quantize_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                  out_scale: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Row-wise FP8 quantisation: x bf16 [B,R,K] | [R,K] -> (q float8_e4m3fn like x, scale fp32 [B,R] | [R]);
+    scale = absmax / 448, q = e4m3(x / scale); x ~= q * scale."""
+    _chk(x)
+    B, R, K, ldx, xbs = _as3(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=fp8)
+    if out_scale is None:
+        out_scale = torch.empty(x.shape[:-1], device=x.device, dtype=torch.float32)
+    _chk(out, fp8), _chk(out_scale, torch.float32)
+    _, _, _, ldq, qbs = _as3(out)
+    args = N.QuantArgs()
+    args.x, args.ldx, args.x_bs = x.data_ptr(), ldx, xbs
+    args.q, args.ldq, args.q_bs = out.data_ptr(), ldq, qbs
+    args.scale = out_scale.data_ptr()
+    args.scale_bs = out_scale.stride(0) if (out_scale.dim() == 2 and B > 1) else R
+    args.batch, args.rows, args.K = B, R, K
+    N.check(N.lib().fx_quantize_rows(C.byref(args), N.stream()))
+    return out, out_scale
 
 
 def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,

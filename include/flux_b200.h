@@ -136,8 +136,26 @@ typedef struct fx_rownorm_args {
   const void* p0; const void* p1; int64_t p_bs; /* mode 0: shift, scale [batch][D]; mode 1: weight, bias; mode 2: weight */
   float eps;
   int32_t mode, batch, rows, D;
+  /* --quantize: out_fp8 != 0 writes e4m3 bytes to `out` (ldo / out_bs in bytes) with one dequantisation scale per
+   * row in scale_out[b * scale_bs + r]; identical to fx_quantize_rows applied to the bf16 result: the A operand of an
+   * fp8 fx_gemm / fx_gemm_qkv */
+  int32_t out_fp8;
+  float* scale_out; int64_t scale_bs;
 } fx_rownorm_args;
 int fx_rownorm(const fx_rownorm_args* a, fx_stream stream);
+
+/* FP8 row quantisation for --quantize (txt2image.py:56,79-82 -- the reference quantises nn.Linear weights to MLX
+ * 4-bit groups; here weights AND activations of the block Linears go to e4m3 for the tcgen05 f8f6f4 MMAs):
+ * x bf16 [batch][rows][K] -> q e4m3 bytes + scale fp32 [batch][rows]; q = e4m3_rn_satfinite(x * (448 / absmax)),
+ * scale = absmax * (1/448) (both 1 for a zero row).  Used once per weight at load and per step for GEMM inputs that no
+ * norm kernel produces (attention output | GELU(mlp) -> linear2 / proj / fc2). */
+typedef struct fx_quant_args {
+  const void* x; int64_t ldx; int64_t x_bs;
+  void* q; int64_t ldq; int64_t q_bs;
+  float* scale; int64_t scale_bs;
+  int32_t batch, rows, K;
+} fx_quant_args;
+int fx_quantize_rows(const fx_quant_args* a, fx_stream stream);
 
 /* ---------------------------------------------------------------- conditioning vector path
  * out[b][n] = sum_k f(in[b][k]) W[n][k] + bias[n] (+ add[b][n]); f = SiLU when silu_in.

@@ -27,6 +27,8 @@ import math
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
+import re
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -41,10 +43,14 @@ class Mode:
     """fp32: every op in float32.  fp64: float64.  bf16: float32 math, result of every reference
     op rounded to bfloat16 (how an unfused bf16 MLX graph behaves: flux/flux.py:24)."""
 
-    def __init__(self, name: str = "fp32"):
+    def __init__(self, name: str = "fp32", quantize: bool = False):
         assert name in ("fp32", "fp64", "bf16")
         self.name = name
         self.dtype = torch.float64 if name == "fp64" else torch.float32
+        # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
+        # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
+        # e4m3 activations and weights (fx_quantize_rows in include/flux_b200.h), everything else is unchanged.
+        self.quantize = quantize
 
     def r(self, x: Tensor) -> Tensor:
         if self.name == "bf16":
@@ -58,9 +64,29 @@ class Mode:
 FP32 = Mode("fp32")
 
 
+FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
+
+
+def fp8_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """Row-wise e4m3 quantisation as fx_quantize_rows does it (all in fp32): inv = 448 / absmax, q = e4m3_rn_sat(x * inv),
+    dequantisation scale = absmax * (1/448); a zero row gets inv = scale = 1.  Returns (q as float32 values, scale [..., 1])."""
+    x32 = x.to(torch.float32)
+    amax = x32.abs().amax(dim=-1, keepdim=True)
+    one = torch.ones_like(amax)
+    scale = torch.where(amax > 0, amax * torch.tensor(1.0 / 448.0, dtype=torch.float32), one)
+    inv = torch.where(amax > 0, torch.tensor(448.0, dtype=torch.float32) / amax, one)
+    q = (x32 * inv).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(torch.float32)
+    return q, scale
+
+
 def _linear(m: Mode, x: Tensor, sd: Dict[str, Tensor], key: str, bias: bool = True) -> Tensor:
     w = m.w(sd[key + ".weight"])
     b = m.w(sd[key + ".bias"]) if bias and (key + ".bias") in sd else None
+    if m.quantize and FP8_LINEARS.match(key):
+        xq, xs = fp8_quant_rows(x)
+        wq, ws = fp8_quant_rows(w)
+        y = F.linear(xq, wq) * xs * ws.squeeze(-1)
+        return m.r(y.to(m.dtype) + b if b is not None else y.to(m.dtype))
     return m.r(F.linear(x, w, b))
 
 

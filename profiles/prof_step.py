@@ -23,6 +23,8 @@ depth = int(os.environ.get("PROF_DEPTH", "19"))
 p = specs.FluxParams(depth=depth, depth_single_blocks=2 * depth)
 model = Flux(p, device=dev)
 model.arena.buffer.normal_(0, 0.02)
+if os.environ.get("PROF_QUANT", "0") == "1":  # the --quantize (FP8) path
+    model.quantize()
 L, S = 4096, 256
 img = torch.randn(B, L, 64, device=dev, dtype=bf)
 txt = torch.randn(B, S, 4096, device=dev, dtype=bf)

@@ -69,6 +69,13 @@ def main(which):
     gate = r(B, D, sc=0.1)
     shift, scale = r(B, D, sc=0.1), r(B, D, sc=0.1)
     f32buf = torch.empty(B, L, M, device=dev, dtype=torch.float32) if 'fc1_f32out' in which else None
+    f8 = any(n.endswith("_f8") for n in which)
+    if f8:  # --quantize operands
+        xm8, xs = ops.quantize_rows(xm)
+        cat8, cs = ops.quantize_rows(cat)
+        w1q, w1s = ops.quantize_rows(w1)
+        w2q, w2s = ops.quantize_rows(w2)
+        wfq, wfs = ops.quantize_rows(wfc1)
     tests = {
         "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
         "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
@@ -81,12 +88,20 @@ def main(which):
         "attn_noseq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=4), 4.0 * B * H * N * N * 128),
         "attn2": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=3), 4.0 * B * H * N * N * 128),
         "rownorm": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm), 0.0),
+        "linear1_f8": (lambda: ops.gemm_qkv(xm8, w1q, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:], a_scale=xs, w_scale=w1s),
+                       2.0 * B * N * (3 * D + M) * D),
+        "linear2_f8": (lambda: ops.gemm(cat8, w2q, b2, gate=gate, resid=x, out=x, a_scale=cs, w_scale=w2s), 2.0 * B * N * D * (D + M)),
+        "fc1_f8": (lambda: ops.gemm(xm8[:, S:], wfq, bfc1, act="gelu_tanh", out=cat[:, S:, D:], a_scale=xs[:, S:], w_scale=wfs),
+                   2.0 * B * L * M * D),
+        "quant_cat_f8": (lambda: ops.quantize_rows(cat, out=cat8, out_scale=cs), 0.0),
+        "rownorm_f8": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm8, out_scale=xs), 0.0),
         "cublas_l1": (lambda: torch.matmul(xm.view(-1, D), w1.T), 2.0 * B * N * (3 * D + M) * D),
     }
     for name in which or list(tests):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
-        extra = f" = {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s" if name == "rownorm" else f" = {tf:.0f} TFLOP/s"
+        nbytes = {"rownorm": 4 * x.numel(), "rownorm_f8": 3 * x.numel(), "quant_cat_f8": 3 * cat.numel()}.get(name)
+        extra = f" = {nbytes / ms / 1e6:.0f} GB/s" if nbytes else f" = {tf:.0f} TFLOP/s"
         print(f"{name:10s} {ms:8.3f} ms{extra}{last_clock}", flush=True)
 
 
