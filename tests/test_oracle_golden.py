@@ -128,3 +128,50 @@ def test_pipeline_end_to_end(variant):
     for i in range(steps):
         close(lats[i], g["latents"][i], rtol=2e-4, atol=2e-4)
     close(img, g["image"], rtol=5e-4, atol=5e-4)
+
+
+def test_fp8_quantiser_known_answers():
+    """oracle.fp8_quant_rows (the restatement of fx_quantize_rows, --quantize): e4m3 known answers.
+    Row absmax maps to 448 (0x7E), zero rows to scale 1 / byte 0, ties round to even, tiny values to subnormals."""
+    import torch
+
+    from oracle import flux_oracle as O
+    x = torch.tensor([[448.0, -448.0, 224.0, 1.0, 0.0, 17.0, 19.0, 2.0 ** -9],
+                      [0.0] * 8,
+                      [-3.5, 3.5, 1.75, 0.21875, 0.109375, 7.0 / 512, 0.0, 0.0]])
+    q, s = O.fp8_quant_rows(x)
+    by = q.to(torch.float8_e4m3fn).view(torch.uint8)
+    assert s.squeeze(-1).tolist() == [1.0, 1.0, float(torch.tensor(3.5) * torch.tensor(1.0 / 448.0))]
+    # row 0 (scale 1): 448 = 0x7E, -448 = 0xFE, 224 = 0x76, 1 = 0x38, 0 = 0x00, 17 -> 16 (tie to even) = 0x58,
+    # 19 -> 20 (nearest) = 0x5A, 2^-9 = smallest subnormal 0x01
+    assert by[0].tolist() == [0x7E, 0xFE, 0x76, 0x38, 0x00, 0x58, 0x5A, 0x01]
+    assert by[1].tolist() == [0] * 8
+    # row 2: absmax 3.5 -> inv = 128: values * 128 = -448, 448, 224, 28, 14, 1.75, 0, 0
+    assert by[2].tolist() == [0xFE, 0x7E, 0x76, 0x5E, 0x56, 0x3E, 0x00, 0x00]
+    # dequantised values stay within half an e4m3 step
+    assert ((q * s - x).abs() <= x.abs() * 2.0 ** -4 + s * 2.0 ** -10).all()
+
+
+def test_quantised_oracle_stays_close_to_fp32():
+    """Mode(quantize=True) only touches the block Linears named by FP8_LINEARS and stays within FP8 noise of fp32."""
+    import json
+
+    import torch
+
+    from flux import specs, synthetic
+    from oracle import flux_oracle as O
+    assert O.FP8_LINEARS.match("double_blocks.3.img_attn.qkv") and O.FP8_LINEARS.match("single_blocks.37.linear2")
+    assert not O.FP8_LINEARS.match("double_blocks.3.img_attn.proj") and not O.FP8_LINEARS.match("txt_in")
+    g = load("flow_schnell.npz")
+    cfg = json.loads(str(g["config"]))
+    p = specs.FluxParams(**cfg, guidance_embed=False)
+    sd = synthetic.synthetic_state_dict(specs.flow_manifest(p))
+    op = O.FluxParams(**cfg, guidance_embed=False)
+    a = [torch.from_numpy(np.asarray(g[k])) for k in ("img", "img_ids", "txt", "txt_ids")]
+    B = a[0].shape[0]
+    tt = torch.full((B,), float(g["t"]), dtype=torch.bfloat16)
+    y = torch.from_numpy(g["y"])
+    ref = O.flux_forward(sd, op, a[0].float(), a[1], a[2].float(), a[3], tt, y.float())
+    qnt = O.flux_forward(sd, op, a[0].float(), a[1], a[2].float(), a[3], tt, y.float(), mode=O.Mode("fp32", quantize=True))
+    rel = ((qnt - ref).norm() / ref.norm()).item()
+    assert 1e-4 < rel < 5e-2, rel
