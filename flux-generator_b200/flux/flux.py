@@ -11,7 +11,8 @@ Differences that follow from the platform, not from choice:
     (seed, global image index) so sharding a batch over G GPUs never changes an image.  Pass
     ``x_T=`` to supply the prior explicitly (parity tests do).
   * T5 / CLIP outputs are cached per prompt (north star: "run once per prompt and cached").
-  * training_loss / LoRA methods are out of scope for this round and raise.
+  * LoRA adapters (linear_to_lora_layers / fuse_lora_layers, flux/lora.py) are always run FUSED into the weights;
+    training_loss is out of scope (training) and raises.
 """
 from __future__ import annotations
 
@@ -173,8 +174,12 @@ class FluxPipeline:
     def training_loss(self, *a, **k):
         raise NotImplementedError("training is outside the B200 hot path (SURVEY 8-f N4)")
 
-    def linear_to_lora_layers(self, *a, **k):
-        raise NotImplementedError("LoRA is outside the B200 hot path (SURVEY 8-f N4)")
+    # ------------------------------------------------------------------ LoRA adapters at inference
+    def linear_to_lora_layers(self, rank: int = 8, num_blocks: int = -1):
+        """flux/flux.py:228-236: prepare the Linears of the last `num_blocks` blocks for an adapter of rank `rank`
+        (`flow.load_weights(adapter, strict=False)` then stages its lora_a / lora_b entries)."""
+        self.flow.enable_lora(rank, num_blocks)
 
-    def fuse_lora_layers(self, *a, **k):
-        raise NotImplementedError("LoRA is outside the B200 hot path (SURVEY 8-f N4)")
+    def fuse_lora_layers(self):
+        """flux/flux.py:238-246: fold the staged adapter into the flow weights."""
+        self.flow.fuse_lora()

@@ -105,6 +105,8 @@ class Flux:
         self._pe_cache: Dict[tuple, torch.Tensor] = {}
         self._txt_cache: Optional[tuple] = None
         self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
+        self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
+        self._lora_pending: Dict[str, torch.Tensor] = {}       # adapter tensors loaded but not yet fused
 
     # ------------------------------------------------------------------ weights
     def sanitize(self, weights: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -134,6 +136,9 @@ class Flux:
     def load_weights(self, weights, strict: bool = True) -> "Flux":
         items = list(weights.items()) if isinstance(weights, dict) else list(weights)
         for key, w in items:
+            if self._lora_cfg is not None and (key.endswith(".lora_a") or key.endswith(".lora_b")):
+                self._lora_pending[key] = w  # adapter file entries (txt2image.py:37): fused by fuse_lora()
+                continue
             if key not in self._shapes_dict():
                 if strict:
                     raise ValueError(f"Received parameters not in model: {key}")
@@ -152,6 +157,34 @@ class Flux:
             self._q8 = {}
             self.quantize()
         return self
+
+    # ------------------------------------------------------------------ LoRA adapters (txt2image.py:32-39)
+    def enable_lora(self, rank: int, num_blocks: int) -> None:
+        """FluxPipeline.linear_to_lora_layers (flux/flux.py:228-236): from now on load_weights accepts the adapter's
+        `<module>.lora_a` / `.lora_b` entries for the Linears of the last `num_blocks` blocks."""
+        self._lora_cfg = (int(rank), int(num_blocks))
+
+    def fuse_lora(self, scale: float = 1.0) -> int:
+        """FluxPipeline.fuse_lora_layers / LoRALinear.fuse (flux/flux.py:238-246, flux/lora.py:28-43):
+        W += ((scale * lora_b.T) @ lora_a.T).astype(W.dtype) in the weight arena.  Returns the number of fused Linears."""
+        from .lora import adapter_deltas
+        if self._lora_cfg is None or not self._lora_pending:
+            return 0
+        rank, blocks = self._lora_cfg
+        pend = {k: v.to(self.device) for k, v in self._lora_pending.items()}
+        deltas = adapter_deltas(pend, rank, blocks, self.params.depth, self.params.depth_single_blocks, scale)
+        for key, d in deltas.items():
+            dst = self._dest(key)
+            if dst is None or tuple(dst.shape) != tuple(d.shape):
+                raise ValueError(f"adapter entry for {key} does not match the model ({None if dst is None else tuple(dst.shape)} vs {tuple(d.shape)})")
+            dst.add_(d.to(bf16))  # flux/lora.py:39: weight + (lora_b @ lora_a).astype(dtype)
+        self._lora_pending = {}
+        self._txt_cache = None
+        self._graphs = {}
+        if self._q8:
+            self._q8 = {}
+            self.quantize()
+        return len(deltas)
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
     def quantized_keys(self) -> List[str]:
@@ -270,6 +303,8 @@ class Flux:
         """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call)."""
         if img.ndim != 3 or txt.ndim != 3:
             raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        if self._lora_pending:  # an adapter was loaded without --fuse-adapter: this build always runs it fused
+            self.fuse_lora()
         p = self.params
         if p.guidance_embed and guidance is None:
             raise ValueError("Didn't get guidance strength for guidance distilled model.")

@@ -9,8 +9,8 @@ truncated uint8 and the grid has a 4-px zero border per image.
 
 Platform notes: --quantize (the reference: MLX 4-bit group quantisation of nn.Linear, txt2image.py:79-82)
 selects the Blackwell-native reduced-precision path instead: the block Linears of the MMDiT run as FP8 e4m3
-tcgen05 GEMMs (per-row scales, fp32 accumulate; Flux.quantize); --adapter / --fuse-adapter (LoRA) are outside this
-round's hot path and raise.  Extra flags: --synthetic (seeded random weights / tokenizers when no
+tcgen05 GEMMs (per-row scales, fp32 accumulate; Flux.quantize); --adapter loads a LoRA adapter and always fuses it
+(flux/lora.py; --fuse-adapter is accepted for parity).  Extra flags: --synthetic (seeded random weights / tokenizers when no
 checkpoints exist offline), --gpus N is handled by launching under torchrun (one process per GPU, the
 image batch sharded contiguously, weights broadcast over NCCL).
 """
@@ -86,12 +86,13 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    if args.adapter:
-        raise NotImplementedError("--adapter (LoRA) is outside the B200 hot path in this round")
     lo, hi = shard(args.n_images, rank, world)
 
     flux = FluxPipeline("flux-" + args.model, t5_padding=args.t5_padding, synthetic=args.synthetic or None,
                         device=f"cuda:{local}", first_image_index=lo)
+    if args.adapter:  # txt2image.py:76-77
+        from flux.lora import load_adapter
+        load_adapter(flux, args.adapter, fuse=args.fuse_adapter)
     if args.quantize:  # txt2image.py:79-82 quantises flow / t5 / clip; here: the flow model's block Linears -> FP8
         flux.flow.quantize()
     if args.preload_models:

@@ -91,6 +91,42 @@ def _linear(m: Mode, x: Tensor, sd: Dict[str, Tensor], key: str, bias: bool = Tr
 
 
 # --------------------------------------------------------------------------------------------
+# N4: LoRA adapters at inference   (txt2image.py:32-39, flux/flux.py:228-246, flux/lora.py:28-43)
+# --------------------------------------------------------------------------------------------
+def lora_blocks(depth: int, depth_single: int, num_blocks: int) -> List[str]:
+    """Prefixes of the blocks FluxPipeline.linear_to_lora_layers wraps (flux/flux.py:230-233): the list
+    double_blocks + single_blocks REVERSED, first `num_blocks` entries (all of them when num_blocks <= 0)."""
+    allb = [f"double_blocks.{i}" for i in range(depth)] + [f"single_blocks.{i}" for i in range(depth_single)]
+    allb.reverse()
+    return allb[:num_blocks if num_blocks > 0 else len(allb)]
+
+
+def lora_checkpoint_key(module_path: str) -> str:
+    """MLX module path -> checkpoint-side Linear name: the inverse of Flux.sanitize's nn.Sequential renaming
+    (flux/model.py:92-95: `.img_mlp.` -> `.img_mlp.layers.`)."""
+    return module_path.replace(".layers.", ".")
+
+
+def lora_fuse(sd: Dict[str, Tensor], adapter: Dict[str, Tensor], num_blocks: int, depth: int, depth_single: int,
+              scale: float = 1.0) -> Dict[str, Tensor]:
+    """LoRALinear.fuse (flux/lora.py:28-43) for every adapted Linear: W' = W + ((scale * lora_b.T) @ lora_a.T).astype(W.dtype).
+    `adapter` holds `<module path>.lora_a` [in, r] / `.lora_b` [r, out] as dreambooth.py:46-59 saves them; entries
+    outside the wrapped blocks are ignored exactly like load_weights(strict=False) ignores them (txt2image.py:37)."""
+    out = dict(sd)
+    prefixes = tuple(p + "." for p in lora_blocks(depth, depth_single, num_blocks))
+    for k, a in adapter.items():
+        if not k.endswith(".lora_a") or not k.startswith(prefixes):
+            continue
+        mod = k[:-len(".lora_a")]
+        b = adapter[mod + ".lora_b"]
+        wk = lora_checkpoint_key(mod) + ".weight"
+        w = sd[wk]
+        delta = (scale * b.to(torch.float32).T) @ a.to(torch.float32).T
+        out[wk] = w + delta.to(w.dtype)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # a1: schedule   (flux/sampler.py:15-31)
 # --------------------------------------------------------------------------------------------
 def timesteps(num_steps: int, image_seq_len: int, schnell: bool, start: float = 1.0,

@@ -257,8 +257,62 @@ def golden_pipeline():
                  crc=np.asarray([synthetic.state_dict_checksum(s) for s in (flow_sd, ae_sd, t5_sd, clip_sd)]))
 
 
+def golden_lora():
+    """LoRA adapter at inference: txt2image.py:32-39 (load_adapter) -> FluxPipeline.linear_to_lora_layers /
+    fuse_lora_layers (flux/flux.py:228-246) -> LoRALinear.__call__ / fuse (flux/lora.py:28-43,73-76), executed by the
+    reference's own code on the small dev model.  The adapter file is written the way dreambooth.py:46-59 writes it
+    (tree_flatten of the LoRA parameters + lora_rank / lora_blocks metadata)."""
+    import zlib
+
+    from flux.lora import LoRALinear
+    from safetensors.torch import save_file
+    model, sd = build_flow(True)
+    pipe = ref.FluxPipeline.__new__(ref.FluxPipeline)
+    pipe.flow = model
+    rank, blocks = 4, 3  # the LAST three blocks: single.1, single.0, double.1 (flux/flux.py:230-232)
+    pipe.linear_to_lora_layers(rank, blocks)
+    adapter, names = {}, []
+    for name, m in model.named_modules():
+        if isinstance(m, LoRALinear):
+            names.append(name)
+            gen = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+            din, dout = m.lora_a.shape[0], m.lora_b.shape[1]
+            adapter[name + ".lora_a"] = (torch.randn(din, rank, generator=gen) * din ** -0.5).to(torch.bfloat16).float()
+            adapter[name + ".lora_b"] = (torch.randn(rank, dout, generator=gen) * 0.05).to(torch.bfloat16).float()
+    model.load_weights([(k, mx.array(v)) for k, v in adapter.items()], strict=False)
+    g = torch.Generator().manual_seed(11)
+    B, h, w, S = 2, 8, 12, 16
+    x = mx.array(torch.randn((B, h, w, 16), generator=g).to(torch.bfloat16))
+    img, img_ids = pipe._prepare_latent_images(x)
+    txt = mx.array(torch.randn((B, S, SMALL_FLOW["context_in_dim"]), generator=g).to(torch.bfloat16))
+    txt_ids = mx.zeros((B, S, 3), dtype=mx.int32)
+    y = mx.array(torch.randn((B, SMALL_FLOW["vec_in_dim"]), generator=g).to(torch.bfloat16))
+    t = mx.full((B,), 0.5, dtype=mx.bfloat16)
+    gd = mx.full((B,), 3.5, dtype=mx.bfloat16)
+    call = lambda: model(img=img.astype(mx.float32), img_ids=img_ids, txt=txt.astype(mx.float32), txt_ids=txt_ids,  # noqa: E731
+                         timesteps=t, y=y.astype(mx.float32), guidance=gd)
+    out_unfused = call()
+    pipe.fuse_lora_layers()
+    assert not any(isinstance(m, LoRALinear) for _, m in model.named_modules())
+    out_fused = call()
+    fused = {"single_blocks.1.linear1.weight": model.single_blocks[1].linear1.weight,
+             "double_blocks.1.img_mlp.layers.2.weight": model.double_blocks[1].img_mlp.layers[2].weight,
+             "double_blocks.1.txt_mod.lin.weight": model.double_blocks[1].txt_mod.lin.weight,
+             "double_blocks.0.img_attn.qkv.weight": model.double_blocks[0].img_attn.qkv.weight}  # untouched block
+    save_file({k: v.to(torch.bfloat16).contiguous() for k, v in adapter.items()}, os.path.join(OUT, "lora_adapter.safetensors"),
+              metadata={"lora_rank": str(rank), "lora_blocks": str(blocks)})
+    np.savez(os.path.join(OUT, "lora.npz"), config=json.dumps(SMALL_FLOW), rank=rank, blocks=blocks,
+             weights_crc=synthetic.state_dict_checksum(sd), lora_modules=np.asarray(names), img=npy(img), img_ids=npy(img_ids),
+             txt=npy(txt), txt_ids=npy(txt_ids), y=npy(y), t=0.5, guidance=3.5, out_unfused=npy(out_unfused),
+             out_fused=npy(out_fused), **{"fused." + k: npy(v[:48]) for k, v in fused.items()})  # first 48 rows of each
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "lora":  # add one fixture without touching the others
+        torch.manual_seed(0)
+        golden_lora()
+        sys.exit(0)
     torch.manual_seed(0)
     golden_schedule()
     golden_patchify()
@@ -266,5 +320,6 @@ if __name__ == "__main__":
     golden_ae()
     golden_text()
     golden_pipeline()
+    golden_lora()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

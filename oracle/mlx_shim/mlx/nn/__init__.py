@@ -101,6 +101,25 @@ class Module:
     def eval(self):
         return self
 
+    def __contains__(self, key):  # `"bias" in linear` (flux/lora.py:30)
+        return key in vars(self)
+
+    def update_modules(self, tree):
+        """Replace sub-modules along dotted paths (mlx.nn.Module.update_modules; flux/flux.py:236,246)."""
+        def rec(cur, sub):
+            for k, v in sub.items():
+                if isinstance(v, dict):
+                    nxt = cur[int(k)] if isinstance(cur, (list, tuple)) else (cur[k] if isinstance(cur, dict) else getattr(cur, k))
+                    rec(nxt, v)
+                elif isinstance(cur, list):
+                    cur[int(k)] = v
+                elif isinstance(cur, dict):
+                    cur[k] = v
+                else:
+                    setattr(cur, k, v)
+        rec(self, tree)
+        return self
+
 
 class Identity(Module):
     def __init__(self, *a, **k):
