@@ -28,6 +28,8 @@ bf16 = torch.bfloat16
 
 
 class FluxPipeline:
+    _b200_native = True  # callers that also accept reference-style pipelines (flux_app.py) key the GPU fast path on this
+
     def __init__(self, name: str, t5_padding: bool = True, synthetic: Optional[bool] = None,
                  device: Optional[str] = None, flow_params=None, ae_params=None, t5_config=None, clip_config=None,
                  first_image_index: int = 0):
