@@ -14,6 +14,34 @@ namespace fx {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static unsigned long long l2_policy(int code) { return code == 1 ? kL2EvictFirst : (code == 2 ? kL2EvictLast : kL2EvictNormal); }
+
+// L2 management (the GEMMs stream 1-13 GB per launch through a 126 MB L2; measured with tests/gpu_l2_probe.py under
+// ncu + tests/gpu_microbench.py, profiles/r01_l2_experiments.txt):
+//  * eviction-priority hints on the tile loads: EVICT_FIRST on either operand multiplies the DRAM reads (linear1 3.6 ->
+//    10.7 GB, +18 % sustained time): the CTAs of a wave re-use each other's tiles at normal priority only.  EVICT_LAST
+//    changes nothing.  Default: normal / normal (FX_GEMM_HINT_A / _W: 0 normal, 1 first, 2 last).
+//  * outputs the kernel never re-reads are stored evict-first (st.global.cs; FX_GEMM_STCS=0 disables): -7 % DRAM reads.
+//  * wave lockstep (gemm.cuh), opt-in: FX_GEMM_LOCKSTEP = k-blocks per group (0 off, default), FX_GEMM_LS_SLACK = groups
+//    of run-ahead.  For the long-K GEMMs it cuts linear2's DRAM reads from 12.9 to 4.4 GB and its isolated sustained time
+//    from 2.87 to 2.74 ms, but inside the pipeline (clocks set by the whole mix) the coupling costs more than the DRAM
+//    energy it saves: bench 4.017 -> 3.980 images/s.  Measured and left off.
+static void fill_l2_policy(GemmParams& p, int esz) {
+  static int ha = env_int("FX_GEMM_HINT_A", 0), hw = env_int("FX_GEMM_HINT_W", 0), cs = env_int("FX_GEMM_STCS", 1);
+  p.hint_a = l2_policy(ha);
+  p.hint_w = l2_policy(hw);
+  p.stream_out = cs;
+  // (a group must outlast the sync warp's atomic + poll round trip, ~2 us: 16 k-blocks = 6 us of bf16 MMAs)
+  static int ls = env_int("FX_GEMM_LOCKSTEP", -1), slack = env_int("FX_GEMM_LS_SLACK", 2);
+  p.ls_group = ls > 0 ? ls : 0;
+  (void)esz;
+  p.ls_slack = slack < 1 ? 1 : slack;
+}
+
 static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   p.tiles_m_per_batch = tiles_m_per_batch;
   p.tiles_m = tiles_m_per_batch * p.batch;
@@ -139,6 +167,7 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   const int bn = pick_bn(a->N);
   const int ncta = want_ncta(bn);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), bn);
+  fill_l2_policy(p, esz);
   CUtensorMap ta, tw;
   int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, bn, ncta, esz);
   if (rc) return rc;
@@ -170,6 +199,7 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
   const int ncta = want_ncta(256);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);
+  fill_l2_policy(p, esz);
   CUtensorMap ta, tw;
   int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, 256, ncta, esz);
   if (rc) return rc;
@@ -195,6 +225,7 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   p.out = a->out; p.ldo = a->Cout; p.out_bs = (long long)a->H * a->Wd * a->Cout; p.out_f32 = a->out_f32;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = p.out_bs;
   fill_tiling(p, p.conv_tiles_x * p.conv_tiles_y, bn);
+  fill_l2_policy(p, 2);
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->batch};

@@ -23,6 +23,21 @@ constexpr int GEMM_WARP_TMA = 8, GEMM_WARP_MMA = 9, GEMM_CTRL0 = 8, GEMM_EPI0 = 
 
 enum : int { EPI_GENERIC = 0, EPI_QKV = 1 };
 
+// ------------------------------------------------------------------ wave lockstep (L2 reuse across CTA pairs)
+// The CTA pairs that run concurrently share operand tiles (a wave of 74 pairs = ~6 row tiles x 12 column tiles for the
+// narrow-output GEMMs), but nothing keeps them at the same K position: with K = 12288 / 15360 a wave's operand set is
+// ~140 MB > L2, pairs drift apart by whole tiles, and ncu showed linear2 reading 11 GB from DRAM for 1.2 GB of
+// operands.  Under the 1 kW cap that traffic is time (measured ~0.09 ms per GB).  A sliding-window barrier keeps the
+// producers of a wave within `ls_slack` K-groups of each other, so a tile fetched by one pair is still in L2 when the
+// others ask for it.  Split-phase, sense-reversing, self-cleaning slots in global memory; a bounded wait (the barrier
+// is an optimisation: on timeout the pair just stops synchronising) makes a hang impossible.
+constexpr int LS_RING = 256;
+struct LockstepSlots {
+  unsigned int count[LS_RING];
+  unsigned int gen[LS_RING];
+};
+__device__ LockstepSlots g_lockstep;
+
 struct GemmParams {
   int batch, rows, N, K;
   int tiles_m_per_batch, tiles_m, tiles_n, num_tiles, k_blocks, group_m;
@@ -46,6 +61,10 @@ struct GemmParams {
   const float* a_scale;
   long long a_scale_bs;
   const float* w_scale;
+  // ---- L2 management: eviction-priority policies of the A / W tile loads and streaming (evict-first) output stores
+  unsigned long long hint_a, hint_w;
+  int stream_out;
+  int ls_group, ls_slack;  // wave lockstep: k-blocks per group (0 = off), groups a producer may run ahead
   // ---- 3x3 conv mode (A is [batch][H][W][C] NHWC, pad 1, stride 1)
   int conv_H, conv_W, conv_tiles_x, conv_tiles_y, cin_blocks;
 };
@@ -96,7 +115,7 @@ __device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float* f) {
 //   f: this lane's 32 values (row = lane); base: address of (row 0 of the warp, first column of the chunk);
 //   ld: row stride in elements; vmask: bit r set = row r exists.
 __device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, const float* f, __nv_bfloat16* base,
-                                                        long long ld, uint32_t vmask) {
+                                                        long long ld, uint32_t vmask, bool streaming = false) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 u;
@@ -110,7 +129,10 @@ __device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, 
   for (int i = 0; i < 4; ++i) {
     const int r = (lane >> 2) + 8 * i;
     const uint4 u = *reinterpret_cast<const uint4*>(wst + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
-    if ((vmask >> r) & 1u) *reinterpret_cast<uint4*>(base + r * ld + ch * 8) = u;
+    if ((vmask >> r) & 1u) {
+      if (streaming) st_global_cs(base + r * ld + ch * 8, u);
+      else *reinterpret_cast<uint4*>(base + r * ld + ch * 8) = u;
+    }
   }
   __syncwarp();
 }
@@ -192,7 +214,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
       }
     } else if (wst != nullptr) {  // warp-collective: every lane takes part, rows are masked
       store_chunk32_coalesced(wst, lane, f, reinterpret_cast<__nv_bfloat16*>(p.out) + out_off - (long long)lane * p.ldo + n0,
-                              p.ldo, vmask);
+                              p.ldo, vmask, p.stream_out != 0 && p.resid == nullptr);
     } else if (valid) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + n0;
 #pragma unroll
@@ -236,6 +258,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  volatile uint32_t* ls_issued = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 192);   // producer -> sync warp
+  volatile uint32_t* ls_allowed = ls_issued + 1;                                                               // sync warp -> producer
+  const bool lockstep = (NCTA == 2) && !CONV && p.ls_group > 0 && cta_rank == 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -252,6 +277,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 8 * NCTA);
     }
+    *ls_issued = 0;
+    *ls_allowed = uint32_t(p.ls_slack);
     fence_barrier_init();
   }
   if (warp == GEMM_WARP_MMA) {
@@ -278,6 +305,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t lsg = 0;  // global K-group index of this pair (monotonic across its tiles)
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
         int tm, tn;
         gemm_tile_coords(p, tile, tm, tn);
@@ -289,6 +317,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           cx = (tmb % p.conv_tiles_x) * (16 * NCTA) + int(cta_rank) * 16;
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (lockstep && kb % p.ls_group == 0) {  // entering K-group `lsg`: stay within ls_slack groups of the slowest pair
+            if (kb != 0 || lsg != 0) *ls_issued = lsg;  // groups < lsg are fully issued
+            while (*ls_allowed <= lsg) {
+            }
+            ++lsg;
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
@@ -300,9 +334,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
               tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
             } else {
-              tma2_load_3d(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b);
+              tma2_load_3d_hint(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b, p.hint_a);
             }
-            tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN + int(cta_rank) * (BN / 2));
+            tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {
@@ -316,6 +350,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      if (lockstep) *ls_issued = lsg;
+    }
+  } else if (warp == GEMM_CTRL0 + 2) {
+    // ================= wave-lockstep sync warp (leader CTA of the pair) =================
+    if (lockstep && lane == 0) {
+      const int groups_per_tile = (p.k_blocks + p.ls_group - 1) / p.ls_group;
+      int rounds = 0;
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) ++rounds;
+      const uint32_t total = uint32_t(rounds) * groups_per_tile;
+      bool alive = true;
+      for (uint32_t g = 0; g < total; ++g) {
+        if (alive) {
+          while (*ls_issued <= g) {  // the producer has issued every load of group g
+          }
+          const int round = int(g) / groups_per_tile;
+          const int members = min(tile_stride, p.num_tiles - round * tile_stride);  // pairs with a tile in this round
+          const int slot = int(g % LS_RING);
+          const unsigned int gen0 = *reinterpret_cast<volatile unsigned int*>(&g_lockstep.gen[slot]);
+          const unsigned int old = atomicAdd(&g_lockstep.count[slot], 1u);
+          if (old == unsigned(members - 1)) {
+            g_lockstep.count[slot] = 0;
+            __threadfence();
+            atomicAdd(&g_lockstep.gen[slot], 1u);
+          } else {
+            int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(&g_lockstep.gen[slot]) == gen0) {
+              if (++spins > (1 << 18)) {  // ~0.2 s: something else is wrong; run unsynchronised from here on
+                alive = false;
+                break;
+              }
+              __nanosleep(200);
+            }
+          }
+        }
+        *ls_allowed = alive ? g + 1 + uint32_t(p.ls_slack) : 0xffffffffu;
       }
     }
   } else if (warp == GEMM_WARP_MMA) {
@@ -559,7 +629,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                   }
                 }
-                store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask);
+                store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask, p.stream_out != 0);
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];
