@@ -561,43 +561,62 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// attn2_kernel: same math, decoupled schedule.  The key/value stream is consumed in 64-key steps; every
-// query tile owns TWO 64-column S buffers in TMEM, and S(n+2) = Q K(n+2)^T is issued right after
-// P(n) V(n), i.e. always one step AHEAD of the softmax.  The softmax warpgroups therefore never wait for the
-// "P ready -> PV -> QK -> S ready" round trip of attn_kernel: they are throughput-bound, not latency-bound.
-//   TMEM: S[i][b] at columns (2 i + b) * 64 (P[i][b] aliases its first 32 columns), O[i] at 256 + 128 i.
+// attn3_kernel (variants 5 / 6; measured, NOT the default): same math and roles as attn_kernel, but the per-tile
+// dependency loop is cut.
+//   attn_kernel hands P to the P.V MMA through TMEM, aliasing S: S_i(j+1) = Q_i K(j+1)^T cannot be issued before
+//   P_i(j) V(j) has consumed P_i(j), so every query tile runs the chain  S -> softmax -> P -> PV -> QK -> S  (probe:
+//   ~2100 + ~1100 clocks per key tile against a 2048-clock tensor floor for both tiles together).
+//   Here P goes through shared memory, so S_i is free again as soon as the softmax warps have READ it (~120 clocks
+//   after it was ready): the issuer starts Q_i K(j+1)^T right then and S_i(j+1) is waiting when the softmax of step j
+//   ends -- the warpgroups never wait for the tensor pipe, the tensor pipe only for P.
+//   Shared memory: Q 64 KB + ONE 32 KB P buffer (two 64-key half slots that the two query tiles take turns on:
+//   tile i writes half h after tile 1-i's P.V of that half has completed) + a 4-stage K/V ring = 224 KB.
+//   TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+//   Result (probe, SM clocks per key tile): 3880 with / 3707 without turn taking against attn_kernel's 3300 / 3230: the
+//   softmax warps no longer wait for S, but their exp phase grows from ~1730 to ~2600 clocks (P through st.shared +
+//   proxy fence + half-slot waits, both warpgroups now always contending for the same sub-partition), and the in-order
+//   issuer idles the tensor pipe between Q K(j+1)^T and the P it then waits for.  With two softmax warps per
+//   sub-partition the kernel is bound by the serial latency of the softmax instruction stream, not by the S -> P -> PV
+//   loop; the next step is more softmax threads per row, not a different hand-off.  (An earlier 64-key-step decoupled
+//   variant, attn2_kernel, was 15 % slower for the same reason plus N = 64 MMAs and has been removed.)
 // ------------------------------------------------------------------------------------------
-struct Attn2Cfg {
-  static constexpr int KV_STAGES = 5;
+struct Attn3Cfg {
+  static constexpr int KV_STAGES = 4;
   static constexpr int Q_OFF = 0;
-  static constexpr int KV_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int P_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int KV_OFF = 3 * ATT_TILE_BYTES;
   static constexpr int BAR_OFF = KV_OFF + KV_STAGES * ATT_TILE_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using Cfg = Attn2Cfg;
+  using Cfg = Attn3Cfg;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* kv_full = bars + 1;          // NS
-  uint64_t* kv_empty = kv_full + NS;     // NS
-  uint64_t* s_full = kv_empty + NS;      // [tile][buffer] = 4
-  uint64_t* p_full = s_full + 4;         // [tile][buffer] = 4
-  uint64_t* pv_done = p_full + 4;        // [tile] = 2
-  uint64_t* o_full = pv_done + 2;        // [tile] = 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* q_full = bars;              // 1
+  uint64_t* kv_full = bars + 1;         // NS
+  uint64_t* kv_empty = kv_full + NS;    // NS
+  uint64_t* s_full = kv_empty + NS;     // [tile] 2: S_i(j) is in TMEM
+  uint64_t* s_read = s_full + 2;        // [tile] 2: the softmax warps hold S_i(j) in registers (4 warp arrivals)
+  uint64_t* p_full = s_read + 2;        // [tile][half] 4: P_i(j) half h is in shared memory (4 warp arrivals)
+  uint64_t* p_free = p_full + 4;        // [tile][half] 4: P_i(j) V(j) of half h has completed (tcgen05.commit)
+  uint64_t* pv_done = p_free + 4;       // [tile] 2: O_i is quiescent after step j (rare rescale path)
+  uint64_t* o_full = pv_done + 2;       // [tile] 2
+  uint64_t* seq_bar = o_full + 2;       // [tile] 2: exp-phase turn taking
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(seq_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256;
   const int bh = blockIdx.z * p.heads + blockIdx.y;
-  const int T = p.kv_tiles;                 // 128-key tiles
-  const int NSTEP = (p.seq + 63) / 64;      // 64-key steps
+  const int T = p.kv_tiles;
+#ifdef FX_ATTN_PROBE
+  const bool probe_on = g_attn_probe && blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 1 && lane == 0;
+#endif
 
   if (warp == ATT_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -608,13 +627,16 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-    }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_read[i], 4);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
+      mbar_init(&seq_bar[i], 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
     }
     fence_barrier_init();
   }
@@ -628,9 +650,11 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= ATT_CTRL0 && warp < ATT_CTRL0 + 4) {
+    reg_dec<88>();
     if (warp == ATT_WARP_TMA) {
       if (lane == 0) {
-        // ---------------- TMA producer: Q (both tiles), then K0 V0 K1 V1 ... (128-key tiles)
+        // ---------------- TMA producer: Q (both tiles), then K0 V0 K1 V1 ... through one ring.  Consumption order is
+        // K(j+1) early in step j, V(j) late in step j; every load is still issued a full step before its use.
         mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
         for (int i = 0; i < 2; ++i)
           for (int hf = 0; hf < 2; ++hf)
@@ -649,102 +673,166 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         }
       }
     } else if (warp == ATT_WARP_MMA) {
-      if (lane == 0) {
-        // ---------------- MMA issuer
-        constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);
-        constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
-        const uint32_t q_base = smem_u32(smem + Cfg::Q_OFF);
-        const uint32_t kv_base = smem_u32(smem + Cfg::KV_OFF);
-        int stage = 0;
-        uint32_t phase = 0;
-        auto acquire = [&]() {
-          mbar_wait(&kv_full[stage], phase);
-          const int s = stage;
-          if (++stage == NS) { stage = 0; phase ^= 1; }
-          return s;
-        };
-        // S[i][n&1] = Q_i . K(step n)^T  (64 keys: rows 64*(n&1).. of the 128-key tile in `kslot`)
-        auto issue_qk = [&](int i, int n, int kslot) {
-          const uint32_t k_addr = kv_base + kslot * ATT_TILE_BYTES + (n & 1) * 8192;
+      // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues)
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t TILE16 = ATT_TILE_BYTES >> 4;
+      const uint32_t q_lo = (smem_u32(smem + Cfg::Q_OFF) >> 4) | (1u << 16);
+      const uint32_t p_lo = (smem_u32(smem + Cfg::P_OFF) >> 4) | (1u << 16);
+      const uint32_t k_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1u << 16);
+      const uint32_t v_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1024u << 16);
+      // ring slot / parity of load number t (K(j) is load 2j, V(j) is load 2j+1)
+      auto slot_of = [](int t) { return t & (NS - 1); };
+      auto par_of = [](int t) { return uint32_t(t / NS) & 1u; };
+      auto issue_qk = [&](int i, int kslot) {
+        const uint32_t a_lo = q_lo + i * TILE16, b_lo = k_lo0 + kslot * TILE16;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-            umma_ss(tmem + i * 128 + (n & 1) * 64, make_smem_desc_sw128(q_base + i * ATT_TILE_BYTES + off, 16, 1024),
-                    make_smem_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0);
-          }
-          tc_commit(&s_full[i * 2 + (n & 1)]);
-        };
-        // O_i (+)= P[i][n&1] . V(step n)
-        auto issue_pv = [&](int i, int n, int vslot) {
-          const uint32_t v_addr = kv_base + vslot * ATT_TILE_BYTES + (n & 1) * 4 * 2048;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ts(tmem + 256 + i * 128, tmem + i * 128 + (n & 1) * 64 + ks * 8,
-                    make_smem_desc_sw128(v_addr + ks * 2048, 16384, 1024), idesc_pv, (n > 0 || ks != 0) ? 1u : 0u);
-          tc_commit(&pv_done[i]);
-        };
-        mbar_wait(q_full, 0);
-        int kslot = acquire();  // K(0)
-        tc_fence_after();
-        for (int n = 0; n < 2 && n < NSTEP; ++n)
-          for (int i = 0; i < 2; ++i) issue_qk(i, n, kslot);
-        tc_commit(&kv_empty[kslot]);  // K(0) has no further readers (steps 0 and 1 are both issued)
-        int vslot = 0, knext = 0;
-        for (int n = 0; n < NSTEP; ++n) {
-          const bool more = n + 2 < NSTEP;
-          if ((n & 1) == 0) {
-            vslot = acquire();               // V(n/2)
-            if (more) knext = acquire();     // K(n/2 + 1): feeds steps n+2 and n+3
-          }
-          for (int i = 0; i < 2; ++i) {
-            mbar_wait(&p_full[i * 2 + (n & 1)], (n >> 1) & 1);
-            tc_fence_after();
-            issue_pv(i, n, vslot);
-            if (more) issue_qk(i, n + 2, knext);
-          }
-          if ((n & 1) == 1 || n == NSTEP - 1) tc_commit(&kv_empty[vslot]);                       // V(n/2) done
-          if (more && (((n + 2) & 1) == 1 || n + 2 == NSTEP - 1)) tc_commit(&kv_empty[knext]);  // K tile done
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;
+          umma_ss(tmem + i * 128, make_desc(a_lo + off, kDescHiSw128), make_desc(b_lo + off, kDescHiSw128), idesc_qk, ks != 0);
         }
+      };
+      // O_i (+)= P(half hf: 64 keys, K-major 16 KB slot) . V(rows hf*64 .. of the tile in vslot)
+      auto issue_pv = [&](int i, int vslot, bool acc, int hf) {
+        const uint32_t a_lo = p_lo + hf * 1024, b_lo = v_lo0 + vslot * TILE16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int ks = hf * 4 + kk;
+          umma_ss(tmem + 256 + i * 128, make_desc(a_lo + kk * 2, kDescHiSw128), make_desc(b_lo + ks * 128, kDescHiSw128), idesc_pv,
+                  (acc || ks != 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);  // K(0)
+      tc_fence_after();
+      if (elect_one()) {
+        issue_qk(0, 0);
+        tc_commit(&s_full[0]);
+        issue_qk(1, 0);
+        tc_commit(&s_full[1]);
+        tc_commit(&kv_empty[0]);
+      }
+      __syncwarp();
+      for (int j = 0; j < T; ++j) {
+        const bool more = (j + 1 < T);
+        const int tk = 2 * j + 2, tv = 2 * j + 1;  // load numbers of K(j+1) and V(j)
+        const int ks_ = slot_of(tk), vs = slot_of(tv);
+        const uint32_t ph = j & 1;
+        if (more) mbar_wait(&kv_full[ks_], par_of(tk));
+        PROBE(0, j, 0);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (more) {  // S_i(j) has been read: S_i(j+1) may overwrite it
+            mbar_wait(&s_read[i], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_qk(i, ks_);
+              tc_commit(&s_full[i]);
+              if (i == 1) tc_commit(&kv_empty[ks_]);
+            }
+            __syncwarp();
+          }
+          PROBE(0, j, 1 + 3 * i);
+          mbar_wait(&p_full[2 * i], ph);
+          if (i == 0) mbar_wait(&kv_full[vs], par_of(tv));  // V(j)
+          PROBE(0, j, 2 + 3 * i);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(i, vs, j > 0, 0);
+            tc_commit(&p_free[2 * i]);
+          }
+          __syncwarp();
+          mbar_wait(&p_full[2 * i + 1], ph);
+          PROBE(0, j, 3 + 3 * i);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(i, vs, j > 0, 1);
+            tc_commit(&p_free[2 * i + 1]);
+            tc_commit(&pv_done[i]);
+            if (i == 1) tc_commit(&kv_empty[vs]);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) {
         tc_commit(&o_full[0]);
         tc_commit(&o_full[1]);
       }
+      __syncwarp();
     }
   } else {
     // ---------------- softmax / correction / epilogue warpgroups
+    reg_inc<208>();
     const int i = (warp - ATT_SM0) >> 2;  // query tile 0/1
     const int quarter = warp & 3;         // TMEM lane quarter
     const int r = quarter * 32 + lane;
     const int q_row = q0 + i * 128 + r;
     const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const uint32_t s_addr = tmem + lane_base + i * 128;
     const uint32_t o_addr = tmem + lane_base + 256 + i * 128;
+    uint8_t* p_smem = smem + Cfg::P_OFF;
     const float sl2 = p.scale_log2;
     const uint64_t sl2_2 = pack2(sl2, sl2);
     float m_run = -INFINITY, l_run = 0.f;
+#ifdef FX_ATTN_PROBE
+    const bool probe_sm = probe_on && quarter == 0;
+#define S3PROBE(j, ev) do { if (probe_sm && (j) < 64) g_attn_probe[((1 + i) * 64 + (j)) * 8 + (ev)] = probe_clock(); } while (0)
+#else
+#define S3PROBE(j, ev) do {} while (0)
+#endif
 
-    for (int n = 0; n < NSTEP; ++n) {
-      const int b = n & 1;
-      const uint32_t s_addr = tmem + lane_base + i * 128 + b * 64;
-      const int kv_valid = min(64, p.seq - n * 64);
-      mbar_wait(&s_full[i * 2 + b], (n >> 1) & 1);
+    for (int j = 0; j < T; ++j) {
+      const int kv_valid = min(128, p.seq - j * 128);
+      mbar_wait(&s_full[i], j & 1);
+      S3PROBE(j, 0);
       tc_fence_after();
-      uint32_t sv[64];
+      uint32_t sv[128];
       __syncwarp();
       tmem_ld_x32(s_addr, sv);
       tmem_ld_x32(s_addr + 32, sv + 32);
+      tmem_ld_x32(s_addr + 64, sv + 64);
+      tmem_ld_x32(s_addr + 96, sv + 96);
       tmem_ld_wait();
-      if (kv_valid < 64) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_read[i]);  // S_i is free: the issuer may start Q_i K(j+1)^T
+      S3PROBE(j, 1);
+      if (kv_valid < 128) {
 #pragma unroll
-        for (int e = 0; e < 64; ++e)
+        for (int e = 0; e < 128; ++e)
           if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
       }
-      float mx0 = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
-      float mx1 = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+      auto exp_chunk = [&](int c, uint32_t* dst, uint32_t* pk, uint64_t nm2) {
 #pragma unroll
-      for (int e = 4; e < 64; e += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
+        for (int e = 0; e < 32; e += 2) {
+          const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
+          float p0, p1;
+          if (EMU_MASK & (1u << ((e >> 1) & 7))) {
+            exp2_emu2(t2, p0, p1);
+          } else {
+            const float2 t = unpack2(t2);
+            p0 = fast_exp2(t.x);
+            p1 = fast_exp2(t.y);
+          }
+          dst[e] = __float_as_uint(p0);
+          dst[e + 1] = __float_as_uint(p1);
+          pk[e >> 1] = pack_bf16(p0, p1);
+        }
+      };
+      if (p.sequence) mbar_wait(&seq_bar[i], (i == 0) ? ((j & 1) ^ 1) : (j & 1));
+      S3PROBE(j, 2);
+      uint64_t nm2 = pack2(-m_run, -m_run);
+      uint32_t pa[32], pk0[16];
+      exp_chunk(0, pa, pk0, nm2);  // speculative against the lazy running max (see attn_kernel)
+      float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+      float mxb = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+#pragma unroll
+      for (int e = 4; e < 128; e += 4) {
+        mx = fmax3(mx, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+        mxb = fmax3(mxb, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
       }
-      const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * sl2);
+      mx = fmaxf(mx, mxb);
+      const float m_new = fmaxf(m_run, mx * sl2);
       const bool need = (m_new - m_run) > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
@@ -752,9 +840,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           m_run = m_new;
           l_run *= alpha;
         }
-        if (n > 0) {
-          // O_i must be quiescent: P(n-1) V(n-1) was issued BEFORE S(n+1) but possibly after S(n) was ready
-          mbar_wait(&pv_done[i], (n - 1) & 1);
+        if (j > 0) {
+          // O_i must be quiescent: S_i(j) being ready only proves P_i(j-2) V(j-2) complete
+          mbar_wait(&pv_done[i], (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
@@ -767,45 +855,62 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             tmem_st_x32(o_addr + c * 32, v);
           }
           tmem_st_wait();
+          tc_fence_before();
         }
+        nm2 = pack2(-m_run, -m_run);
+        exp_chunk(0, pa, pk0, nm2);
       }
-      const uint64_t nm2 = pack2(-m_run, -m_run);
-      uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int e = 0; e < 32; ++e) sv[e] = pa[e];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
+        if (c == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const uint64_t ta = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
-          const uint64_t tb = ffma2(pack2(__uint_as_float(sv[c * 32 + e + 2]), __uint_as_float(sv[c * 32 + e + 3])), sl2_2, nm2);
-          float pa0, pa1, pb0, pb1;
-          if (EMU_MASK & (1u << ((e >> 2) & 7))) {
-            exp2_emu2(ta, pa0, pa1);
-          } else {
-            const float2 t = unpack2(ta);
-            pa0 = fast_exp2(t.x);
-            pa1 = fast_exp2(t.y);
-          }
-          {
-            const float2 t = unpack2(tb);
-            pb0 = fast_exp2(t.x);
-            pb1 = fast_exp2(t.y);
-          }
-          ls0 = fadd2(ls0, pack2(pa0, pa1));
-          ls1 = fadd2(ls1, pack2(pb0, pb1));
-          pk[e >> 1] = pack_bf16(pa0, pa1);
-          pk[(e >> 1) + 1] = pack_bf16(pb0, pb1);
+          for (int e = 0; e < 16; ++e) pk[e] = pk0[e];
+        } else {
+          exp_chunk(c, sv + c * 32, pk, nm2);
         }
-        tmem_st_x16(s_addr + c * 16, pk);
+        if ((c & 1) == 0) {
+          // half slot c>>1 was last read by the OTHER tile's P.V: tile 0 waits for P_1(j-1) V, tile 1 for P_0(j) V
+          const int hf = c >> 1;
+          if (i == 0) {
+            if (j > 0) mbar_wait(&p_free[2 + hf], (j - 1) & 1);
+          } else {
+            mbar_wait(&p_free[hf], j & 1);
+          }
+        }
+        {
+          // K-major SW128 half slot: row r, keys (c&1)*32 .. +31 -> 16-byte chunks ((c&1)*4 + q) ^ (r&7)
+          uint8_t* rowp = p_smem + (c >> 1) * 16384 + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+        if (c & 1) {
+          if (c == 3 && p.sequence) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&seq_bar[i ^ 1]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[2 * i + (c >> 1)]);
+          S3PROBE(j, 4 + (c >> 1));
+        }
       }
       {
-        const float2 a = unpack2(fadd2(ls0, ls1));
-        l_run += a.x + a.y;
+        uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 128; e += 4) {
+          ls0 = fadd2(ls0, pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+          ls1 = fadd2(ls1, pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+        }
+        const float2 ls = unpack2(fadd2(ls0, ls1));
+        l_run += ls.x + ls.y;
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[i * 2 + b]);
+      S3PROBE(j, 6);
     }
 
     // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
@@ -952,7 +1057,7 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   FX_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v), "fx_attention: q/k/v must be 16-byte aligned");
   AttnParams p{};
   p.seq = a->seq; p.heads = a->heads; p.kv_tiles = (a->seq + 127) / 128;
-  p.sequence = (a->variant == 4) ? 0 : 1;
+  p.sequence = (a->variant == 4) ? 1 : 0;  // turn taking lost its edge once the issuer was fixed: 3314 vs 3230 clocks per key tile
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out; p.out_bs = a->out_bs;
   CUtensorMap tq, tk, tv;
@@ -963,20 +1068,19 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   if ((rc = make_tmap_bf16(&tq, a->q, 3, dims, strides, box))) return rc;
   if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box))) return rc;
   if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box))) return rc;
-  if (a->variant == 1) return launch_attn<false>(a, tq, tk, tv, p, (cudaStream_t)stream);
-  if (a->variant == 3) {
-    // decoupled 64-key-step schedule (attn2_kernel): correct, but measured slower than attn_kernel
-    // (861 vs 1026 TFLOP/s sustained at B=8, H=24, N=4352): the doubled per-step overheads outweigh the
-    // shorter critical path.  Kept selectable for the next round's work on the softmax pipeline.
-    static bool attr_done = false;
-    if (!attr_done) {
-      FX_CUDA(cudaFuncSetAttribute(attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg::SMEM_BYTES));
-      attr_done = true;
+  if (a->variant == 5 || a->variant == 6) {
+    // decoupled schedule (attn3_kernel): P through shared memory, Q K(j+1)^T issued as soon as S(j) has been read
+    p.sequence = a->variant == 5 ? 1 : 0;
+    static bool attr3_done = false;
+    if (!attr3_done) {
+      FX_CUDA(cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg::SMEM_BYTES));
+      attr3_done = true;
     }
     dim3 grid((a->seq + 255) / 256, a->heads, a->batch);
-    attn2_kernel<<<grid, ATT_THREADS, Attn2Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
-    return launched("attn2_kernel");
+    attn3_kernel<<<grid, ATT_THREADS, Attn3Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
+    return launched("attn3_kernel");
   }
+  if (a->variant == 1) return launch_attn<false>(a, tq, tk, tv, p, (cudaStream_t)stream);
   return launch_attn<true>(a, tq, tk, tv, p, (cudaStream_t)stream);
 }
 

@@ -110,7 +110,9 @@ typedef struct fx_attn_args {
   void* out; int64_t ld_out; int64_t out_bs;
   float scale;
   int32_t batch, heads, seq;
-  int32_t variant;             /* 0 = default (P via TMEM); 1 = P via shared memory; 3 = decoupled 64-key-step schedule (tests / A-B) */
+  int32_t variant;             /* 0 = default; 1 = P via shared memory (coupled schedule); 4 = default with
+                                  exp-phase turn taking between the softmax warpgroups; 5 / 6 = decoupled schedule with P through shared memory (attn3_kernel), with / without
+                                  turn taking (tests / A-B) */
 } fx_attn_args;
 int fx_attention(const fx_attn_args* a, fx_stream stream);
 

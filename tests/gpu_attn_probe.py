@@ -19,11 +19,12 @@ fn = lib.fx_dbg_attn_probe
 fn.restype, fn.argtypes = C.c_int, [C.c_void_p]
 buf = torch.zeros(3 * 64 * 8, device="cuda", dtype=torch.int64)
 _native.check(fn(buf.data_ptr()))
+VARIANT = int(os.environ.get("PROBE_VARIANT", "0"))  # 4: no exp-phase turn taking between the softmax warpgroups
 for _ in range(5):
-    ops.attention(q, k, v, out, 128 ** -0.5)
+    ops.attention(q, k, v, out, 128 ** -0.5, variant=VARIANT)
 torch.cuda.synchronize()
 buf.zero_()
-ops.attention(q, k, v, out, 128 ** -0.5)
+ops.attention(q, k, v, out, 128 ** -0.5, variant=VARIANT)
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(3, 64, 8)
 os.makedirs("gpurun_out", exist_ok=True)

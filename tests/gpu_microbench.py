@@ -85,8 +85,9 @@ def main(which):
         "fc1_f32out": (lambda: ops.gemm(xm[:, S:], wfc1, out=f32buf), 2.0 * B * L * M * D),
         "fc1_plain": (lambda: ops.gemm(xm[:, S:], wfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "attn": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5), 4.0 * B * H * N * N * 128),
-        "attn_noseq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=4), 4.0 * B * H * N * N * 128),
-        "attn2": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=3), 4.0 * B * H * N * N * 128),
+        "attn_seq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=4), 4.0 * B * H * N * N * 128),
+        "attn3": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=5), 4.0 * B * H * N * N * 128),
+        "attn3_noseq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=6), 4.0 * B * H * N * N * 128),
         "rownorm": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm), 0.0),
         "linear1_f8": (lambda: ops.gemm_qkv(xm8, w1q, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:], a_scale=xs, w_scale=w1s),
                        2.0 * B * N * (3 * D + M) * D),

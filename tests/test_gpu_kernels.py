@@ -114,7 +114,7 @@ def test_conv3x3(B, H, W, Cin, Cout):
         ops.conv3x3(rnd(1, 4, 4, 16), rnd(8, 144), None)  # Cin must be a multiple of 64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6])
 @pytest.mark.parametrize("B,H,S", [(1, 1, 128), (2, 3, 512), (1, 2, 320), (1, 1, 77), (1, 2, 1280), (1, 1, 1)])
 def test_attention(variant, B, H, S):
     q, k, v = rnd(B, H, S, 128, seed=21), rnd(B, H, S, 128, seed=22), rnd(B, H, S, 128, seed=23)
@@ -125,21 +125,22 @@ def test_attention(variant, B, H, S):
     assert out[:, :, H * 128:].abs().max().item() == 0
 
 
-def test_attention_sharp_softmax_and_properties():
+@pytest.mark.parametrize("variant", [0, 5, 6])
+def test_attention_sharp_softmax_and_properties(variant):
     q, k, v = rnd(1, 2, 512, 128, seed=24, scale=4), rnd(1, 2, 512, 128, seed=25, scale=4), rnd(1, 2, 512, 128, seed=26)
     out = torch.empty(1, 512, 256, device=dev, dtype=bf)
-    ops.attention(q, k, v, out, 128 ** -0.5)
+    ops.attention(q, k, v, out, 128 ** -0.5, variant=variant)
     ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(1, 512, 256)
     assert rel_l2(out, ref) <= 5e-3
     # BASELINE size (one image, N = 4352): rows are convex combinations of V rows, and permuting the
     # keys/values together leaves the output unchanged
     q, k, v = rnd(1, 24, 4352, 128, seed=27), rnd(1, 24, 4352, 128, seed=28), rnd(1, 24, 4352, 128, seed=29)
     o1 = torch.empty(1, 4352, 3072, device=dev, dtype=bf)
-    ops.attention(q, k, v, o1, 128 ** -0.5)
+    ops.attention(q, k, v, o1, 128 ** -0.5, variant=variant)
     assert o1.float().abs().max() <= v.float().abs().max() + 1e-2
     perm = torch.randperm(4352, generator=torch.Generator().manual_seed(30)).to(dev)
     o2 = torch.empty_like(o1)
-    ops.attention(q, k[:, :, perm].contiguous(), v[:, :, perm].contiguous(), o2, 128 ** -0.5)
+    ops.attention(q, k[:, :, perm].contiguous(), v[:, :, perm].contiguous(), o2, 128 ** -0.5, variant=variant)
     assert rel_l2(o2, o1) <= 5e-3
     ref = F.scaled_dot_product_attention(q[:, :2].float(), k[:, :2].float(), v[:, :2].float()).transpose(1, 2).reshape(1, 4352, 256)
     assert rel_l2(o1[:, :, :256], ref) <= 5e-3
