@@ -577,8 +577,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 //   proxy fence + half-slot waits, both warpgroups now always contending for the same sub-partition), and the in-order
 //   issuer idles the tensor pipe between Q K(j+1)^T and the P it then waits for.  With two softmax warps per
 //   sub-partition the kernel is bound by the serial latency of the softmax instruction stream, not by the S -> P -> PV
-//   loop; the next step is more softmax threads per row, not a different hand-off.  (An earlier 64-key-step decoupled
-//   variant, attn2_kernel, was 15 % slower for the same reason plus N = 64 MMAs and has been removed.)
+//   loop.  Two more variants were built, measured and removed again: attn2_kernel (decoupled 64-key steps: -15 %, N = 64
+//   MMAs double the operand traffic) and attn4_kernel (two threads per query row = 16 softmax warps, partial maxima
+//   exchanged through shared memory behind 64-thread named barriers: correct, 3551 clocks -- the S -> P time per tile
+//   stayed at ~2100 clocks although each thread did half the work, i.e. the sub-partition, not the warp, is the limit;
+//   lesson kept: setmaxnreg.inc draws from the register pool the CTA was LAUNCHED with and blocks forever beyond it).
 // ------------------------------------------------------------------------------------------
 struct Attn3Cfg {
   static constexpr int KV_STAGES = 4;
