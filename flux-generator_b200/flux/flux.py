@@ -125,7 +125,9 @@ class FluxPipeline:
             t = timesteps[i]
             t_prev = timesteps[i + 1]
             fwd = self.flow.forward_graphed if self.use_graph else self.flow.forward
-            pred = fwd(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=scalar(t), guidance=guidance)
+            # one prompt, one t, one guidance for the whole batch: the conditioning path runs for one row (uniform)
+            pred = fwd(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=scalar(t), guidance=guidance,
+                       uniform=True)
             x_t = ops.euler_step(x_t.clone(), pred, t_prev - t)  # sampler.step (flux/sampler.py:56-57)
             yield x_t
 

@@ -244,7 +244,7 @@ class Flux:
         """chunk `idx` (shift, scale, gate[, shift2, scale2, gate2]) of modulation `key`: [B, D] view."""
         D = self.hidden_size
         off = self._mod_off[key] + idx * D
-        return ws["mod"][:, off:off + D]
+        return ws["modv"][:, off:off + D]
 
     def _workspace(self, B: int, L: int, S: int) -> dict:
         key = (B, L, S)
@@ -299,8 +299,13 @@ class Flux:
 
     # ------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
-                timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call)."""
+                timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
+                uniform: bool = False) -> torch.Tensor:
+        """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call).
+        uniform=True: the caller guarantees that every batch row carries the same (timestep, y, guidance) -- what
+        FluxPipeline always does (one prompt, one t per step) -- so the conditioning vector and the 1 056 768-wide
+        modulation GEMV run for ONE row and are broadcast (the GEMV over 8 identical rows is FMA-bound, over one row it
+        is the 6.5 GB weight stream)."""
         if img.ndim != 3 or txt.ndim != 3:
             raise ValueError("Input img and txt tensors must have 3 dimensions.")
         if self._lora_pending:  # an adapter was loaded without --fuse-adapter: this build always runs it fused
@@ -319,20 +324,25 @@ class Flux:
         timesteps = timesteps.to(bf16) if timesteps.dtype != bf16 else timesteps
 
         # ---- conditioning vector (flux/model.py:113-120) and every block's modulation in one GEMV
-        temb = ops.timestep_embedding(timesteps, 256)
-        ops.gemv(temb, self._w("time_in.in_layer"), self._b("time_in.in_layer"), out=ws["h"])
-        ops.gemv(ws["h"], self._w("time_in.out_layer"), self._b("time_in.out_layer"), silu_in=True, out=ws["vec"])
+        Bc = 1 if (uniform and B > 1) else B  # rows of (t, y, guidance) that actually differ
+        bh, bh2, bvec = ws["h"], ws["h2"], ws["vec"]
+        temb = ops.timestep_embedding(timesteps[:Bc], 256)
+        ops.gemv(temb, self._w("time_in.in_layer"), self._b("time_in.in_layer"), out=bh[:Bc])
+        ops.gemv(bh[:Bc], self._w("time_in.out_layer"), self._b("time_in.out_layer"), silu_in=True, out=bvec[:Bc])
         if p.guidance_embed:
-            gemb = ops.timestep_embedding(guidance.to(bf16), 256)
-            ops.gemv(gemb, self._w("guidance_in.in_layer"), self._b("guidance_in.in_layer"), out=ws["h"])
-            ops.gemv(ws["h"], self._w("guidance_in.out_layer"), self._b("guidance_in.out_layer"), silu_in=True,
-                     add=ws["vec"], out=ws["h2"])
-            ws["vec"], ws["h2"] = ws["h2"], ws["vec"]
-        ops.gemv(y, self._w("vector_in.in_layer"), self._b("vector_in.in_layer"), out=ws["h"])
-        ops.gemv(ws["h"], self._w("vector_in.out_layer"), self._b("vector_in.out_layer"), silu_in=True,
-                 add=ws["vec"], out=ws["h2"])
-        ws["vec"], ws["h2"] = ws["h2"], ws["vec"]
-        ops.gemv(ws["vec"], self.arena["__mod_w"], self.arena["__mod_b"], silu_in=True, out=ws["mod"])
+            gemb = ops.timestep_embedding(guidance[:Bc].to(bf16), 256)
+            ops.gemv(gemb, self._w("guidance_in.in_layer"), self._b("guidance_in.in_layer"), out=bh[:Bc])
+            ops.gemv(bh[:Bc], self._w("guidance_in.out_layer"), self._b("guidance_in.out_layer"), silu_in=True,
+                     add=bvec[:Bc], out=bh2[:Bc])
+            bvec, bh2 = bh2, bvec
+        ops.gemv(y[:Bc], self._w("vector_in.in_layer"), self._b("vector_in.in_layer"), out=bh[:Bc])
+        ops.gemv(bh[:Bc], self._w("vector_in.out_layer"), self._b("vector_in.out_layer"), silu_in=True,
+                 add=bvec[:Bc], out=bh2[:Bc])
+        bvec, bh2 = bh2, bvec
+        ws["vec"], ws["h2"] = bvec, bh2
+        ops.gemv(bvec[:Bc], self.arena["__mod_w"], self.arena["__mod_b"], silu_in=True, out=ws["mod"][:Bc])
+        # batch stride 0 when broadcast: every consumer takes the modulation's batch stride as an argument
+        ws["modv"] = ws["mod"][:1].expand(B, -1) if Bc < B else ws["mod"]
 
         # ---- embedders write straight into the joint buffer (text rows first)
         x_txt, x_img = x[:, :S], x[:, S:]
@@ -424,12 +434,13 @@ class Flux:
             ops.gemm(cat8, w8, self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x, a_scale=cs, w_scale=wsc)
 
     def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
-                        timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
+                        uniform: bool = False) -> torch.Tensor:
         """forward() replayed from a CUDA graph (captured once per shape and conditioning tensors): removes the
         ~450 host launches per step, which dominate the small configurations (512x512, batch 1).  `img`,
         `timesteps` and `guidance` are copied into static buffers; txt / y / ids are captured by address."""
         key = (tuple(img.shape), txt.data_ptr(), txt._version, y.data_ptr(), y._version, img_ids.data_ptr(),
-               txt_ids.data_ptr(), guidance is not None)
+               txt_ids.data_ptr(), guidance is not None, uniform)
         g = self._graphs.get(key) if hasattr(self, "_graphs") else None
         if g is None:
             if not hasattr(self, "_graphs"):
@@ -440,11 +451,11 @@ class Flux:
             st["t"].copy_(timesteps)
             if guidance is not None:
                 st["g"].copy_(guidance)
-            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"])  # warm-up: caches, attributes
+            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform)  # warm-up: caches, attributes
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"])
+                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform)
             st["graph"] = graph
             self._graphs = {key: st}  # one resident graph: shapes change rarely
             g = st

@@ -206,6 +206,26 @@ def test_cuda_graph_replay_is_bit_identical_to_eager():
         assert torch.equal(eager, graphed), f"step {step}"
 
 
+def test_uniform_conditioning_is_bit_identical():
+    """FluxPipeline's batches share one (t, y, guidance): forward(uniform=True) runs the conditioning GEMVs for one row
+    and broadcasts -- same bits as the per-row path, eager and graphed."""
+    cfg = small_configs()[0]
+    model, _, p = build_flow(cfg, True)
+    g = torch.Generator().manual_seed(12)
+    B, L, S = 3, 24, 16
+    img = torch.randn(B, L, 64, generator=g).to(bf).to(dev)
+    txt = torch.randn(1, S, cfg["context_in_dim"], generator=g).to(bf).to(dev).expand(B, -1, -1).contiguous()
+    y = torch.randn(1, cfg["vec_in_dim"], generator=g).to(bf).to(dev).expand(B, -1).contiguous()
+    ids = O.prepare_latent_images(torch.zeros(B, 8, 12, 16))[1].to(dev)
+    tids = torch.zeros(B, S, 3, dtype=torch.int32, device=dev)
+    ts = torch.full((B,), 0.75, dtype=bf, device=dev)
+    gd = torch.full((B,), 3.5, dtype=bf, device=dev)
+    ref = model.forward(img, ids, txt, tids, ts, y, gd).clone()
+    uni = model.forward(img, ids, txt, tids, ts, y, gd, uniform=True).clone()
+    assert torch.equal(ref, uni)
+    assert torch.equal(model.forward_graphed(img, ids, txt, tids, ts, y, gd, uniform=True), ref)
+
+
 def test_batch_invariance_and_determinism():
     """An image does not depend on what else is in the batch (sharding over GPUs is exact), and
     repeated runs are bit-identical."""
