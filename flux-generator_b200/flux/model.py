@@ -188,14 +188,15 @@ class Flux:
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
     def quantized_keys(self) -> List[str]:
-        """The Linears that run in FP8 when quantised: the four big projections of every block (97 % of the
-        step's FLOPs).  The reference's predicate is `isinstance(m, nn.Linear) and in_dim % 512 == 0` with MLX
-        4-bit groups (txt2image.py:79-82); attention `proj`, the embedders and the modulation GEMVs stay bf16."""
+        """The Linears that run in FP8 when quantised: every projection of every block (99 % of the step's linear
+        FLOPs).  The reference's predicate is `isinstance(m, nn.Linear) and in_dim % 512 == 0` with MLX 4-bit groups
+        (txt2image.py:79-82); the embedders, the final layer and the modulation GEMVs stay bf16."""
         p = self.params
         keys = []
         for i in range(p.depth):
             for s in ("img", "txt"):
-                keys += [f"double_blocks.{i}.{s}_attn.qkv", f"double_blocks.{i}.{s}_mlp.0", f"double_blocks.{i}.{s}_mlp.2"]
+                keys += [f"double_blocks.{i}.{s}_attn.qkv", f"double_blocks.{i}.{s}_attn.proj", f"double_blocks.{i}.{s}_mlp.0",
+                         f"double_blocks.{i}.{s}_mlp.2"]
         for i in range(p.depth_single_blocks):
             keys += [f"single_blocks.{i}.linear1", f"single_blocks.{i}.linear2"]
         return keys
@@ -388,8 +389,8 @@ class Flux:
         return ws["pred"]
 
     def _blocks_fp8(self, ws: dict, S: int, pe: torch.Tensor, scale: float) -> None:
-        """The 19 + 38 blocks with FP8 operands for qkv / mlp.0 / mlp.2 / linear1 / linear2 (same dataflow as the
-        bf16 path in forward(); `proj` stays bf16).  A operands: the AdaLN row norm writes e4m3 + row scales directly;
+        """The 19 + 38 blocks with FP8 operands for qkv / proj / mlp.0 / mlp.2 / linear1 / linear2 (same dataflow as the
+        bf16 path in forward()).  A operands: the AdaLN row norm writes e4m3 + row scales directly;
         the attention | GELU(mlp) buffer `cat` takes one fx_quantize_rows pass before mlp.2 / linear2."""
         p = self.params
         D = self.hidden_size
@@ -412,7 +413,10 @@ class Flux:
                 ak = pre + name + "_attn."
                 mlp = pre + name + "_mlp."
                 xr = x[:, rows]
-                ops.gemm(cat[:, rows, :D], self._w(ak + "proj"), self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xr, out=xr)
+                ops.quantize_rows(cat[:, rows, :D], out=cat8[:, rows, :D], out_scale=cs[:, rows])
+                w8, wsc = self._q8[ak + "proj"]
+                ops.gemm(cat8[:, rows, :D], w8, self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xr, out=xr,
+                         a_scale=cs[:, rows], w_scale=wsc)
                 ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
                 w8, wsc = self._q8[mlp + "0"]
                 ops.gemm(xm8[:, rows], w8, self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:], a_scale=xs[:, rows], w_scale=wsc)

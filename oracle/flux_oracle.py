@@ -64,7 +64,7 @@ class Mode:
 FP32 = Mode("fp32")
 
 
-FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
+FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|attn\.proj|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
 
 
 def fp8_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor]:

@@ -156,7 +156,7 @@ def _full_width(quantize):
 def test_flow_fp8_full_width_vs_quantised_oracle():
     """hidden 3072 / 24 heads, depth 1+1, batch 2: quantised CUDA forward vs the quantised and the plain oracle."""
     model, sd, (img, ids, txt, tids, ts, y, gd) = _full_width(True)
-    assert model.quantized and len(model.quantized_keys()) == 2 * 3 + 2
+    assert model.quantized and len(model.quantized_keys()) == 2 * 4 + 2
     op = O.FluxParams(depth=1, depth_single_blocks=1, guidance_embed=True)
     ref_q = O.flux_forward(sd, op, img.float(), ids, txt.float(), tids, ts, y.float(), gd, mode=O.Mode("fp32", quantize=True))
     ref = O.flux_forward(sd, op, img.float(), ids, txt.float(), tids, ts, y.float(), gd)

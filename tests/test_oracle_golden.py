@@ -161,7 +161,8 @@ def test_quantised_oracle_stays_close_to_fp32():
     from flux import specs, synthetic
     from oracle import flux_oracle as O
     assert O.FP8_LINEARS.match("double_blocks.3.img_attn.qkv") and O.FP8_LINEARS.match("single_blocks.37.linear2")
-    assert not O.FP8_LINEARS.match("double_blocks.3.img_attn.proj") and not O.FP8_LINEARS.match("txt_in")
+    assert O.FP8_LINEARS.match("double_blocks.3.img_attn.proj") and not O.FP8_LINEARS.match("txt_in")
+    assert not O.FP8_LINEARS.match("double_blocks.3.img_mod.lin") and not O.FP8_LINEARS.match("final_layer.linear")
     g = load("flow_schnell.npz")
     cfg = json.loads(str(g["config"]))
     p = specs.FluxParams(**cfg, guidance_embed=False)
