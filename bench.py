@@ -368,8 +368,8 @@ def main_arm(args) -> None:
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"], "traffic": 3.88e9, "peak_source": pk["src"],
-                         "traffic_note": "DRAM bytes per launch of the dominant member (single-block linear1, 34816x21504x3072), ncu --set full: profiles/r01_gemm_ncu_final.txt; algorithmic 1.84e9",
+                         "frac": achieved / pk["tflops"], "traffic": 4.22e9, "peak_source": pk["src"],
+                         "traffic_note": "DRAM bytes per launch of the dominant member (single-block linear1, 34816x21504x3072), ncu --set full: profiles/r01_gemm_ncu_c.txt; algorithmic 1.84e9 (operand tiles are shared between concurrent CTA pairs through L2 only: profiles/r01_l2_experiments.txt)",
                          "kernel": "fx::gemm_kernel<BN,EPI,CONV> (tcgen05 GEMM family: all Linear layers of the MMDiT + VAE 1x1)",
                          "launches_timed": gem["launches"], "share_of_step": gem["ms"] / eager_ms,
                          "note": "per-launch CUDA events over an eager (non-graph) repeat of the timed steps"},
