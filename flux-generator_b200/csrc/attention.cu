@@ -521,28 +521,24 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       SPROBE(j, 6);
     }
 
-    // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...]
+    // epilogue: O / l -> bf16 -> out[b][q_row][h*128 ...].  Every MMA has completed (o_full), so the K/V ring is free:
+    // it serves as the per-warp transposition buffer for coalesced stores (a thread owns a row: see sm100.cuh)
     mbar_wait(&o_full[i], 0);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
-    __nv_bfloat16* dst = p.out + (long long)blockIdx.z * p.out_bs + (long long)q_row * p.ld_out + blockIdx.y * 128;
+    uint8_t* wst = smem + Cfg::KV_OFF + (warp - ATT_SM0) * 2048;
+    const uint32_t vmask = __ballot_sync(0xffffffffu, q_row < p.seq);
+    __nv_bfloat16* dst0 = p.out + (long long)blockIdx.z * p.out_bs + (long long)(q_row - lane) * p.ld_out + blockIdx.y * 128;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
       __syncwarp();
       tmem_ld_x32(o_addr + c * 32, v);
       tmem_ld_wait();
-      if (q_row < p.seq) {
+      float f[32];
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c * 32 + e) = u;
-        }
-      }
+      for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * inv_l;
+      store_chunk32_coalesced(wst, lane, f, dst0 + c * 32, p.ld_out, vmask);
     }
   }
 

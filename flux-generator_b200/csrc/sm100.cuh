@@ -379,4 +379,34 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Coalesced store of one 32-column bf16 chunk of a warp's 32 accumulator rows.  In the tcgen05.ld layout a
+// thread owns a ROW, so a direct store makes every lane write 16 bytes into a different 128-byte line (32 half-
+// filled sectors per request: ncu showed the LSU / L1 store path, not the tensor pipe, bounding the FP8 kernels).
+// The chunk is transposed through a per-warp 2 KB shared-memory buffer (XOR-swizzled: conflict-free both ways)
+// so that each store instruction writes 8 rows x 64 contiguous bytes = 16 full sectors.
+//   f: this lane's 32 values (row = lane); base: address of (row 0 of the warp, first column of the chunk);
+//   ld: row stride in elements; vmask: bit r set = row r exists.
+__device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, const float* f, __nv_bfloat16* base,
+                                                        long long ld, uint32_t vmask, bool streaming = false) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(f[8 * j], f[8 * j + 1]); u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+  }
+  __syncwarp();
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const uint4 u = *reinterpret_cast<const uint4*>(wst + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+    if ((vmask >> r) & 1u) {
+      if (streaming) st_global_cs(base + r * ld + ch * 8, u);
+      else *reinterpret_cast<uint4*>(base + r * ld + ch * 8) = u;
+    }
+  }
+  __syncwarp();
+}
+
 }  // namespace fx
