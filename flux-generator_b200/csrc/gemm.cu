@@ -187,6 +187,7 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
                  a->ld_mlp % 8 == 0 && a->mlp_bs % 8 == 0,
              "fx_gemm_qkv: strides must be multiples of 16 bytes");
   FX_REQUIRE(!a->fp8 || (a->a_scale && a->w_scale), "fx_gemm_qkv: fp8 needs a_scale and w_scale");
+  FX_REQUIRE(!a->pe_blocked || (a->seq_off % 32 == 0), "fx_gemm_qkv: the blocked pe layout needs seq_off %% 32 == 0");
   GemmParams p{};
   p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
   p.k_blocks = (a->K * esz + 127) / 128;
@@ -196,6 +197,7 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   p.heads = a->heads; p.seq_total = a->seq_total; p.seq_off = a->seq_off; p.rms_eps = a->rms_eps;
   p.qnorm_w = (const __nv_bfloat16*)a->q_scale; p.knorm_w = (const __nv_bfloat16*)a->k_scale;
   p.pe = (const uint32_t*)a->pe;
+  p.pe_blocked = a->pe_blocked;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
   const int ncta = want_ncta(256);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);

@@ -54,7 +54,8 @@ struct GemmParams {
   int heads, seq_total, seq_off;
   float rms_eps;
   const __nv_bfloat16 *qnorm_w, *knorm_w;
-  const uint32_t* pe;  // [seq_total][64] (cos, sin) bf16 pairs
+  const uint32_t* pe;  // [seq_total][64] (cos, sin) bf16 pairs; or, pe_blocked, [seq/32][16 pieces][32 rows][16 B]
+  int pe_blocked;      // blocked layout: the 32 rows of a warp read each 16-byte piece as ONE 512-byte coalesced request
   __nv_bfloat16 *q, *k, *v;  // [batch][heads][seq_total][128]
   // ---- FP8 mode (F8): A, W are e4m3 with per-row / per-output-channel dequantisation scales,
   //      acc * a_scale[b][row] * w_scale[n] enters the epilogue in place of the raw accumulator
@@ -487,7 +488,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const bool active = g0 < p.N;
         const int hidx = g0 >> 7;
         const int which = (g0 >= D3) ? 3 : hidx / p.heads;  // 0 q, 1 k, 2 v, 3 mlp
-        const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe + pos * 64);
+        // piece k (4 (cos, sin) pairs) of this row: pe4[k * pe_st]
+        const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe) + (p.pe_blocked ? (pos >> 5) * 512 + (pos & 31) : pos * 16);
+        const int pe_st = p.pe_blocked ? 32 : 1;
         // ---- before the accumulator wait: bias / norm weight to smem, first RoPE chunk to registers
         uint4 pcur[4], pnxt[4];
         __syncwarp();
@@ -502,7 +505,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             stage_vec(sg, which == 0 ? p.qnorm_w : p.knorm_w, 0, 128, 128, 1.f, lane);
             if (valid) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pe4 + i);
+              for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pe4 + i * pe_st);
             }
           }
         }
@@ -562,7 +565,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int c = 0; c < 4; ++c) {  // pass 2: normalise, rotate, store
               if (which < 2 && valid && c < 3) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pe4 + (c + 1) * 4 + i);
+                for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pe4 + ((c + 1) * 4 + i) * pe_st);
               }
               uint32_t v[32];
               __syncwarp();

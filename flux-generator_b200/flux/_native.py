@@ -32,7 +32,7 @@ class QkvArgs(C.Structure):
                 ("mlp_out", c_vp), ("ld_mlp", c_i64), ("mlp_bs", c_i64), ("rms_eps", c_f32),
                 ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32), ("heads", c_i32),
                 ("seq_total", c_i32), ("seq_off", c_i32),
-                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp)]
+                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp), ("pe_blocked", c_i32)]
 
 
 class ConvArgs(C.Structure):

@@ -286,6 +286,11 @@ class Flux:
         if pe is None:
             ids = torch.cat([txt_ids[0].to("cpu"), img_ids[0].to("cpu")], dim=0)
             pe = self.rope_table(ids, self.params.axes_dim, self.params.theta).to(self.device)
+            if txt_ids.shape[1] % 32 == 0:  # every seq_off used below (0 and S) is a multiple of 32: coalesced layout
+                pe = ops.block_pe(pe)
+                self._pe_blocked = True
+            else:
+                self._pe_blocked = False
             self._pe_cache = {key: pe}
             self._keep_ids = (txt_ids, img_ids)  # pin the tensors whose addresses key the cache
         return pe
@@ -362,7 +367,7 @@ class Flux:
                 ops.rownorm(xs, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xms)
                 ak = pre + name + "_attn."
                 ops.gemm_qkv(xms, self._w(ak + "qkv"), self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
-                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS)
+                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS, pe_blocked=self._pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, xs, xms, cs, off in streams:
                 mk = pre + name + "_mod.lin"
@@ -378,7 +383,7 @@ class Flux:
             mk = pre + "modulation.lin"
             ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
             ops.gemm_qkv(xm, self._w(pre + "linear1"), self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
-                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS)
+                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS, pe_blocked=self._pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             ops.gemm(cat, self._w(pre + "linear2"), self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x)
 
@@ -406,7 +411,7 @@ class Flux:
                 w8, wsc = self._q8[ak + "qkv"]
                 ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
                              self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS,
-                             a_scale=xs[:, rows], w_scale=wsc)
+                             a_scale=xs[:, rows], w_scale=wsc, pe_blocked=self._pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, rows, off in streams:
                 mk = pre + name + "_mod.lin"
@@ -431,7 +436,7 @@ class Flux:
             w8, wsc = self._q8[pre + "linear1"]
             ops.gemm_qkv(xm8, w8, self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
                          self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
-                         a_scale=xs, w_scale=wsc)
+                         a_scale=xs, w_scale=wsc, pe_blocked=self._pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             ops.quantize_rows(cat, out=cat8, out_scale=cs)
             w8, wsc = self._q8[pre + "linear2"]

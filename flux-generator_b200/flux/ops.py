@@ -94,9 +94,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_scale: torch.Tensor,
              k_scale: torch.Tensor, pe: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
              seq_off: int, mlp_out: Optional[torch.Tensor] = None, rms_eps: float = 1e-5,
-             a_scale: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None) -> None:
-    """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16.
-    a / w may be float8_e4m3fn with a_scale / w_scale (see gemm)."""
+             a_scale: Optional[torch.Tensor] = None, w_scale: Optional[torch.Tensor] = None,
+             pe_blocked: bool = False) -> None:
+    """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16, or the blocked
+    layout of block_pe() with pe_blocked=True.  a / w may be float8_e4m3fn with a_scale / w_scale (see gemm)."""
     is8 = a.dtype == fp8
     _chk(a, fp8 if is8 else bf16), _chk(w, fp8 if is8 else bf16), _chk(q), _chk(k), _chk(v), _chk(pe)
     B, R, K, lda, abs_ = _as3(a)
@@ -113,9 +114,20 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_s
     args.rms_eps = rms_eps
     args.batch, args.rows, args.N, args.K = B, R, w.shape[0], K
     args.heads, args.seq_total, args.seq_off = H, seq_total, seq_off
+    args.pe_blocked = int(pe_blocked)
     if is8:
         _fp8_operands(args, a, w, a_scale, w_scale, B, R)
     N.check(N.lib().fx_gemm_qkv(C.byref(args), N.stream()))
+
+
+def block_pe(pe: torch.Tensor) -> torch.Tensor:
+    """RoPE table [N, 64, 2] bf16 -> blocked layout [ceil(N/32), 16 pieces, 32 rows, 8 bf16] for gemm_qkv(pe_blocked=True):
+    the QKV epilogue owns one row per thread, and in this layout a warp's 32 rows read each 16-byte piece contiguously."""
+    n = pe.shape[0]
+    nb = (n + 31) // 32
+    flat = torch.zeros((nb * 32, 16, 8), device=pe.device, dtype=pe.dtype)
+    flat[:n] = pe.reshape(n, 16, 8)
+    return flat.view(nb, 32, 16, 8).permute(0, 2, 1, 3).contiguous()
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor] = None,

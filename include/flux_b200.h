@@ -85,6 +85,9 @@ typedef struct fx_qkv_args {
   int32_t fp8;                 /* as fx_gemm_args.fp8 */
   const float* a_scale; int64_t a_scale_bs;
   const float* w_scale;
+  /* pe_blocked != 0: `pe` is laid out [ceil(seq_total / 32)][16 pieces][32 rows][16 bytes] (piece = 4 (cos, sin) pairs)
+   * so that the 32 rows a warp owns read every piece as one coalesced 512-byte request; needs seq_off % 32 == 0. */
+  int32_t pe_blocked;
 } fx_qkv_args;
 int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream);
 

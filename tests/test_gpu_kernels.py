@@ -100,6 +100,26 @@ def test_gemm_qkv_epilogue(B, R, H, K, mlp):
         assert rel_l2(mo[:, off:, D:], rm) <= 5e-3 and mo[:, :, :D].abs().max().item() == 0
 
 
+def test_gemm_qkv_blocked_rope_table_is_bit_identical():
+    """The coalesced (blocked) RoPE table layout gives the same bits as the plain [seq, 64, 2] table."""
+    B, R, H, K, off = 2, 200, 2, 256, 64
+    D = H * 128
+    a, w = rnd(B, R, K, seed=41), rnd(3 * D, K, seed=42, scale=K ** -0.5)
+    bias, qs, ks = rnd(3 * D, seed=43, scale=0.1), rnd(128, seed=44), rnd(128, seed=45)
+    ang = torch.rand(R + off, 64, generator=torch.Generator().manual_seed(46)) * 6.28
+    pe = torch.stack([torch.cos(ang), torch.sin(ang)], -1).to(bf).to(dev)
+    outs = []
+    for blocked in (False, True):
+        q = torch.zeros(B, H, R + off, 128, device=dev, dtype=bf)
+        k, v = torch.zeros_like(q), torch.zeros_like(q)
+        ops.gemm_qkv(a, w, bias, qs, ks, ops.block_pe(pe) if blocked else pe, q, k, v, off, pe_blocked=blocked)
+        outs.append((q, k, v))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    with pytest.raises(ValueError):  # the blocked layout needs seq_off % 32 == 0
+        ops.gemm_qkv(a, w, bias, qs, ks, ops.block_pe(pe), q, k, v, 40, pe_blocked=True)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 16, 64, 64), (2, 12, 20, 128, 256), (1, 33, 47, 64, 3), (1, 5, 3, 64, 128)])
 def test_conv3x3(B, H, W, Cin, Cout):
     x, w = rnd(B, H, W, Cin, seed=17), rnd(Cout, Cin, 3, 3, seed=18, scale=(9 * Cin) ** -0.5)
