@@ -116,7 +116,8 @@ template <bool F8 = false>
 __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f, const float* sb, const float* sg,
                                                   const uint4* rr, bool rr_ok, long long out_off, long long res_off,
                                                   int n0, bool fast, const float* sw = nullptr, float rs = 1.f,
-                                                  uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true) {
+                                                  uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true,
+                                                  long long lane_off = -1, long long ld_hi = -1) {
   if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -184,8 +185,10 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
           *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
       }
     } else if (wst != nullptr) {  // warp-collective: every lane takes part, rows are masked
-      store_chunk32_coalesced(wst, lane, f, reinterpret_cast<__nv_bfloat16*>(p.out) + out_off - (long long)lane * p.ldo + n0,
-                              p.ldo, vmask, p.stream_out != 0 && p.resid == nullptr);
+      // lane_off: distance (elements) from the warp's row 0 to this lane's row (lane * ldo unless the rows are image patches)
+      store_chunk32_coalesced(wst, lane, f,
+                              reinterpret_cast<__nv_bfloat16*>(p.out) + out_off - (lane_off < 0 ? (long long)lane * p.ldo : lane_off) + n0,
+                              p.ldo, vmask, p.stream_out != 0 && p.resid == nullptr, ld_hi);
     } else if (valid) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + n0;
 #pragma unroll
@@ -407,8 +410,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - GEMM_EPI0) * 384;  // bias (<= 128 floats)
     float* sg = sb + 128;                                                           // gate / norm weight
     float* sw = sb + 256;                                                           // FP8: per-column weight scales
-    // conv tiles map accumulator rows to 8x16 pixel patches (row -> address is not affine): direct stores there
-    uint8_t* wst = CONV ? nullptr : smem + Cfg::STORE_OFF + (warp - GEMM_EPI0) * 2048;
+    // conv tiles map accumulator rows to 8x16 pixel patches: a warp's 32 rows are two image lines of 16 pixels
+    uint8_t* wst = smem + Cfg::STORE_OFF + (warp - GEMM_EPI0) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
@@ -475,7 +478,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
             epi_generic_chunk<F8>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0,
-                                  vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs, wst, lane, vmask, valid);
+                                  vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs, wst, lane, vmask, valid,
+                                  CONV ? ((long long)(lane & 15) + (long long)(lane >> 4) * p.conv_W) * p.ldo : -1,
+                                  CONV ? (long long)p.conv_W * p.ldo : -1);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];

@@ -385,9 +385,12 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // The chunk is transposed through a per-warp 2 KB shared-memory buffer (XOR-swizzled: conflict-free both ways)
 // so that each store instruction writes 8 rows x 64 contiguous bytes = 16 full sectors.
 //   f: this lane's 32 values (row = lane); base: address of (row 0 of the warp, first column of the chunk);
-//   ld: row stride in elements; vmask: bit r set = row r exists.
+//   row r lives at base + (r & 15) * ld + (r >> 4) * ld_hi (ld_hi = 16 * ld for a matrix; the 3x3 convolution's rows are
+//   two image lines of 16 pixels: ld_hi = image width * ld); vmask: bit r set = row r exists.
 __device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, const float* f, __nv_bfloat16* base,
-                                                        long long ld, uint32_t vmask, bool streaming = false) {
+                                                        long long ld, uint32_t vmask, bool streaming = false,
+                                                        long long ld_hi = -1) {
+  if (ld_hi < 0) ld_hi = 16 * ld;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     uint4 u;
@@ -402,8 +405,9 @@ __device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, 
     const int r = (lane >> 2) + 8 * i;
     const uint4 u = *reinterpret_cast<const uint4*>(wst + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
     if ((vmask >> r) & 1u) {
-      if (streaming) st_global_cs(base + r * ld + ch * 8, u);
-      else *reinterpret_cast<uint4*>(base + r * ld + ch * 8) = u;
+      __nv_bfloat16* dst = base + (r & 15) * ld + (r >> 4) * ld_hi + ch * 8;
+      if (streaming) st_global_cs(dst, u);
+      else *reinterpret_cast<uint4*>(dst) = u;
     }
   }
   __syncwarp();
