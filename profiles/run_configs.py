@@ -28,6 +28,8 @@ def main():
             torch.cuda.empty_cache()
             pipes[model] = FluxPipeline("flux-" + model, synthetic=True, device="cuda")
         pipe = pipes[model]
+        if os.environ.get("RUN_QUANT") == "1" and not pipe.flow.quantized:
+            pipe.flow.quantize()  # the --quantize (FP8) path
         lat = (H // 8, W // 8)
         L, S = lat[0] * lat[1] // 4, (256 if model == "schnell" else 512)
         for graph in (True, False):
