@@ -348,7 +348,7 @@ def main_arm(args) -> None:
         pipe.flow.quantize()
         split_events.clear()
         q_ms, _, q_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
-        quant = {"dtype": "fp8_e4m3 (block Linears W8A8, per-row scales, fp32 accumulate; attention / proj / VAE bf16)",
+        quant = {"dtype": "fp8_e4m3 (block Linears W8A8, per-row scales, fp32 accumulate; attention / embedders / VAE bf16)",
                  "value": B * world * args.steps / (q_ms * 1e-3), "unit": UNIT, "ms_per_step": q_ms / args.steps,
                  "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
                  "clocks": q_clocks, "flag": "txt2image.py --quantize / Flux.quantize()",
