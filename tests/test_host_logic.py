@@ -178,3 +178,35 @@ def test_two_rank_gloo_sharding_and_broadcast(tmp_path):
             break
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok 0" in r.stdout and "ok 1" in r.stdout
+
+
+def test_blocked_rope_table_layout():
+    """ops.block_pe puts 16-byte piece k of position pos at uint4 index ((pos >> 5) * 16 + k) * 32 + (pos & 31) -- the
+    address the QKV epilogue computes (gemm.cuh) -- and pads the last block of 32 positions with zeros."""
+    import torch
+    from flux import ops
+    n = 77
+    pe = torch.arange(n * 128, dtype=torch.float32).reshape(n, 64, 2).to(torch.bfloat16)
+    blk = ops.block_pe(pe)
+    assert blk.shape == (3, 16, 32, 8) and blk.is_contiguous()
+    flat = blk.reshape(-1, 8)
+    src = pe.reshape(n, 16, 8)
+    for pos in (0, 1, 31, 32, 63, 76):
+        for k in (0, 5, 15):
+            assert torch.equal(flat[((pos >> 5) * 16 + k) * 32 + (pos & 31)], src[pos, k])
+    assert flat[((76 >> 5) * 16 + 3) * 32 + 13 + 1:].abs().sum() >= 0  # padded rows exist
+    assert torch.count_nonzero(blk[2, :, 13:]) == 0                    # positions 77..95 are zero padding
+
+
+def test_adapter_file_needs_metadata(tmp_path):
+    import pytest
+    import torch
+    from flux import lora
+    from safetensors.torch import save_file
+    f = tmp_path / "a.safetensors"
+    save_file({"single_blocks.0.linear1.lora_a": torch.zeros(8, 2)}, str(f))
+    with pytest.raises(ValueError, match="lora_rank"):   # txt2image.py:34-35 reads both keys unconditionally
+        lora.read_adapter(str(f))
+    save_file({"single_blocks.0.linear1.lora_a": torch.zeros(8, 2)}, str(f), metadata={"lora_rank": "2", "lora_blocks": "1"})
+    t, rank, blocks = lora.read_adapter(str(f))
+    assert (rank, blocks) == (2, 1) and list(t) == ["single_blocks.0.linear1.lora_a"]
