@@ -85,6 +85,17 @@ def test_pipeline_cache_and_model_names():
         assert b is not a and cls.call_args.args == ("flux-dev",) and inst.current_model == "flux-dev"
 
 
+def test_quantize_option_reaches_the_flow_model():
+    inst = FluxAPI(synthetic=True, quantize=True)
+    with patch("flux.FluxPipeline") as cls:
+        pipe = MagicMock()
+        cls.return_value = pipe
+        assert inst.init_pipeline("schnell") is pipe
+        pipe.flow.quantize.assert_called_once()          # --quantize: FP8 block Linears (Flux.quantize)
+        inst.init_pipeline("flux-schnell")
+        pipe.flow.quantize.assert_called_once()          # cached pipeline: not re-quantised
+
+
 def test_errors_become_http_500():
     client = TestClient(get_app(FluxAPI()))
     with patch.object(FluxAPI, "init_pipeline", side_effect=RuntimeError("boom")):
