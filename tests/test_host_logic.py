@@ -210,3 +210,22 @@ def test_adapter_file_needs_metadata(tmp_path):
     save_file({"single_blocks.0.linear1.lora_a": torch.zeros(8, 2)}, str(f), metadata={"lora_rank": "2", "lora_blocks": "1"})
     t, rank, blocks = lora.read_adapter(str(f))
     assert (rank, blocks) == (2, 1) and list(t) == ["single_blocks.0.linear1.lora_a"]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU oracle on the host cores) prints ONE JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "flux_schnell_1024x1024_4step_images_per_sec" and d["unit"] == "images/s"
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["higher_is_better"] is True and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
