@@ -118,16 +118,20 @@ class FluxPipeline:
         def scalar(x):
             return torch.full((B,), x, dtype=self.dtype, device=self.device)
 
+        guidance_value = guidance
         guidance = scalar(guidance)
         timesteps = self.sampler.timesteps(num_steps, x_t.shape[1], start=start, stop=stop)
+        table = self.flow.conditioning_table(timesteps[:num_steps], vec[:1],
+                                             guidance_value if self.flow.params.guidance_embed else None)
         x_t = x_t.clone()
         for i in range(num_steps):
             t = timesteps[i]
             t_prev = timesteps[i + 1]
             fwd = self.flow.forward_graphed if self.use_graph else self.flow.forward
-            # one prompt, one t, one guidance for the whole batch: the conditioning path runs for one row (uniform)
+            # one prompt, one t, one guidance for the whole batch, and none of them depends on x_t: the modulation of
+            # every step was computed above in one pass over the modulation weights
             pred = fwd(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=scalar(t), guidance=guidance,
-                       uniform=True)
+                       uniform=True, mod_row=table[i])
             x_t = ops.euler_step(x_t.clone(), pred, t_prev - t)  # sampler.step (flux/sampler.py:56-57)
             yield x_t
 

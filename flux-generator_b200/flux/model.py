@@ -303,11 +303,47 @@ class Flux:
             self._txt_cache = (key, out, txt)
         return self._txt_cache[1]
 
+    # ------------------------------------------------------------------ conditioning
+    def _conditioning(self, timesteps, y, guidance, bh, bh2, bvec, mod):
+        """vec = time_in(temb(t)) [+ guidance_in(temb(g))] + vector_in(y) (flux/model.py:113-120), then ALL modulation
+        Linears in one GEMV into `mod`.  Buffers hold one row per (t, y, guidance) row; returns (vec buffer, spare buffer)."""
+        p = self.params
+        temb = ops.timestep_embedding(timesteps, 256)
+        ops.gemv(temb, self._w("time_in.in_layer"), self._b("time_in.in_layer"), out=bh)
+        ops.gemv(bh, self._w("time_in.out_layer"), self._b("time_in.out_layer"), silu_in=True, out=bvec)
+        if p.guidance_embed:
+            gemb = ops.timestep_embedding(guidance.to(bf16), 256)
+            ops.gemv(gemb, self._w("guidance_in.in_layer"), self._b("guidance_in.in_layer"), out=bh)
+            ops.gemv(bh, self._w("guidance_in.out_layer"), self._b("guidance_in.out_layer"), silu_in=True, add=bvec, out=bh2)
+            bvec, bh2 = bh2, bvec
+        ops.gemv(y, self._w("vector_in.in_layer"), self._b("vector_in.in_layer"), out=bh)
+        ops.gemv(bh, self._w("vector_in.out_layer"), self._b("vector_in.out_layer"), silu_in=True, add=bvec, out=bh2)
+        bvec, bh2 = bh2, bvec
+        ops.gemv(bvec, self.arena["__mod_w"], self.arena["__mod_b"], silu_in=True, out=mod)
+        return bvec, bh2
+
+    def conditioning_table(self, timesteps, y1: torch.Tensor, guidance: Optional[float] = None) -> torch.Tensor:
+        """Modulation rows for ALL denoise steps of one prompt in one go: [len(timesteps), 1 056 768] bf16.
+        `vec` depends on (t, y, guidance) only, never on x_t (flux/model.py:113-120), so the 6.5 GB of modulation weights
+        are streamed once per 8 steps instead of once per step -- what matters for the batch-1 configurations, where that
+        stream is 2 of a step's 14-64 ms.  Row i is bit-identical to what forward() computes at step i."""
+        if self.params.guidance_embed and guidance is None:
+            raise ValueError("Didn't get guidance strength for guidance distilled model.")
+        n, D, dev = len(timesteps), self.hidden_size, self.device
+        t = torch.tensor(list(timesteps), dtype=torch.float32, device=dev).to(bf16)
+        y = y1.reshape(1, -1).to(device=dev, dtype=bf16).expand(n, -1).contiguous()
+        g = None if guidance is None else torch.full((n,), float(guidance), dtype=bf16, device=dev)
+        e = lambda *sh: torch.empty(sh, device=dev, dtype=bf16)  # noqa: E731
+        table = e(n, self._mod_total)
+        self._conditioning(t, y, g, e(n, D), e(n, D), e(n, D), table)
+        return table
+
     # ------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                 timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
-                uniform: bool = False) -> torch.Tensor:
+                uniform: bool = False, mod_row: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call).
+        mod_row: this step's row of conditioning_table() -- implies uniform conditioning; the GEMV chain is skipped.
         uniform=True: the caller guarantees that every batch row carries the same (timestep, y, guidance) -- what
         FluxPipeline always does (one prompt, one t per step) -- so the conditioning vector and the 1 056 768-wide
         modulation GEMV run for ONE row and are broadcast (the GEMV over 8 identical rows is FMA-bound, over one row it
@@ -330,25 +366,18 @@ class Flux:
         timesteps = timesteps.to(bf16) if timesteps.dtype != bf16 else timesteps
 
         # ---- conditioning vector (flux/model.py:113-120) and every block's modulation in one GEMV
-        Bc = 1 if (uniform and B > 1) else B  # rows of (t, y, guidance) that actually differ
-        bh, bh2, bvec = ws["h"], ws["h2"], ws["vec"]
-        temb = ops.timestep_embedding(timesteps[:Bc], 256)
-        ops.gemv(temb, self._w("time_in.in_layer"), self._b("time_in.in_layer"), out=bh[:Bc])
-        ops.gemv(bh[:Bc], self._w("time_in.out_layer"), self._b("time_in.out_layer"), silu_in=True, out=bvec[:Bc])
-        if p.guidance_embed:
-            gemb = ops.timestep_embedding(guidance[:Bc].to(bf16), 256)
-            ops.gemv(gemb, self._w("guidance_in.in_layer"), self._b("guidance_in.in_layer"), out=bh[:Bc])
-            ops.gemv(bh[:Bc], self._w("guidance_in.out_layer"), self._b("guidance_in.out_layer"), silu_in=True,
-                     add=bvec[:Bc], out=bh2[:Bc])
-            bvec, bh2 = bh2, bvec
-        ops.gemv(y[:Bc], self._w("vector_in.in_layer"), self._b("vector_in.in_layer"), out=bh[:Bc])
-        ops.gemv(bh[:Bc], self._w("vector_in.out_layer"), self._b("vector_in.out_layer"), silu_in=True,
-                 add=bvec[:Bc], out=bh2[:Bc])
-        bvec, bh2 = bh2, bvec
-        ws["vec"], ws["h2"] = bvec, bh2
-        ops.gemv(bvec[:Bc], self.arena["__mod_w"], self.arena["__mod_b"], silu_in=True, out=ws["mod"][:Bc])
-        # batch stride 0 when broadcast: every consumer takes the modulation's batch stride as an argument
-        ws["modv"] = ws["mod"][:1].expand(B, -1) if Bc < B else ws["mod"]
+        if mod_row is not None:
+            # the caller computed this step's modulation row up front (conditioning_table): nothing to stream here
+            ws["mod"][:1].copy_(mod_row.reshape(1, -1))
+            ws["modv"] = ws["mod"][:1].expand(B, -1)
+        else:
+            Bc = 1 if (uniform and B > 1) else B  # rows of (t, y, guidance) that actually differ
+            bvec, bh2 = self._conditioning(timesteps[:Bc], y[:Bc], None if guidance is None else guidance[:Bc],
+                                           ws["h"][:Bc], ws["h2"][:Bc], ws["vec"][:Bc], ws["mod"][:Bc])
+            if bvec.data_ptr() != ws["vec"].data_ptr():  # the chain ends in the other buffer: keep ws["vec"] = final vec
+                ws["vec"], ws["h2"] = ws["h2"], ws["vec"]
+            # batch stride 0 when broadcast: every consumer takes the modulation's batch stride as an argument
+            ws["modv"] = ws["mod"][:1].expand(B, -1) if Bc < B else ws["mod"]
 
         # ---- embedders write straight into the joint buffer (text rows first)
         x_txt, x_img = x[:, :S], x[:, S:]
@@ -444,27 +473,30 @@ class Flux:
 
     def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                         timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
-                        uniform: bool = False) -> torch.Tensor:
+                        uniform: bool = False, mod_row: Optional[torch.Tensor] = None) -> torch.Tensor:
         """forward() replayed from a CUDA graph (captured once per shape and conditioning tensors): removes the
         ~450 host launches per step, which dominate the small configurations (512x512, batch 1).  `img`,
         `timesteps` and `guidance` are copied into static buffers; txt / y / ids are captured by address."""
         key = (tuple(img.shape), txt.data_ptr(), txt._version, y.data_ptr(), y._version, img_ids.data_ptr(),
-               txt_ids.data_ptr(), guidance is not None, uniform)
+               txt_ids.data_ptr(), guidance is not None, uniform, mod_row is not None)
         g = self._graphs.get(key) if hasattr(self, "_graphs") else None
         if g is None:
             if not hasattr(self, "_graphs"):
                 self._graphs = {}
             st = dict(img=torch.empty_like(img, dtype=bf16), t=torch.empty_like(timesteps, dtype=bf16),
-                      g=None if guidance is None else torch.empty_like(guidance, dtype=bf16), keep=(txt, y, img_ids, txt_ids))
+                      g=None if guidance is None else torch.empty_like(guidance, dtype=bf16), keep=(txt, y, img_ids, txt_ids),
+                      mod=None if mod_row is None else torch.empty_like(mod_row.reshape(1, -1), dtype=bf16))
             st["img"].copy_(img)
             st["t"].copy_(timesteps)
             if guidance is not None:
                 st["g"].copy_(guidance)
-            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform)  # warm-up: caches, attributes
+            if mod_row is not None:
+                st["mod"].copy_(mod_row.reshape(1, -1))
+            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform, st["mod"])  # warm-up: caches, attributes
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform)
+                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform, st["mod"])
             st["graph"] = graph
             self._graphs = {key: st}  # one resident graph: shapes change rarely
             g = st
@@ -472,6 +504,8 @@ class Flux:
         g["t"].copy_(timesteps)
         if guidance is not None:
             g["g"].copy_(guidance)
+        if mod_row is not None:
+            g["mod"].copy_(mod_row.reshape(1, -1))
         g["graph"].replay()
         return g["pred"]
 

@@ -226,6 +226,31 @@ def test_uniform_conditioning_is_bit_identical():
     assert torch.equal(model.forward_graphed(img, ids, txt, tids, ts, y, gd, uniform=True), ref)
 
 
+@pytest.mark.parametrize("ge", [True, False])
+def test_conditioning_table_rows_are_bit_identical(ge):
+    """Flux.conditioning_table (all denoise steps' modulation in one pass) row i == what forward() computes at step i;
+    forward(mod_row=...) then gives the same bits as the per-step path, eager and graphed."""
+    cfg = small_configs()[0]
+    model, _, p = build_flow(cfg, ge)
+    g = torch.Generator().manual_seed(13)
+    B, L, S = 3, 24, 16
+    txt = torch.randn(1, S, cfg["context_in_dim"], generator=g).to(bf).to(dev).expand(B, -1, -1).contiguous()
+    y = torch.randn(1, cfg["vec_in_dim"], generator=g).to(bf).to(dev).expand(B, -1).contiguous()
+    ids = O.prepare_latent_images(torch.zeros(B, 8, 12, 16))[1].to(dev)
+    tids = torch.zeros(B, S, 3, dtype=torch.int32, device=dev)
+    gd = torch.full((B,), 3.5, dtype=bf, device=dev)
+    steps = [1.0, 0.9921875, 0.75, 0.5, 0.2501220703125, 0.1, 0.05, 0.01, 0.003]   # > 8 rows: two GEMV passes
+    table = model.conditioning_table(steps, y[:1], 3.5 if ge else None)
+    assert table.shape == (len(steps), model._mod_total)
+    for i, tval in enumerate(steps):
+        img = torch.randn(B, L, 64, generator=g).to(bf).to(dev)
+        ts = torch.full((B,), tval, dtype=bf, device=dev)
+        ref = model.forward(img, ids, txt, tids, ts, y, gd, uniform=True).clone()
+        assert torch.equal(next(iter(model._ws.values()))["mod"][0], table[i]), f"row {i}"
+        assert torch.equal(model.forward(img, ids, txt, tids, ts, y, gd, uniform=True, mod_row=table[i]), ref)
+        assert torch.equal(model.forward_graphed(img, ids, txt, tids, ts, y, gd, uniform=True, mod_row=table[i]), ref)
+
+
 def test_batch_invariance_and_determinism():
     """An image does not depend on what else is in the batch (sharding over GPUs is exact), and
     repeated runs are bit-identical."""
