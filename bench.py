@@ -50,6 +50,17 @@ def workload_config(n_gpus: int) -> dict:
             "l2": "inputs larger than L2: 23.8 GB of weights + 2 GB of activations stream per denoise step (126 MB L2)"}
 
 
+def measured_traffic() -> dict:
+    """DRAM bytes per launch of the dominant GEMM members, read from the committed ncu capture of THIS build
+    (profiles/gemm_traffic.json, written by profiles/parse_traffic.py from `ncu --metrics dram__bytes_*` over
+    tests/gpu_l2_probe.py).  None when no capture has been committed for the build."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def peaks() -> dict:
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -121,6 +132,8 @@ def reference_arm(args) -> None:
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "ms_per_step_note": "wall time of ONE bounded CPU sample (3 of 57 blocks for one image + a 256x256 VAE decode), "
+                                "not of the 8-image workload `value` is extrapolated to",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -273,9 +286,15 @@ def main_arm(args) -> None:
         split_events.append(ev)
         return out
 
+    cold = {"on": False, "n": 0}
+
     def step_e2e():
+        prompt = PROMPT
+        if cold["on"]:  # a prompt never seen before: tokenise + T5 + CLIP + txt_in + conditioning inside the step
+            cold["n"] += 1
+            prompt = f"{PROMPT} number {cold['n']} of rank {rank}"
         x = x_T_host.to(dev, non_blocking=True)                      # H2D: prior (+ token ids inside tokenize)
-        gen = pipe.generate_latents(PROMPT, n_images=B, num_steps=STEPS_DENOISE, guidance=4.0, latent_size=latent, x_T=x)
+        gen = pipe.generate_latents(prompt, n_images=B, num_steps=STEPS_DENOISE, guidance=4.0, latent_size=latent, x_T=x)
         next(gen)
         x_t = None
         for x_t in gen:
@@ -341,6 +360,25 @@ def main_arm(args) -> None:
     e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
     e2e_value = B * world * args.steps / (max(e2e_ms, e2e_wall) * 1e-3)
 
+    # ---- cold prompts: the same call with a NEW prompt every step (text encoders, txt_in, modulation table are not
+    # cached; the CUDA graph is keyed on shapes only and is replayed as before)
+    cold["on"] = True
+    graphs_before = len(pipe.flow._graphs)
+    c_ms, c_wall, _ = timed(step_e2e, args.steps, 1)
+    cold["on"] = False
+    cold_value = B * world * args.steps / (max(c_ms, c_wall) * 1e-3)
+    recaptured = len(pipe.flow._graphs) != graphs_before
+    # text encoders alone (T5-XXL + CLIP-L shapes, synthetic weights) for one fresh prompt
+    te = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t5_tok, clip_tok = pipe.tokenize(PROMPT + " text encoder timing")
+    torch.cuda.synchronize()
+    te[0].record()
+    pipe.t5(t5_tok)
+    pipe.clip(clip_tok)
+    te[1].record()
+    torch.cuda.synchronize()
+    text_ms = te[0].elapsed_time(te[1])
+
     # ---- --quantize leg (reported beside the bf16 headline, never in its place): the block Linears as FP8 e4m3
     # tcgen05 GEMMs (W8A8, per-row scales, fp32 accumulate); same workload, device-resident inputs
     quant = None
@@ -363,13 +401,18 @@ def main_arm(args) -> None:
                     gem[key] += ksum[name][key]
         achieved = gem["tflop"] / (gem["ms"] * 1e-3) if gem["ms"] > 0 else 0.0
         step_ms = ms / args.steps
+        traffic = measured_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["tflops"], "traffic": 4.22e9, "peak_source": pk["src"],
-                         "traffic_note": "DRAM bytes per launch of the dominant member (single-block linear1, 34816x21504x3072), ncu --set full: profiles/r01_gemm_ncu_c.txt; algorithmic 1.84e9 (operand tiles are shared between concurrent CTA pairs through L2 only: profiles/r01_l2_experiments.txt)",
+                         "frac": achieved / pk["tflops"], "traffic": traffic.get("linear1", {}).get("dram_bytes"),
+                         "peak_source": pk["src"],
+                         "traffic_note": "DRAM bytes (read + write) per launch of the dominant member (single-block linear1, "
+                                         "34816x21504x3072; algorithmic 1.84e9), from the committed ncu capture of this build: "
+                                         "profiles/gemm_traffic.json (all members under `traffic_members`)",
+                         "traffic_members": traffic,
                          "kernel": "fx::gemm_kernel<BN,EPI,CONV> (tcgen05 GEMM family: all Linear layers of the MMDiT + VAE 1x1)",
                          "launches_timed": gem["launches"], "share_of_step": gem["ms"] / eager_ms,
                          "note": "per-launch CUDA events over an eager (non-graph) repeat of the timed steps"},
@@ -380,6 +423,10 @@ def main_arm(args) -> None:
             "gpu_launches": int(launches), "cuda_graph": bool(use_graph), "eager_ms_per_step": eager_ms / args.steps, "clocks": clocks,
             # BASELINE metric's second half: per-denoise-step ms (one MMDiT forward + Euler update over the 8 images)
             "ms_per_denoise_step": denoise_ms, "ms_vae_decode_batch": decode_ms,
+            # a new prompt every step (tokenise + T5 + CLIP + txt_in + modulation table + 4 steps + decode, host buffers)
+            "e2e_cold_prompt": {"value": cold_value, "unit": UNIT, "ms_per_step": max(c_ms, c_wall) / args.steps,
+                                "vs_warm": cold_value / e2e_value, "graph_recaptured": bool(recaptured)},
+            "ms_text_encode": text_ms,
             "quantized": quant,
         }
         if not args.no_cpu:

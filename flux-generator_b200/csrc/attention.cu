@@ -9,6 +9,8 @@
 // P (bf16 probabilities) is handed to the P.V MMA either through TMEM (aliasing S, default) or through
 // 128B-swizzled shared memory (variant 1, bring-up fallback).  V is consumed MN-major straight from its
 // [seq][128] layout (no transposed copy).
+#include <mutex>
+
 #include "api_common.cuh"
 #include "sm100.cuh"
 #include "tmap.cuh"
@@ -1039,11 +1041,10 @@ static int launch_attn(const fx_attn_args* a, const CUtensorMap& tq, const CUten
                        const AttnParams& p, cudaStream_t st) {
   using Cfg = AttnCfg<P_TMEM>;
   auto kern = attn_kernel<P_TMEM>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    FX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES); });
+  if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(attr_err));
   dim3 grid((a->seq + 255) / 256, a->heads, a->batch);
   kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
   return launched("attn_kernel");
@@ -1070,11 +1071,10 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   if (a->variant == 5 || a->variant == 6) {
     // decoupled schedule (attn3_kernel): P through shared memory, Q K(j+1)^T issued as soon as S(j) has been read
     p.sequence = a->variant == 5 ? 1 : 0;
-    static bool attr3_done = false;
-    if (!attr3_done) {
-      FX_CUDA(cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg::SMEM_BYTES));
-      attr3_done = true;
-    }
+    static std::once_flag once3;
+    static cudaError_t attr3_err = cudaSuccess;
+    std::call_once(once3, [&] { attr3_err = cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg::SMEM_BYTES); });
+    if (attr3_err != cudaSuccess) return fail(FX_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(attr3_err));
     dim3 grid((a->seq + 255) / 256, a->heads, a->batch);
     attn3_kernel<<<grid, ATT_THREADS, Attn3Cfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p);
     return launched("attn3_kernel");

@@ -1,6 +1,7 @@
 // Bring-up probe (tests only, never on the product path): one CTA issues K/16 tcgen05.mma on operands
 // it lays out in shared memory by hand, with the descriptor fields supplied by the caller.  Lets a
 // single GPU run sweep UMMA descriptor encodings (MN-major B, A-from-TMEM) against a CPU matmul.
+#include "../../include/flux_b200_dbg.h"
 #include "api_common.cuh"
 #include "sm100.cuh"
 
@@ -293,4 +294,32 @@ extern "C" int fx_dbg_umma_tile(const void* A, const void* B, float* D, int32_t 
   }
   dbg_umma_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
   return launched("dbg_umma_kernel");
+}
+
+// CUDA-core reference GEMM (tests only): out[m][n] = sum_k A[m][k] W[n][k], fp32 out
+__global__ void dbg_gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
+                                    float* out, long long ldo, int M, int N, int K) {
+  __shared__ float sa[16][17], sw[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ka = k0 + tx;
+    sa[ty][tx] = (m < M && ka < K) ? __bfloat162float(A[(long long)m * lda + ka]) : 0.f;
+    const int nw = blockIdx.x * 16 + ty;
+    sw[ty][tx] = (nw < N && ka < K) ? __bfloat162float(W[(long long)nw * ldw + ka]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
+    __syncthreads();
+  }
+  if (m < M && n < N) out[(long long)m * ldo + n] = acc;
+}
+
+extern "C" int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo,
+                               int32_t M, int32_t N, int32_t K, fx_stream stream) {
+  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+  dbg_gemm_ref_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W,
+                                                               ldw, out, ldo, M, N, K);
+  return launched("dbg_gemm_ref_kernel");
 }

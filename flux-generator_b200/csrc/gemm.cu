@@ -52,13 +52,19 @@ static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   // Narrow outputs (N = 3072: 12 column tiles) run all their column tiles of ~6 row tiles in one wave, so every
   // A k-slice is fetched once per wave; wide outputs keep 16 row tiles per group (measured, sustained regime:
   // linear2 1136 -> 1159 TFLOP/s with small groups, linear1 / fc1 best at 16).  FX_GEMM_GROUP_M overrides.
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("FX_GEMM_GROUP_M");
-    forced = e ? atoi(e) : 0;
-  }
+  // (the raster knobs are read on every call -- a getenv is nanoseconds -- so one tuning process can sweep them)
+  const int forced = env_int("FX_GEMM_GROUP_M", 0);
   int gm = forced > 0 ? forced : (p.tiles_n <= 16 ? 6 : 16);
   p.group_m = p.tiles_m < gm ? p.tiles_m : gm;
+  // column bands for the long-K narrow-N members (see gemm_tile_coords): FX_GEMM_GROUP_N n-tiles per band when
+  // K >= FX_GEMM_GROUP_N_MINK; FX_GEMM_GROUP_M_BAND overrides group_m for banded launches
+  const int gn = env_int("FX_GEMM_GROUP_N", 0), gn_mink = env_int("FX_GEMM_GROUP_N_MINK", 8192),
+            gm_band = env_int("FX_GEMM_GROUP_M_BAND", 0);
+  p.group_n = 0;
+  if (gn > 0 && p.K >= gn_mink && p.tiles_n > gn) {
+    p.group_n = gn;
+    if (gm_band > 0) p.group_m = p.tiles_m < gm_band ? p.tiles_m : gm_band;
+  }
 }
 
 template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false>
@@ -258,32 +264,4 @@ extern "C" int fx_check_device(int device) {
   FX_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
   if (major != 10) return fail(FX_ERR_ARCH, "device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
   return FX_OK;
-}
-
-// CUDA-core reference GEMM (tests only): out[m][n] = sum_k A[m][k] W[n][k], fp32 out
-__global__ void dbg_gemm_ref_kernel(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* W, long long ldw,
-                                    float* out, long long ldo, int M, int N, int K) {
-  __shared__ float sa[16][17], sw[16][17];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    const int ka = k0 + tx;
-    sa[ty][tx] = (m < M && ka < K) ? __bfloat162float(A[(long long)m * lda + ka]) : 0.f;
-    const int nw = blockIdx.x * 16 + ty;
-    sw[ty][tx] = (nw < N && ka < K) ? __bfloat162float(W[(long long)nw * ldw + ka]) : 0.f;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sw[tx][k];
-    __syncthreads();
-  }
-  if (m < M && n < N) out[(long long)m * ldo + n] = acc;
-}
-
-extern "C" int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo,
-                               int32_t M, int32_t N, int32_t K, fx_stream stream) {
-  dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
-  dbg_gemm_ref_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W,
-                                                               ldw, out, ldo, M, N, K);
-  return launched("dbg_gemm_ref_kernel");
 }

@@ -41,6 +41,7 @@ __device__ LockstepSlots g_lockstep;
 struct GemmParams {
   int batch, rows, N, K;
   int tiles_m_per_batch, tiles_m, tiles_n, num_tiles, k_blocks, group_m;
+  int group_n;  // raster super-columns: n-tiles per column band (0 = one band of all n-tiles)
   // ---- generic epilogue: v = acc + bias; act; v *= gate[b][n]; v += resid[b][r][n]; store
   const __nv_bfloat16* bias;
   void* out;
@@ -85,14 +86,25 @@ struct GemmCfg {
                                     8 * 2048 /*store transposition*/ + 1024 /*align*/;
 };
 
+// Tile raster.  The n-tiles are cut into bands of `group_n` columns (one band = all columns when group_n == 0); a band
+// is walked in groups of `group_m` row tiles x the band's columns, rows fastest.  A wave of ~74 CTA pairs then works on
+// group_m A row-blocks and one band of W: for the long-K, narrow-N members (linear2 / fc2: W = 94 / 75 MB, more than
+// the L2 can keep next to the streaming A) a half-width band makes the resident part (the band's W rows, 47 MB) fit,
+// at the price of streaming A once per band.
 __device__ __forceinline__ void gemm_tile_coords(const GemmParams& p, int tile, int& tm, int& tn) {
-  const int per_group = p.group_m * p.tiles_n;
-  const int g = tile / per_group;
+  const int gn = p.group_n > 0 ? p.group_n : p.tiles_n;
+  const int per_band = p.tiles_m * gn;  // every band before the last is full
+  const int band = tile / per_band;
+  const int n0 = band * gn;
+  const int bw = min(gn, p.tiles_n - n0);
+  const int t = tile - band * per_band;
+  const int per_group = p.group_m * bw;
+  const int g = t / per_group;
   const int first_m = g * p.group_m;
   const int gsize = min(p.tiles_m - first_m, p.group_m);
-  const int rem = tile - g * per_group;
+  const int rem = t - g * per_group;
   tm = first_m + rem % gsize;
-  tn = rem / gsize;
+  tn = n0 + rem / gsize;
 }
 
 // 8 bf16 (one 16-byte vector) -> 8 floats

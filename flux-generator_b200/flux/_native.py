@@ -97,11 +97,34 @@ SYMBOLS = {
     "fx_finish_image": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "fx_embedding": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp]),
     "fx_act_mul": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+}
+
+
+# include/flux_b200_dbg.h: the test-only companion library (bring-up probes, CUDA-core reference GEMM)
+DBG_SYMBOLS = {
     "fx_dbg_gemm_ref": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp]),
     "fx_dbg_umma_tile": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, C.c_uint32, C.c_uint32,
                                    C.c_uint32, c_vp]),
     "fx_dbg_mma_pattern": (C.c_int, [c_i32, c_i32, c_vp, c_vp]),
 }
+_dbg = None
+
+
+def dbg_lib():
+    """libflux_b200_dbg.so (tests / profiling scripts only; the product path never loads it)."""
+    global _dbg
+    if _dbg is None:
+        lib()  # the product library first: the companion links against it
+        path = os.path.join(os.path.dirname(lib_path()), "libflux_b200_dbg.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not found: build it with `make -C flux-generator_b200/csrc`")
+        d = C.CDLL(path)
+        for name, (res, args) in DBG_SYMBOLS.items():
+            fn = getattr(d, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dbg = d
+    return _dbg
 
 
 def lib_path() -> str:

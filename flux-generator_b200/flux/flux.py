@@ -16,7 +16,9 @@ Differences that follow from the platform, not from choice:
 """
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import os
+from collections import OrderedDict
+from typing import Optional, Tuple
 
 import torch
 
@@ -27,7 +29,29 @@ from .utils import (load_ae, load_clip, load_clip_tokenizer, load_flow_model, lo
 bf16 = torch.bfloat16
 
 
+def _lru_put(cache: OrderedDict, key, value, limit: int):
+    cache[key] = value
+    cache.move_to_end(key)
+    while len(cache) > limit:
+        cache.popitem(last=False)
+    return value
+
+
+def _draw_seed(device) -> int:
+    """A fresh 63-bit seed for a call without `seed=` (the reference's global MLX PRNG is simply not reseeded then,
+    flux/flux.py:138-139: every call draws new noise).  With several ranks, rank 0's draw is broadcast so the shards of
+    one batch stay distinct (the prior is keyed by (seed, global image index)) but consistent."""
+    import torch.distributed as dist
+    seed = int.from_bytes(os.urandom(8), "little") >> 1
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([seed], dtype=torch.int64, device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
+    return seed
+
+
 class FluxPipeline:
+    COND_CACHE_PROMPTS = 16   # T5 / CLIP outputs kept (LRU)
     _b200_native = True  # callers that also accept reference-style pipelines (flux_app.py) key the GPU fast path on this
 
     def __init__(self, name: str, t5_padding: bool = True, synthetic: Optional[bool] = None,
@@ -51,10 +75,12 @@ class FluxPipeline:
         self.t5_tokenizer = load_t5_tokenizer(name, synthetic=synthetic,
                                               vocab_size=min(self.t5.config.vocab_size, 32100))
         self.sampler = FluxSampler(name)
-        self._cond_cache: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
-        self._bcast_cache: Dict[tuple, tuple] = {}
-        self._ids_cache: Dict[tuple, torch.Tensor] = {}
-        import os
+        # prompt cache (north star: T5 / CLIP "run once per prompt and cached"): a bounded LRU -- a long-running server
+        # sees an unbounded stream of prompts (4 MB of T5 output each)
+        self._cond_cache: "OrderedDict[tuple, Tuple[torch.Tensor, torch.Tensor]]" = OrderedDict()
+        self._bcast_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._ids_cache: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
+        self._txt_ids_cache: "OrderedDict[tuple, torch.Tensor]" = OrderedDict()
         self.use_graph = os.environ.get("FLUX_B200_GRAPH", "1") not in ("0", "")
 
     def ensure_models_are_loaded(self):
@@ -64,6 +90,8 @@ class FluxPipeline:
         kw = dict(synthetic=self._synthetic, device=str(self.device))
         self.t5 = load_t5(self.name, config=self._t5_config, **kw)
         self.clip = load_clip(self.name, config=self._clip_config, **kw)
+        self._cond_cache.clear()  # outputs of the previous encoders
+        self._bcast_cache.clear()
 
     def tokenize(self, text):
         t5_tokens = self.t5_tokenizer.encode(text, pad=self.t5_padding)
@@ -83,32 +111,44 @@ class FluxPipeline:
             j, k = torch.meshgrid(torch.arange(h // 2, dtype=torch.int32), torch.arange(w // 2, dtype=torch.int32),
                                   indexing="ij")
             x_ids = torch.stack([i, j, k], dim=-1).reshape(1, h * w // 4, 3).repeat(b, 1, 1).to(self.device)
-            self._ids_cache = {(b, h, w): x_ids}
+            _lru_put(self._ids_cache, (b, h, w), x_ids, 4)
         return x_ids
 
     def _prepare_conditioning(self, n_images, t5_tokens, clip_tokens):
-        key = (tuple(t5_tokens.flatten().tolist()), tuple(clip_tokens.flatten().tolist()))
+        key = (tuple(t5_tokens.flatten().tolist()), tuple(clip_tokens.flatten().tolist()), tuple(t5_tokens.shape))
         hit = self._cond_cache.get(key)
         if hit is None:
             if not hasattr(self, "t5") or not hasattr(self, "clip"):
                 raise RuntimeError("text encoders were deleted; call reload_text_encoders()")
             txt1 = self.t5(t5_tokens)
             vec1 = self.clip(clip_tokens).pooled_output
-            hit = (txt1, vec1)
-            self._cond_cache[key] = hit
-        # the broadcast copies are cached too: the flow model keys its txt_in cache and its CUDA graph on them
+            hit = _lru_put(self._cond_cache, key, (txt1, vec1), self.COND_CACHE_PROMPTS)
+        else:
+            self._cond_cache.move_to_end(key)
+        # the broadcast copies are cached too (the flow model keys its txt_in cache on the tensor)
         bkey = (key, n_images)
         bhit = self._bcast_cache.get(bkey)
         if bhit is None:
             txt, vec = hit
             if len(txt) == 1 and n_images > 1:
                 txt = txt.expand(n_images, *txt.shape[1:]).contiguous()
-            txt_ids = torch.zeros((n_images, txt.shape[1], 3), dtype=torch.int32, device=self.device)
-            if len(vec) == 1 and n_images > 1:
+            single = len(vec) == 1
+            if single and n_images > 1:
                 vec = vec.expand(n_images, *vec.shape[1:]).contiguous()
-            bhit = (txt, txt_ids, vec)
-            self._bcast_cache = {bkey: bhit}
+            if single:  # rows known identical without asking the device (see _denoising_loop)
+                self._uniform_vecs = {vec.data_ptr()} | {p for p in getattr(self, "_uniform_vecs", set())
+                                                         if any(p == b[2].data_ptr() for b in self._bcast_cache.values())}
+            bhit = _lru_put(self._bcast_cache, bkey, (txt, self._txt_ids(n_images, txt.shape[1]), vec), 2)
         return bhit
+
+    def _txt_ids(self, n_images: int, S: int) -> torch.Tensor:
+        """All-zero text position ids (flux/flux.py:84): ONE tensor per (batch, S), so the flow model's RoPE table and
+        CUDA graph (keyed on the id tensors) survive a change of prompt."""
+        ids = self._txt_ids_cache.get((n_images, S))
+        if ids is None:
+            ids = _lru_put(self._txt_ids_cache, (n_images, S),
+                           torch.zeros((n_images, S, 3), dtype=torch.int32, device=self.device), 4)
+        return ids
 
     # ------------------------------------------------------------------ flux/flux.py:87-126
     def _denoising_loop(self, x_t, x_ids, txt, txt_ids, vec, num_steps: int = 35, guidance: float = 4.0,
@@ -121,17 +161,22 @@ class FluxPipeline:
         guidance_value = guidance
         guidance = scalar(guidance)
         timesteps = self.sampler.timesteps(num_steps, x_t.shape[1], start=start, stop=stop)
-        table = self.flow.conditioning_table(timesteps[:num_steps], vec[:1],
-                                             guidance_value if self.flow.params.guidance_embed else None)
+        # One prompt for the whole batch (what txt2image.py / flux_app.py do): (t, y, guidance) are the same for every
+        # row and none depends on x_t, so the modulation of EVERY step is computed up front in one pass over the
+        # modulation weights.  A list of prompts (one per image, which tokenize() accepts like the reference's does)
+        # gives per-row CLIP vectors: then every row needs its own modulation and the per-row path runs.
+        uniform = len(vec) == 1 or vec.data_ptr() in getattr(self, "_uniform_vecs", ()) or bool((vec == vec[:1]).all())
+        table = None
+        if uniform:
+            table = self.flow.conditioning_table(timesteps[:num_steps], vec[:1],
+                                                 guidance_value if self.flow.params.guidance_embed else None)
         x_t = x_t.clone()
         for i in range(num_steps):
             t = timesteps[i]
             t_prev = timesteps[i + 1]
             fwd = self.flow.forward_graphed if self.use_graph else self.flow.forward
-            # one prompt, one t, one guidance for the whole batch, and none of them depends on x_t: the modulation of
-            # every step was computed above in one pass over the modulation weights
             pred = fwd(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=scalar(t), guidance=guidance,
-                       uniform=True, mod_row=table[i])
+                       uniform=uniform, mod_row=None if table is None else table[i])
             x_t = ops.euler_step(x_t.clone(), pred, t_prev - t)  # sampler.step (flux/sampler.py:56-57)
             yield x_t
 
@@ -142,8 +187,8 @@ class FluxPipeline:
             h, w = latent_size
             if h % 2 or w % 2:
                 raise ValueError(f"latent size {latent_size} must be even")
-            x_T = ops.prior_packed(n_images, latent_size, 16, 0 if seed is None else seed, self.first_image_index,
-                                   device=self.device)
+            x_T = ops.prior_packed(n_images, latent_size, 16, _draw_seed(self.device) if seed is None else seed,
+                                   self.first_image_index, device=self.device)
             x_ids = self._latent_ids(n_images, h, w)
         else:
             x_T, x_ids = self._prepare_latent_images(x_T)

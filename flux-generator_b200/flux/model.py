@@ -17,6 +17,7 @@ arena (one ``ncclBroadcast`` at load for multi-GPU).
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -70,6 +71,8 @@ class WeightArena:
 class Flux:
     """Drop-in for flux.model.Flux (flux/model.py:35-136) backed by sm_100a kernels."""
 
+    MAX_SHAPES = 4  # workspaces / RoPE tables / CUDA graphs kept resident (LRU)
+
     def __init__(self, params: FluxParams, device: Optional[str] = None):
         params.validate()  # same ValueErrors as flux/model.py:42-50
         self.params = params
@@ -101,8 +104,12 @@ class Flux:
         entries = [("__mod_w", (tot, D)), ("__mod_b", (tot,))]
         entries += [(k, s) for k, s, _ in self._manifest if not any(k.startswith(m + ".") for m in self._mod_keys)]
         self.arena = WeightArena(entries, self.device)
-        self._ws: Dict[Tuple[int, int, int], dict] = {}
-        self._pe_cache: Dict[tuple, torch.Tensor] = {}
+        # small LRUs: workspaces per (B, L, S), RoPE tables per id tensors, CUDA graphs per shape.  A captured graph
+        # keeps its own references to the workspace / table it replays into (see forward_graphed), so evicting an
+        # entry here never frees memory a resident graph still addresses.
+        self._ws: "OrderedDict[Tuple[int, int, int], dict]" = OrderedDict()
+        self._pe_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._txt_cache: Optional[tuple] = None
         self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
         self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
@@ -152,7 +159,7 @@ class Flux:
             if missing:
                 raise ValueError(f"Missing {len(missing)} parameters, e.g. {missing[:3]}")
         self._txt_cache = None
-        self._graphs = {}
+        self._graphs.clear()
         if self._q8:  # weights changed under a quantised model: requantise
             self._q8 = {}
             self.quantize()
@@ -180,7 +187,7 @@ class Flux:
             dst.add_(d.to(bf16))  # flux/lora.py:39: weight + (lora_b @ lora_a).astype(dtype)
         self._lora_pending = {}
         self._txt_cache = None
-        self._graphs = {}
+        self._graphs.clear()
         if self._q8:
             self._q8 = {}
             self.quantize()
@@ -218,8 +225,15 @@ class Flux:
             self._q8[k] = (q, s)
             o += n * kk
             r += n
-        self._graphs = {}
-        self._ws = {}  # the workspace gains the FP8 operand buffers
+        self._graphs.clear()
+        self._ws.clear()  # the workspace gains the FP8 operand buffers
+        return self
+
+    def dequantize(self) -> "Flux":
+        """Back to the bf16 Linears (drops the FP8 copies; the bf16 arena was never modified)."""
+        self._q8 = {}
+        self._graphs.clear()
+        self._ws.clear()
         return self
 
     @property
@@ -250,6 +264,8 @@ class Flux:
     def _workspace(self, B: int, L: int, S: int) -> dict:
         key = (B, L, S)
         ws = self._ws.get(key)
+        if ws is not None:
+            self._ws.move_to_end(key)
         if ws is None:
             D, H, M = self.hidden_size, self.num_heads, self.params.mlp_hidden
             N = S + L
@@ -263,7 +279,9 @@ class Flux:
                           cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
                           xs=torch.empty((B, N), device=dev, dtype=torch.float32),
                           cs=torch.empty((B, N), device=dev, dtype=torch.float32))
-            self._ws = {key: ws}  # keep one shape resident
+            self._ws[key] = ws
+            while len(self._ws) > self.MAX_SHAPES:  # a few shapes stay resident (server: mixed request sizes)
+                self._ws.popitem(last=False)
         return ws
 
     @staticmethod
@@ -280,20 +298,24 @@ class Flux:
             cs.append(torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1))
         return torch.cat(cs, dim=1).to(bf16).contiguous()
 
-    def _pe(self, txt_ids: torch.Tensor, img_ids: torch.Tensor) -> torch.Tensor:
+    def _pe(self, txt_ids: torch.Tensor, img_ids: torch.Tensor) -> Tuple[torch.Tensor, bool]:
+        """(RoPE table, blocked-layout flag) for the joint sequence; cached per id tensors (the pipeline hands out the
+        same id tensors for a given (batch, S, h, w), so a new prompt never rebuilds the table)."""
         key = (txt_ids.data_ptr(), img_ids.data_ptr(), tuple(txt_ids.shape), tuple(img_ids.shape))
-        pe = self._pe_cache.get(key)
-        if pe is None:
+        hit = self._pe_cache.get(key)
+        if hit is None:
             ids = torch.cat([txt_ids[0].to("cpu"), img_ids[0].to("cpu")], dim=0)
             pe = self.rope_table(ids, self.params.axes_dim, self.params.theta).to(self.device)
-            if txt_ids.shape[1] % 32 == 0:  # every seq_off used below (0 and S) is a multiple of 32: coalesced layout
+            blocked = txt_ids.shape[1] % 32 == 0  # every seq_off used below (0 and S) is a multiple of 32: coalesced layout
+            if blocked:
                 pe = ops.block_pe(pe)
-                self._pe_blocked = True
-            else:
-                self._pe_blocked = False
-            self._pe_cache = {key: pe}
-            self._keep_ids = (txt_ids, img_ids)  # pin the tensors whose addresses key the cache
-        return pe
+            hit = (pe, blocked, (txt_ids, img_ids))  # pin the tensors whose addresses key the cache
+            self._pe_cache[key] = hit
+            while len(self._pe_cache) > self.MAX_SHAPES:
+                self._pe_cache.popitem(last=False)
+        else:
+            self._pe_cache.move_to_end(key)
+        return hit[0], hit[1]
 
     def _txt_in(self, txt: torch.Tensor) -> torch.Tensor:
         """txt_in(txt) is step-invariant (flux/model.py:121 recomputes it every step): cached per tensor."""
@@ -327,6 +349,8 @@ class Flux:
         `vec` depends on (t, y, guidance) only, never on x_t (flux/model.py:113-120), so the 6.5 GB of modulation weights
         are streamed once per 8 steps instead of once per step -- what matters for the batch-1 configurations, where that
         stream is 2 of a step's 14-64 ms.  Row i is bit-identical to what forward() computes at step i."""
+        if self._lora_pending:  # the modulation Linears are adapted too: fuse before reading them
+            self.fuse_lora()
         if self.params.guidance_embed and guidance is None:
             raise ValueError("Didn't get guidance strength for guidance distilled model.")
         n, D, dev = len(timesteps), self.hidden_size, self.device
@@ -341,8 +365,10 @@ class Flux:
     # ------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                 timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
-                uniform: bool = False, mod_row: Optional[torch.Tensor] = None) -> torch.Tensor:
+                uniform: bool = False, mod_row: Optional[torch.Tensor] = None,
+                _txt_emb: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Same as __call__ but returns the workspace-owned prediction buffer (overwritten by the next call).
+        _txt_emb: txt_in(txt) computed by the caller (forward_graphed keeps it in a static buffer).
         mod_row: this step's row of conditioning_table() -- implies uniform conditioning; the GEMV chain is skipped.
         uniform=True: the caller guarantees that every batch row carries the same (timestep, y, guidance) -- what
         FluxPipeline always does (one prompt, one t per step) -- so the conditioning vector and the 1 056 768-wide
@@ -382,12 +408,12 @@ class Flux:
         # ---- embedders write straight into the joint buffer (text rows first)
         x_txt, x_img = x[:, :S], x[:, S:]
         ops.gemm(img, self._w("img_in"), self._b("img_in"), out=x_img)
-        x_txt.copy_(self._txt_in(txt))
-        pe = self._pe(txt_ids, img_ids)
+        x_txt.copy_(self._txt_in(txt) if _txt_emb is None else _txt_emb)
+        pe, pe_blocked = self._pe(txt_ids, img_ids)
         scale = 128 ** -0.5
 
         if self._q8:
-            self._blocks_fp8(ws, S, pe, scale)
+            self._blocks_fp8(ws, S, pe, pe_blocked, scale)
         for i in range(0 if self._q8 else p.depth):
             pre = f"double_blocks.{i}."
             streams = (("img", x_img, xm[:, S:], cat[:, S:], S), ("txt", x_txt, xm[:, :S], cat[:, :S], 0))
@@ -396,7 +422,7 @@ class Flux:
                 ops.rownorm(xs, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xms)
                 ak = pre + name + "_attn."
                 ops.gemm_qkv(xms, self._w(ak + "qkv"), self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
-                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS, pe_blocked=self._pe_blocked)
+                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, xs, xms, cs, off in streams:
                 mk = pre + name + "_mod.lin"
@@ -412,7 +438,7 @@ class Flux:
             mk = pre + "modulation.lin"
             ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
             ops.gemm_qkv(xm, self._w(pre + "linear1"), self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
-                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS, pe_blocked=self._pe_blocked)
+                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             ops.gemm(cat, self._w(pre + "linear2"), self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x)
 
@@ -422,7 +448,7 @@ class Flux:
         ops.gemm(xm[:, S:], self._w("final_layer.linear"), self._b("final_layer.linear"), out=ws["pred"])
         return ws["pred"]
 
-    def _blocks_fp8(self, ws: dict, S: int, pe: torch.Tensor, scale: float) -> None:
+    def _blocks_fp8(self, ws: dict, S: int, pe: torch.Tensor, pe_blocked: bool, scale: float) -> None:
         """The 19 + 38 blocks with FP8 operands for qkv / proj / mlp.0 / mlp.2 / linear1 / linear2 (same dataflow as the
         bf16 path in forward()).  A operands: the AdaLN row norm writes e4m3 + row scales directly;
         the attention | GELU(mlp) buffer `cat` takes one fx_quantize_rows pass before mlp.2 / linear2."""
@@ -440,7 +466,7 @@ class Flux:
                 w8, wsc = self._q8[ak + "qkv"]
                 ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
                              self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS,
-                             a_scale=xs[:, rows], w_scale=wsc, pe_blocked=self._pe_blocked)
+                             a_scale=xs[:, rows], w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, rows, off in streams:
                 mk = pre + name + "_mod.lin"
@@ -465,7 +491,7 @@ class Flux:
             w8, wsc = self._q8[pre + "linear1"]
             ops.gemm_qkv(xm8, w8, self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
                          self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
-                         a_scale=xs, w_scale=wsc, pe_blocked=self._pe_blocked)
+                         a_scale=xs, w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             ops.quantize_rows(cat, out=cat8, out_scale=cs)
             w8, wsc = self._q8[pre + "linear2"]
@@ -474,40 +500,60 @@ class Flux:
     def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                         timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
                         uniform: bool = False, mod_row: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """forward() replayed from a CUDA graph (captured once per shape and conditioning tensors): removes the
-        ~450 host launches per step, which dominate the small configurations (512x512, batch 1).  `img`,
-        `timesteps` and `guidance` are copied into static buffers; txt / y / ids are captured by address."""
-        key = (tuple(img.shape), txt.data_ptr(), txt._version, y.data_ptr(), y._version, img_ids.data_ptr(),
-               txt_ids.data_ptr(), guidance is not None, uniform, mod_row is not None)
-        g = self._graphs.get(key) if hasattr(self, "_graphs") else None
+        """forward() replayed from a CUDA graph: removes the ~450 host launches per step, which dominate the small
+        configurations (512x512, batch 1).  The graph is keyed on SHAPES only: everything prompt- or step-dependent
+        (img, timesteps, guidance, y, this step's modulation row and txt_in(txt), which is computed outside the graph
+        once per prompt) is copied into static buffers before the replay, so a new prompt costs one small GEMM and a
+        few copies -- never a re-capture.  Up to MAX_SHAPES graphs stay resident (LRU); each keeps references to the
+        workspace and the RoPE table it replays into."""
+        if img.ndim != 3 or txt.ndim != 3:
+            raise ValueError("Input img and txt tensors must have 3 dimensions.")
+        if self._lora_pending:
+            self.fuse_lora()
+        if self.params.guidance_embed and guidance is None:
+            raise ValueError("Didn't get guidance strength for guidance distilled model.")
+        B, L, _ = img.shape
+        S = txt.shape[1]
+        pe, _ = self._pe(txt_ids, img_ids)
+        temb = self._txt_in(txt.to(bf16) if txt.dtype != bf16 else txt)
+        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8))
+        g = self._graphs.get(key)
         if g is None:
-            if not hasattr(self, "_graphs"):
-                self._graphs = {}
-            st = dict(img=torch.empty_like(img, dtype=bf16), t=torch.empty_like(timesteps, dtype=bf16),
-                      g=None if guidance is None else torch.empty_like(guidance, dtype=bf16), keep=(txt, y, img_ids, txt_ids),
-                      mod=None if mod_row is None else torch.empty_like(mod_row.reshape(1, -1), dtype=bf16))
-            st["img"].copy_(img)
-            st["t"].copy_(timesteps)
-            if guidance is not None:
-                st["g"].copy_(guidance)
-            if mod_row is not None:
-                st["mod"].copy_(mod_row.reshape(1, -1))
-            self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform, st["mod"])  # warm-up: caches, attributes
+            D = self.hidden_size
+            e = lambda *sh: torch.empty(sh, device=self.device, dtype=bf16)  # noqa: E731
+            st = dict(img=e(*img.shape), t=e(*timesteps.shape), temb=e(B, S, D), y=e(*y.shape),
+                      g=None if guidance is None else e(*guidance.shape),
+                      mod=None if mod_row is None else e(1, self._mod_total),
+                      ws=self._workspace(B, L, S), pe=pe, ids=(img_ids, txt_ids))
+            self._copy_in(st, img, timesteps, y, guidance, mod_row, temb)
+            args = (st["img"], img_ids, txt, txt_ids, st["t"], st["y"], st["g"], uniform, st["mod"], st["temb"])
+            self.forward(*args)  # warm-up: kernel attributes, caches
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                st["pred"] = self.forward(st["img"], img_ids, txt, txt_ids, st["t"], y, st["g"], uniform, st["mod"])
+                st["pred"] = self.forward(*args)
             st["graph"] = graph
-            self._graphs = {key: st}  # one resident graph: shapes change rarely
+            self._graphs[key] = st
+            while len(self._graphs) > self.MAX_SHAPES:
+                self._graphs.popitem(last=False)
             g = st
-        g["img"].copy_(img)
-        g["t"].copy_(timesteps)
-        if guidance is not None:
-            g["g"].copy_(guidance)
-        if mod_row is not None:
-            g["mod"].copy_(mod_row.reshape(1, -1))
+        else:
+            self._graphs.move_to_end(key)
+            self._ws[(B, L, S)] = g["ws"]  # the replay writes into this workspace: it is the current one for (B, L, S)
+        self._copy_in(g, img, timesteps, y, guidance, mod_row, temb)
         g["graph"].replay()
         return g["pred"]
+
+    @staticmethod
+    def _copy_in(st: dict, img, timesteps, y, guidance, mod_row, temb) -> None:
+        st["img"].copy_(img)
+        st["t"].copy_(timesteps)
+        st["y"].copy_(y)
+        st["temb"].copy_(temb)
+        if guidance is not None:
+            st["g"].copy_(guidance)
+        if mod_row is not None:
+            st["mod"].copy_(mod_row.reshape(1, -1))
 
     def __call__(self, img, img_ids, txt, txt_ids, timesteps, y, guidance=None) -> torch.Tensor:
         """Flux.__call__ (flux/model.py:99-136): returns a fresh [B, L, in_channels] bf16 tensor."""

@@ -372,7 +372,7 @@ def dbg_gemm_ref(a: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     M, K = a.shape
     Nn = w.shape[0]
     out = torch.empty((M, Nn), device=a.device, dtype=torch.float32)
-    N.check(N.lib().fx_dbg_gemm_ref(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), Nn, M, Nn,
+    N.check(N.dbg_lib().fx_dbg_gemm_ref(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), Nn, M, Nn,
                                     K, N.stream()))
     return out
 
@@ -381,6 +381,6 @@ def dbg_umma_tile(a: torch.Tensor, b: torch.Tensor, n: int, b_mn_major: bool, a_
                   kstep: int) -> torch.Tensor:
     K = a.shape[1]
     d = torch.empty((128, n), device=a.device, dtype=torch.float32)
-    N.check(N.lib().fx_dbg_umma_tile(a.data_ptr(), b.data_ptr(), d.data_ptr(), K, n, int(b_mn_major), int(a_tmem),
+    N.check(N.dbg_lib().fx_dbg_umma_tile(a.data_ptr(), b.data_ptr(), d.data_ptr(), K, n, int(b_mn_major), int(a_tmem),
                                      lbo, sbo, kstep, N.stream()))
     return d

@@ -89,10 +89,14 @@ def _rank_world():
 
 def _finish(model, device_sd, synthetic_manifest, synthetic: bool, gen_device: str):
     """Rank 0 materialises the tensors; with more than one rank the whole arena then travels once over
-    NCCL / NVLink (north star: "NCCL over NVLink used only to broadcast weights at load")."""
+    NCCL / NVLink (north star: "NCCL over NVLink used only to broadcast weights at load").
+    device_sd: a state dict, or a zero-argument callable returning one -- the checkpoint READER, which only rank 0
+    ever calls (the other ranks receive the arena over NVLink and never touch the 24 GB file)."""
     rank, world = _rank_world()
     if rank == 0 or world == 1:
         if device_sd is not None:
+            if callable(device_sd):
+                device_sd = device_sd()
             model.load_weights(list(model.sanitize(device_sd).items()))
         elif synthetic:
             for entry in synthetic_manifest:  # one tensor at a time: no second copy of the model
@@ -113,7 +117,8 @@ def load_flow_model(name: str, hf_download: bool = True, synthetic: Optional[boo
         return _finish(model, None, flow_manifest(params), True, gen_device)
     if path is None and not hf_download:
         return model  # reference: model left at its random init
-    return _finish(model, _load_safetensors(_need(path, f"{name} flow checkpoint")), None, False, gen_device)
+    path = _need(path, f"{name} flow checkpoint")
+    return _finish(model, lambda: _load_safetensors(path), None, False, gen_device)
 
 
 def load_ae(name: str, hf_download: bool = True, synthetic: Optional[bool] = None,
@@ -126,7 +131,8 @@ def load_ae(name: str, hf_download: bool = True, synthetic: Optional[bool] = Non
         return _finish(ae, None, ae_decoder_manifest(params), True, gen_device)
     if path is None and not hf_download:
         return ae
-    return _finish(ae, _load_safetensors(_need(path, "autoencoder checkpoint (AE)")), None, False, gen_device)
+    path = _need(path, "autoencoder checkpoint (AE)")
+    return _finish(ae, lambda: _load_safetensors(path), None, False, gen_device)
 
 
 def load_clip(name: str, synthetic: Optional[bool] = None, config: Optional[CLIPTextModelConfig] = None,
@@ -137,8 +143,8 @@ def load_clip(name: str, synthetic: Optional[bool] = None, config: Optional[CLIP
         return _finish(CLIPTextModel(config, device=device), None, clip_manifest(config), True, gen_device)
     with open(_need(_hf_file(name, "text_encoder/config.json"), "text_encoder/config.json")) as f:
         config = CLIPTextModelConfig.from_dict(json.load(f))
-    sd = _load_safetensors(_need(_hf_file(name, "text_encoder/model.safetensors"), "text_encoder/model.safetensors"))
-    return _finish(CLIPTextModel(config, device=device), sd, None, False, gen_device)
+    path = _need(_hf_file(name, "text_encoder/model.safetensors"), "text_encoder/model.safetensors")
+    return _finish(CLIPTextModel(config, device=device), lambda: _load_safetensors(path), None, False, gen_device)
 
 
 def load_t5(name: str, synthetic: Optional[bool] = None, config: Optional[T5Config] = None,
@@ -152,10 +158,15 @@ def load_t5(name: str, synthetic: Optional[bool] = None, config: Optional[T5Conf
     index = _need(_hf_file(name, "text_encoder_2/model.safetensors.index.json"), "text_encoder_2 index")
     with open(index) as f:
         files = sorted(set(json.load(f)["weight_map"].values()))
-    sd = {}
-    for w in files:
-        sd.update(_load_safetensors(_need(_hf_file(name, f"text_encoder_2/{w}"), w)))
-    return _finish(T5Encoder(config, device=device), sd, None, False, gen_device)
+    paths = [_need(_hf_file(name, f"text_encoder_2/{w}"), w) for w in files]
+
+    def read():
+        sd = {}
+        for w in paths:
+            sd.update(_load_safetensors(w))
+        return sd
+
+    return _finish(T5Encoder(config, device=device), read, None, False, gen_device)
 
 
 def load_clip_tokenizer(name: str, synthetic: Optional[bool] = None, vocab_size: int = 49408):

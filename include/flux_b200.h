@@ -227,24 +227,6 @@ int fx_embedding(const int32_t* ids, const void* table, const void* pos_table, v
 /* y = act(a) * b elementwise (T5 gated FFN, flux/t5.py:178-184), act = fx_act */
 int fx_act_mul(const void* a, const void* b, void* out, int64_t n, int32_t act, fx_stream stream);
 
-/* ---------------------------------------------------------------- bring-up / test kernels
- * Plain CUDA-core reference kernels used only by tests to check the tcgen05 paths at sizes the CPU
- * oracle cannot reach.  Never called by the product path. */
-int fx_dbg_gemm_ref(const void* A, int64_t lda, const void* W, int64_t ldw, float* out, int64_t ldo, int32_t M,
-                    int32_t N, int32_t K, fx_stream stream);
-
-/* One CTA, K/16 tcgen05.mma on hand-laid shared-memory operands with caller-supplied descriptor fields:
- * sweeps UMMA encodings (MN-major B, A-from-TMEM) against a CPU matmul.  A [128][K]; B [N][K] (K-major) or
- * [K][N] (MN-major); D float [128][N]. */
-int fx_dbg_umma_tile(const void* A, const void* B, float* D, int32_t K, int32_t N, int32_t b_mn_major,
-                     int32_t a_tmem, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, fx_stream stream);
-
-/* Tensor-pipe issue-pattern micro-benchmark (profiling only): every SM's CTA has one thread issue `iters`
- * steps of 32 tcgen05.mma (128x128x16) in one of a dozen fixed orders (the attention kernel's QK / PV
- * sequence with and without commits, single-kind streams, N = 256, two issuing threads ...) on the attention
- * kernel's shared-memory / TMEM layout; writes the SM-clock count of CTA 0 to clocks_out[0]. */
-int fx_dbg_mma_pattern(int32_t pattern, int32_t iters, int64_t* clocks_out, fx_stream stream);
-
 #ifdef __cplusplus
 }
 #endif

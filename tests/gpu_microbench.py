@@ -10,9 +10,6 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "flux-generator_b200"))
 from flux import _native, ops  # noqa: E402
 
-if os.environ.get("MB_ALLOW_MISSING"):  # A/B against an older build of the library that lacks newer debug symbols
-    for _k in [k for k in _native.SYMBOLS if k.startswith("fx_dbg_")]:
-        _native.SYMBOLS.pop(_k)
 try:
     import pynvml
     pynvml.nvmlInit()
@@ -54,7 +51,7 @@ def sustained(fn, flops):
     return ms, flops / ms / 1e9
 
 
-def main(which):
+def main(which, sweep=None):
     g = torch.Generator(device=dev).manual_seed(0)
     r = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc).to(bf)  # noqa: E731
     x = r(B, N, D)
@@ -64,6 +61,7 @@ def main(which):
     w1, b1 = r(3 * D + M, D, sc=D ** -0.5), r(3 * D + M, sc=0.1)
     w2, b2 = r(D, D + M, sc=(D + M) ** -0.5), r(D, sc=0.1)
     wfc1, bfc1 = r(M, D, sc=D ** -0.5), r(M, sc=0.1)
+    wfc2, wproj = r(D, M, sc=M ** -0.5), r(D, D, sc=D ** -0.5)
     qs, ks = r(128), r(128)
     pe = r(N, 64, 2)
     gate = r(B, D, sc=0.1)
@@ -79,6 +77,8 @@ def main(which):
     tests = {
         "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
         "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
+        "fc2": (lambda: ops.gemm(cat[:, S:, D:], wfc2, b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * M),
+        "proj": (lambda: ops.gemm(cat[:, S:, :D], wproj, b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * D),
         "fc1": (lambda: ops.gemm(xm[:, S:], wfc1, bfc1, act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "fc1_bias": (lambda: ops.gemm(xm[:, S:], wfc1, bfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "fc1_gelu": (lambda: ops.gemm(xm[:, S:], wfc1, act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
@@ -98,6 +98,15 @@ def main(which):
         "rownorm_f8": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm8, out_scale=xs), 0.0),
         "cublas_l1": (lambda: torch.matmul(xm.view(-1, D), w1.T), 2.0 * B * N * (3 * D + M) * D),
     }
+    if sweep:  # raster sweep of the long-K members: FX_GEMM_GROUP_N (band width) x FX_GEMM_GROUP_M_BAND, one process
+        for gn, gm in sweep:
+            os.environ["FX_GEMM_GROUP_N"], os.environ["FX_GEMM_GROUP_M_BAND"] = str(gn), str(gm)
+            line = f"raster group_n={gn} group_m={gm}:"
+            for name in which:
+                ms, tf = sustained(*tests[name])
+                line += f"  {name} {ms:.3f} ms {tf:.0f} TF{last_clock}"
+            print(line, flush=True)
+        return
     for name in which or list(tests):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
@@ -107,4 +116,9 @@ def main(which):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:])
+    argv = sys.argv[1:]
+    if argv and argv[0] == "--raster-sweep":  # --raster-sweep gn:gm,gn:gm,... op op ...
+        pairs = [tuple(int(v) for v in t.split(":")) for t in argv[1].split(",")]
+        main(argv[2:], pairs)
+    else:
+        main(argv)

@@ -11,7 +11,7 @@ NAMES = {0: "attention order + commits", 1: "attention order, no commits", 2: "3
          3: "32 x TS, one accumulator", 4: "SS alternating accumulators", 5: "TS alternating accumulators",
          6: "QK0 QK1 PV0 PV1", 7: "16 x SS N=256", 8: "attention order, commit every 4", 9: "two issuing threads (QK | PV)",
          10: "QK only (16 MMAs)", 11: "PV only (16 MMAs)"}
-lib = _native.lib()
+lib = _native.dbg_lib()
 out = torch.zeros(1, device="cuda", dtype=torch.int64)
 iters = 400
 for pat in sorted(NAMES):

@@ -28,7 +28,16 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in flux_b200.h but not exported"
     assert declared == set(_native.SYMBOLS), "ctypes table and header disagree"
+    assert not any(n.startswith("fx_dbg_") for n in declared), "test-only probes belong in flux_b200_dbg.h"
     assert lib.fx_version() >= 100
+    # the test-only companion library: its own header, its own .so, same rule
+    import ctypes
+    dbg_header = open(os.path.join(ROOT, "include", "flux_b200_dbg.h")).read()
+    dbg_declared = set(re.findall(r"\b(fx_dbg_[a-z0-9_]+)\s*\(", dbg_header))
+    assert dbg_declared == set(_native.DBG_SYMBOLS)
+    dbg = ctypes.CDLL(os.path.join(os.path.dirname(_native.lib_path()), "libflux_b200_dbg.so"))
+    for name in sorted(dbg_declared):
+        assert hasattr(dbg, name) and not hasattr(lib, name), f"{name} must live in the companion library only"
     # host-only argument validation works without a GPU and reports through fx_last_error
     import ctypes as C
     rc = lib.fx_gemm(C.byref(_native.GemmArgs()), None)
