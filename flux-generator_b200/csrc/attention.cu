@@ -9,6 +9,8 @@
 // P (bf16 probabilities) is handed to the P.V MMA either through TMEM (aliasing S, default) or through
 // 128B-swizzled shared memory (variant 1, bring-up fallback).  V is consumed MN-major straight from its
 // [seq][128] layout (no transposed copy).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "api_common.cuh"
@@ -559,6 +561,343 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------
+// attn_pkernel (variant 7): attn_kernel's schedule as a PERSISTENT work loop.  One CTA per SM walks the work items
+// (256 query rows of one (batch, head)), q-block fastest so that the CTAs running at the same time share K / V in L2.
+// What the loop buys over one CTA per item (measured on attn_kernel: ~4100 clocks of prologue per ~105 000-clock item):
+//   * barrier initialisation, TMEM allocation and the CTA-wide syncs happen once per SM, not once per item;
+//   * the producer runs ahead across the item boundary: Q of item n+1 is loaded as soon as the last Q K^T of item n has
+//     completed (q_empty), its K(0) / V(0) are already in the ring, and the issuer starts S(0) of item n+1 right behind
+//     the last P.V of item n -- so when the softmax warps return from the O epilogue their first S tile is waiting.
+// Differences in resources: the K/V ring has 4 stages instead of 5 (the O epilogue can no longer borrow the ring as its
+// transposition buffer -- it is full of the next item's tiles -- and gets 16 KB of its own).
+// Barrier phases are tracked with running counters (n = tile steps so far), so any kv_tiles parity works.
+// ------------------------------------------------------------------------------------------
+struct AttnPCfg {
+  static constexpr int KV_STAGES = 4;
+  static constexpr int Q_OFF = 0;
+  static constexpr int KV_OFF = 2 * ATT_TILE_BYTES;
+  static constexpr int ST_OFF = KV_OFF + KV_STAGES * ATT_TILE_BYTES;  // 8 warps x 2 KB store transposition buffers
+  static constexpr int BAR_OFF = ST_OFF + 8 * 2048;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, const int q_blocks, const int items) {
+  using Cfg = AttnPCfg;
+  constexpr int NS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* q_full = bars;             // 1: Q of the current item has landed
+  uint64_t* q_empty = bars + 1;        // 1: every Q K^T of the current item has completed (tcgen05.commit)
+  uint64_t* kv_full = bars + 2;        // NS
+  uint64_t* kv_empty = kv_full + NS;   // NS
+  uint64_t* s_full = kv_empty + NS;    // 2
+  uint64_t* p_full = s_full + 2;       // [tile][half] = 4
+  uint64_t* o_full = p_full + 4;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int T = p.kv_tiles;
+
+  if (warp == ATT_WARP_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[2 * i], 4);
+      mbar_init(&p_full[2 * i + 1], 4);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == ATT_WARP_MMA) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i aliases S_i[0,64)
+
+  if (warp >= ATT_CTRL0 && warp < ATT_CTRL0 + 4) {
+    reg_dec<88>();
+    if (warp == ATT_WARP_TMA) {
+      if (lane == 0) {
+        // ---------------- TMA producer: per item Q (both tiles), then K0 V0 K1 V1 ... through ONE ring across items
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+          const int qb = w % q_blocks, bh = w / q_blocks;
+          const int q0 = qb * 256;
+          mbar_wait(q_empty, (it & 1) ^ 1);  // the previous item's Q K^T products are done with the Q buffer
+          mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+          for (int i = 0; i < 2; ++i)
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_3d(smem + Cfg::Q_OFF + i * ATT_TILE_BYTES + hf * 16384, &tmap_q, q_full, hf * 64, q0 + i * 128, bh);
+          for (int t = 0; t < 2 * T; ++t) {
+            const CUtensorMap* m = (t & 1) ? &tmap_v : &tmap_k;
+            const int row = (t >> 1) * 128;
+            mbar_wait(&kv_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
+            uint8_t* dst = smem + Cfg::KV_OFF + stage * ATT_TILE_BYTES;
+            tma_load_3d(dst, m, &kv_full[stage], 0, row, bh);
+            tma_load_3d(dst + 16384, m, &kv_full[stage], 64, row, bh);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == ATT_WARP_MMA) {
+      // ---------------- MMA issuer (whole warp, warp-uniform control flow, one elected lane issues: see attn_kernel)
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_lo = (smem_u32(smem + Cfg::Q_OFF) >> 4) | (1u << 16);
+      const uint32_t k_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1u << 16);
+      const uint32_t v_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1024u << 16);
+      constexpr uint32_t TILE16 = ATT_TILE_BYTES >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t n = 0;   // tile steps so far (parity of the s_full / p_full phases)
+      uint32_t it = 0;  // items so far (parity of q_full / o_full)
+      auto issue_qk = [&](int i, int kslot) {
+        const uint32_t a_lo = q_lo + i * TILE16, b_lo = k_lo0 + kslot * TILE16;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;
+          umma_ss(tmem + i * 128, make_desc(a_lo + off, kDescHiSw128), make_desc(b_lo + off, kDescHiSw128), idesc_qk, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int i, int vslot, bool acc, int hf) {
+        const uint32_t b_lo = v_lo0 + vslot * TILE16;
+#pragma unroll
+        for (int ks = hf * 4; ks < hf * 4 + 4; ++ks)
+          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, make_desc(b_lo + ks * 128, kDescHiSw128), idesc_pv,
+                  (acc || ks != 0) ? 1u : 0u);
+      };
+      for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&kv_full[stage], phase);  // K(0)
+        tc_fence_after();
+        if (elect_one()) {
+          issue_qk(0, stage);
+          tc_commit(&s_full[0]);
+          issue_qk(1, stage);
+          tc_commit(&s_full[1]);
+          tc_commit(&kv_empty[stage]);
+          if (T == 1) tc_commit(q_empty);
+        }
+        __syncwarp();
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        for (int j = 0; j < T; ++j, ++n) {
+          const bool more = (j + 1 < T);
+          const uint32_t par = n & 1;
+          const int vs = stage;
+          mbar_wait(&kv_full[vs], phase);  // V(j)
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+          const int ks_ = stage;
+          if (more) mbar_wait(&kv_full[ks_], phase);  // K(j+1): landed long ago (it trails V(j) in the ring)
+          mbar_wait(&p_full[0], par);
+          tc_fence_after();
+          if (elect_one()) issue_pv(0, vs, j > 0, 0);
+          __syncwarp();
+          mbar_wait(&p_full[1], par);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(0, vs, j > 0, 1);
+            if (more) {
+              issue_qk(0, ks_);
+              tc_commit(&s_full[0]);
+            }
+          }
+          __syncwarp();
+          mbar_wait(&p_full[2], par);
+          tc_fence_after();
+          if (elect_one()) issue_pv(1, vs, j > 0, 0);
+          __syncwarp();
+          mbar_wait(&p_full[3], par);
+          tc_fence_after();
+          if (elect_one()) {
+            issue_pv(1, vs, j > 0, 1);
+            tc_commit(&kv_empty[vs]);
+            if (more) {
+              issue_qk(1, ks_);
+              tc_commit(&s_full[1]);
+              tc_commit(&kv_empty[ks_]);
+              if (j + 2 == T) tc_commit(q_empty);  // that was the item's last Q K^T: the Q buffer may be refilled
+            }
+          }
+          __syncwarp();
+          if (more) {
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one()) {
+          tc_commit(&o_full[0]);
+          tc_commit(&o_full[1]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- softmax / correction / epilogue warpgroups
+    reg_inc<208>();
+    const int i = (warp - ATT_SM0) >> 2;  // query tile 0/1
+    const int quarter = warp & 3;         // TMEM lane quarter
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+    const uint32_t s_addr = tmem + lane_base + i * 128;
+    const uint32_t o_addr = tmem + lane_base + 256 + i * 128;
+    const float sl2 = p.scale_log2;
+    const uint64_t sl2_2 = pack2(sl2, sl2);
+    uint8_t* wst = smem + Cfg::ST_OFF + (warp - ATT_SM0) * 2048;
+    uint32_t n = 0, it = 0;
+    for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
+      const int qb = w % q_blocks, bh = w / q_blocks;
+      const int bz = bh / p.heads, hy = bh - bz * p.heads;
+      const int q_row = qb * 256 + i * 128 + r;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < T; ++j, ++n) {
+        const int kv_valid = min(128, p.seq - j * 128);
+        mbar_wait(&s_full[i], n & 1);
+        tc_fence_after();
+        uint32_t sv[128];
+        __syncwarp();
+        tmem_ld_x32(s_addr, sv);
+        tmem_ld_x32(s_addr + 32, sv + 32);
+        tmem_ld_x32(s_addr + 64, sv + 64);
+        tmem_ld_x32(s_addr + 96, sv + 96);
+        tmem_ld_wait();
+        if (kv_valid < 128) {  // ragged last tile: keys beyond seq do not exist
+#pragma unroll
+          for (int e = 0; e < 128; ++e)
+            if (e >= kv_valid) sv[e] = 0xff800000u;  // -inf
+        }
+        auto exp_chunk = [&](int c, uint32_t* dst, uint32_t* pk, uint64_t nm2) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
+            float p0, p1;
+            if (EMU_MASK & (1u << ((e >> 1) & 7))) {
+              exp2_emu2(t2, p0, p1);
+            } else {
+              const float2 t = unpack2(t2);
+              p0 = fast_exp2(t.x);
+              p1 = fast_exp2(t.y);
+            }
+            dst[e] = __float_as_uint(p0);
+            dst[e + 1] = __float_as_uint(p1);
+            pk[e >> 1] = pack_bf16(p0, p1);
+          }
+        };
+        // speculative first chunk against the lazy running max (see attn_kernel)
+        uint64_t nm2 = pack2(-m_run, -m_run);
+        uint32_t pa[32], pk0[16];
+        exp_chunk(0, pa, pk0, nm2);
+        float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
+        float mxb = fmaxf(__uint_as_float(sv[2]), __uint_as_float(sv[3]));
+#pragma unroll
+        for (int e = 4; e < 128; e += 4) {
+          mx = fmax3(mx, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+          mxb = fmax3(mxb, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
+        }
+        mx = fmaxf(mx, mxb);
+        const float m_new = fmaxf(m_run, mx * sl2);
+        const bool need = (m_new - m_run) > 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
+          if (need) {
+            m_run = m_new;
+            l_run *= alpha;
+          }
+          if (j > 0) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              __syncwarp();
+              tmem_ld_x32(o_addr + c * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+              tmem_st_x32(o_addr + c * 32, v);
+            }
+            tmem_st_wait();
+          }
+          nm2 = pack2(-m_run, -m_run);
+          exp_chunk(0, pa, pk0, nm2);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sv[e] = pa[e];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+          if (c == 0) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = pk0[e];
+          } else {
+            exp_chunk(c, sv + c * 32, pk, nm2);
+          }
+          tmem_st_x16(s_addr + c * 16, pk);
+          if (c & 1) {  // a 64-key half of P is complete: hand it to the MMA warp
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[2 * i + (c >> 1)]);
+          }
+        }
+        {
+          uint64_t ls0 = pack2(0.f, 0.f), ls1 = pack2(0.f, 0.f);
+#pragma unroll
+          for (int e = 0; e < 128; e += 4) {
+            ls0 = fadd2(ls0, pack2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])));
+            ls1 = fadd2(ls1, pack2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])));
+          }
+          const float2 ls = unpack2(fadd2(ls0, ls1));
+          l_run += ls.x + ls.y;
+        }
+      }
+      // epilogue of the item: O / l -> bf16 -> out[b][q_row][h*128 ...] (coalesced through this warp's own buffer)
+      mbar_wait(&o_full[i], it & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const uint32_t vmask = __ballot_sync(0xffffffffu, q_row < p.seq);
+      __nv_bfloat16* dst0 = p.out + (long long)bz * p.out_bs + (long long)(q_row - lane) * p.ld_out + hy * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(o_addr + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * inv_l;
+        store_chunk32_coalesced(wst, lane, f, dst0 + c * 32, p.ld_out, vmask);
+      }
+      // O has been read out of TMEM (tcgen05.wait::ld above): order it before the next item's first p_full arrive, which
+      // is what allows the issuer to overwrite O with P.V of the next item
+      tc_fence_before();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == ATT_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // attn3_kernel (variants 5 / 6; measured, NOT the default): same math and roles as attn_kernel, but the per-tile
 // dependency loop is cut.
 //   attn_kernel hands P to the P.V MMA through TMEM, aliasing S: S_i(j+1) = Q_i K(j+1)^T cannot be issued before
@@ -948,7 +1287,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
-// Small generic attention (text encoders; head_dim 64; seq <= 512): one warp per (b, h, query).
+// Small generic attention (text encoders; head_dim 64; any sequence length): one warp per (b, h, query).
 // ------------------------------------------------------------------------------------------
 struct AttnSmallParams {
   const __nv_bfloat16 *q, *k, *v;
@@ -978,56 +1317,66 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnSmallParams p
     qv[d] = a.x * p.scale; qv[d + 1] = a.y * p.scale; qv[d + 2] = bb.x * p.scale; qv[d + 3] = bb.y * p.scale;
     qv[d + 4] = c.x * p.scale; qv[d + 5] = c.y * p.scale; qv[d + 6] = e.x * p.scale; qv[d + 7] = e.y * p.scale;
   }
-  constexpr int MAXK = 16;  // keys per lane: seq <= 512
-  float sc[MAXK];
-  float mx = -INFINITY;
+  // keys are walked in chunks of 512 (16 per lane) with an online softmax across chunks, so any sequence length works
+  // (the reference's T5 tokenizer never truncates: flux/tokenizers.py:160-173); one chunk = the plain softmax.
+  constexpr int MAXK = 16;
   const int nk = p.causal ? qi + 1 : p.seq;
+  float m_run = -INFINITY, sum = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int k0 = 0; k0 < nk; k0 += 32 * MAXK) {
+    float sc[MAXK];
+    float mx = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < MAXK; ++t) {
-    const int kj = t * 32 + lane;
-    float s = -INFINITY;
-    if (kj < nk) {
-      const __nv_bfloat16* kp = p.k + b * p.bs + (long long)kj * p.ld + h * 64;
-      s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 64; d += 8) {
-        const uint4 u = *reinterpret_cast<const uint4*>(kp + d);
-        float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
-        s += qv[d] * a.x + qv[d + 1] * a.y + qv[d + 2] * bb.x + qv[d + 3] * bb.y + qv[d + 4] * c.x + qv[d + 5] * c.y +
-             qv[d + 6] * e.x + qv[d + 7] * e.y;
-      }
-      if (p.bias) s += p.bias[((long long)h * p.seq + qi) * p.seq + kj];
-    }
-    sc[t] = s;
-    mx = fmaxf(mx, s);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-#pragma unroll
-  for (int t = 0; t < MAXK; ++t) {
-    sc[t] = (sc[t] == -INFINITY) ? 0.f : __expf(sc[t] - mx);
-    sum += sc[t];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.0f / sum;
-  // out[d]: lane owns dims 2*lane, 2*lane+1; loop over all keys, probabilities broadcast by shuffle
-  float o0 = 0.f, o1 = 0.f;
-  for (int t = 0; t < MAXK; ++t) {
-    if (t * 32 >= nk) break;
-    for (int src = 0; src < 32; ++src) {
-      const int kj = t * 32 + src;
-      const float pj = __shfl_sync(0xffffffffu, sc[t], src);
+    for (int t = 0; t < MAXK; ++t) {
+      const int kj = k0 + t * 32 + lane;
+      float s = -INFINITY;
       if (kj < nk) {
-        const __nv_bfloat162 vv =
-            *reinterpret_cast<const __nv_bfloat162*>(p.v + b * p.bs + (long long)kj * p.ld + h * 64 + 2 * lane);
-        const float2 f = __bfloat1622float2(vv);
-        o0 += pj * f.x;
-        o1 += pj * f.y;
+        const __nv_bfloat16* kp = p.k + b * p.bs + (long long)kj * p.ld + h * 64;
+        s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 8) {
+          const uint4 u = *reinterpret_cast<const uint4*>(kp + d);
+          float2 a = unpack_bf16(u.x), bb = unpack_bf16(u.y), c = unpack_bf16(u.z), e = unpack_bf16(u.w);
+          s += qv[d] * a.x + qv[d + 1] * a.y + qv[d + 2] * bb.x + qv[d + 3] * bb.y + qv[d + 4] * c.x + qv[d + 5] * c.y +
+               qv[d + 6] * e.x + qv[d + 7] * e.y;
+        }
+        if (p.bias) s += p.bias[((long long)h * p.seq + qi) * p.seq + kj];
+      }
+      sc[t] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m_new = fmaxf(m_run, mx);
+    const float alpha = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);  // first chunk: nothing to rescale
+    m_run = m_new;
+    float csum = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXK; ++t) {
+      sc[t] = (sc[t] == -INFINITY) ? 0.f : __expf(sc[t] - m_new);
+      csum += sc[t];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+    sum = sum * alpha + csum;
+    o0 *= alpha;
+    o1 *= alpha;
+    // out[d]: lane owns dims 2*lane, 2*lane+1; loop over the chunk's keys, probabilities broadcast by shuffle
+    for (int t = 0; t < MAXK; ++t) {
+      if (k0 + t * 32 >= nk) break;
+      for (int src = 0; src < 32; ++src) {
+        const int kj = k0 + t * 32 + src;
+        const float pj = __shfl_sync(0xffffffffu, sc[t], src);
+        if (kj < nk) {
+          const __nv_bfloat162 vv =
+              *reinterpret_cast<const __nv_bfloat162*>(p.v + b * p.bs + (long long)kj * p.ld + h * 64 + 2 * lane);
+          const float2 f = __bfloat1622float2(vv);
+          o0 += pj * f.x;
+          o1 += pj * f.y;
+        }
       }
     }
   }
+  const float inv = 1.0f / sum;
   __nv_bfloat16* op = p.out + b * p.out_bs + (long long)qi * p.ld_out + h * 64 + 2 * lane;
   *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
 }
@@ -1050,6 +1399,16 @@ static int launch_attn(const fx_attn_args* a, const CUtensorMap& tq, const CUten
   return launched("attn_kernel");
 }
 
+// FX_ATTN_PERSISTENT=0/1: which kernel variant 0 (the default) runs -- the persistent work loop or one CTA per item
+static bool persistent_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FX_ATTN_PERSISTENT");
+    v = e ? atoi(e) : 1;  // measured: 1.612 -> 1.565 ms isolated, 419 -> 401 ms per bench step (profiles/README.md)
+  }
+  return v != 0;
+}
+
 extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention: null pointer");
   FX_REQUIRE(a->batch > 0 && a->heads > 0 && a->seq > 0, "fx_attention: empty problem");
@@ -1068,6 +1427,19 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   if ((rc = make_tmap_bf16(&tq, a->q, 3, dims, strides, box))) return rc;
   if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box))) return rc;
   if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box))) return rc;
+  if (a->variant == 7 || (a->variant == 0 && persistent_default())) {
+    // persistent work loop (attn_pkernel): one CTA per SM over the (q-block, head, batch) items
+    static std::once_flag oncep;
+    static cudaError_t attrp_err = cudaSuccess;
+    std::call_once(oncep, [&] { attrp_err = cudaFuncSetAttribute(attn_pkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPCfg::SMEM_BYTES); });
+    if (attrp_err != cudaSuccess) return fail(FX_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(attrp_err));
+    const int q_blocks = (a->seq + 255) / 256;
+    const long long items = (long long)q_blocks * a->heads * a->batch;
+    FX_REQUIRE(items < (1ll << 31), "fx_attention: too many work items");
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    attn_pkernel<<<grid, ATT_THREADS, AttnPCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p, q_blocks, (int)items);
+    return launched("attn_pkernel");
+  }
   if (a->variant == 5 || a->variant == 6) {
     // decoupled schedule (attn3_kernel): P through shared memory, Q K(j+1)^T issued as soon as S(j) has been read
     p.sequence = a->variant == 5 ? 1 : 0;
@@ -1093,7 +1465,7 @@ extern "C" int fx_dbg_attn_probe(void* buf) {  // profiling builds only: device 
 
 extern "C" int fx_attention_small(const fx_attn_small_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention_small: null pointer");
-  FX_REQUIRE(a->seq > 0 && a->seq <= 512, "fx_attention_small: seq %d out of range (1..512)", a->seq);
+  FX_REQUIRE(a->seq > 0, "fx_attention_small: empty sequence");
   FX_REQUIRE(a->ld % 8 == 0 && a->bs % 8 == 0 && a->ld_out % 2 == 0, "fx_attention_small: unaligned strides");
   AttnSmallParams p{(const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k, (const __nv_bfloat16*)a->v, a->ld, a->bs,
                     a->bias, (__nv_bfloat16*)a->out, a->ld_out, a->out_bs, a->scale, a->batch, a->heads, a->seq, a->causal};

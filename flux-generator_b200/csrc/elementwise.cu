@@ -156,6 +156,138 @@ __global__ void __launch_bounds__(256, 2) rownorm_kernel(const RowNormParams p) 
   }  // row loop
 }
 
+// Wide rows (D >= 1024: the MMDiT's 3072-wide residual stream, T5's 4096): one 128-thread block per row, the row
+// AND its modulation vectors requested up front (one exposed latency instead of two), statistics through two
+// block reductions.  Same arithmetic per element as rownorm_kernel.  Measured on the benchmark's [8 x 4352, 3072]
+// tensor: the warp-per-row kernel above sustains 3.9 TB/s (bf16 out) / 1.6 TB/s (e4m3 out, 3 B per element); the
+// block-per-row quantiser below, which has this structure, 6.5 TB/s.
+__device__ __forceinline__ float block_sum4(float v, float* red, int lane, int warp) {
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {  // packed bf16 pair -> packed fp32 pair (2 ALU ops)
+  return pack2f(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <int VPT, bool F8OUT>  // VPT = ceil(D / 1024) 16-byte vectors per thread
+__global__ void __launch_bounds__(128) rownorm_block_kernel(const RowNormParams p) {
+  // Persistent blocks walk the rows with a grid stride; the next row's loads are issued before the current row is
+  // reduced.  The kernel was INSTRUCTION-bound, not HBM-bound (~350 instructions per thread and row: the packed row was
+  // unpacked three times and the modulation vectors once per row; 3.9 TB/s whatever the launch geometry).  Now the row
+  // is unpacked once into packed fp32 pairs, all arithmetic runs on FADD2 / FFMA2, the centred row is reused by the
+  // output pass, and the per-column affine (P, A) -- (1 + scale, shift) / (weight, bias) / (weight, 0) -- is converted
+  // once per batch element and kept in registers: ~140 instructions per thread and row.
+  __shared__ float red[2][3][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long total = (long long)p.batch * p.rows;
+  long long gr = blockIdx.x;
+  if (gr >= total) return;
+  constexpr int NP = VPT * 4;  // fp32 pairs per thread
+  uint4 nxt[VPT];
+  uint64_t P2[NP], A2[NP];
+  bool in[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) in[i] = (i * 128 + tid) * 8 < p.D;
+  int pb_batch = -1;
+  auto load_row = [&](long long g, uint4* dst) {
+    const int b = int(g / p.rows);
+    const long long r = g - (long long)b * p.rows;
+    const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      dst[i] = in[i] ? *reinterpret_cast<const uint4*>(xr + (i * 128 + tid) * 8) : make_uint4(0, 0, 0, 0);
+  };
+  load_row(gr, nxt);
+  const uint64_t one2 = pack2f(1.0f, 1.0f);
+  const float inv_d = 1.0f / float(p.D);
+  int flip = 0;
+  for (; gr < total; gr += gridDim.x, flip ^= 1) {
+    const int b = int(gr / p.rows);
+    const long long r = gr - (long long)b * p.rows;
+    uint64_t v2[NP];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      v2[4 * i] = bf2_to_f2(nxt[i].x); v2[4 * i + 1] = bf2_to_f2(nxt[i].y);
+      v2[4 * i + 2] = bf2_to_f2(nxt[i].z); v2[4 * i + 3] = bf2_to_f2(nxt[i].w);
+    }
+    const int pbb = (p.mode == 0) ? b : 0;
+    if (pbb != pb_batch) {  // (1 + scale, shift) of this batch element / (weight, bias) / (weight, 0)
+      pb_batch = pbb;
+      const long long pb = (long long)pbb * p.p_bs;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int c = (i * 128 + tid) * 8;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const uint4 u0 = in[i] ? __ldg(reinterpret_cast<const uint4*>(p.p0 + pb + c)) : z;
+        const uint4 u1 = (in[i] && p.mode != 2) ? __ldg(reinterpret_cast<const uint4*>(p.p1 + pb + c)) : z;
+        const uint32_t w0[4] = {u0.x, u0.y, u0.z, u0.w}, w1[4] = {u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.mode == 0) { P2[4 * i + j] = fadd2(one2, bf2_to_f2(w1[j])); A2[4 * i + j] = bf2_to_f2(w0[j]); }
+          else { P2[4 * i + j] = bf2_to_f2(w0[j]); A2[4 * i + j] = bf2_to_f2(w1[j]); }
+        }
+      }
+    }
+    if (gr + gridDim.x < total) load_row(gr + gridDim.x, nxt);  // in flight while this row is reduced
+    float (*rd)[4] = red[flip];  // double-buffered: the next iteration's first reduction cannot overtake a reader
+    float mean = 0.f;
+    if (p.mode != 2) {
+      uint64_t s0 = pack2f(0.f, 0.f), s1 = s0;
+#pragma unroll
+      for (int k = 0; k < NP; k += 2) { s0 = fadd2(s0, v2[k]); s1 = fadd2(s1, v2[k + 1]); }
+      const float2 t = unpack2f(fadd2(s0, s1));
+      mean = block_sum4(t.x + t.y, rd[0], lane, warp) * inv_d;
+    }
+    const uint64_t nm2 = pack2f(-mean, -mean);
+    uint64_t q0 = pack2f(0.f, 0.f), q1 = q0;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t d = in[i] ? fadd2(v2[4 * i + j], nm2) : pack2f(0.f, 0.f);  // centred row, reused below
+        v2[4 * i + j] = d;
+        if (j & 1) q1 = ffma2(d, d, q1);
+        else q0 = ffma2(d, d, q0);
+      }
+    }
+    const float2 tq = unpack2f(fadd2(q0, q1));
+    const float rstd = rsqrtf(block_sum4(tq.x + tq.y, rd[1], lane, warp) * inv_d + p.eps);
+    const uint64_t k2 = pack2f(rstd, rstd);
+    __nv_bfloat16* orow = p.out + b * p.out_bs + r * p.ldo;
+    uint8_t* qrow = reinterpret_cast<uint8_t*>(p.out) + b * p.out_bs + r * p.ldo;
+    __nv_bfloat162 amax2 = __floats2bfloat162_rn(0.f, 0.f);
+    uint4 keep[VPT];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 o = unpack2f(ffma2(fmul2(v2[4 * i + j], k2), P2[4 * i + j], A2[4 * i + j]));
+        w[j] = pack_bf16(o.x, o.y);
+        if (F8OUT) amax2 = __hmax2(amax2, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&w[j])));
+      }
+      keep[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      if (!F8OUT && in[i]) *reinterpret_cast<uint4*>(orow + (i * 128 + tid) * 8) = keep[i];
+    }
+    if (F8OUT) {  // exactly quantize_rows(rownorm(x)): absmax of the ROUNDED values, then e4m3 + the row's scale
+      float amax = warp_max(fmaxf(__low2float(amax2), __high2float(amax2)));
+      if (lane == 0) rd[2][warp] = amax;
+      __syncthreads();
+      amax = fmaxf(fmaxf(rd[2][0], rd[2][1]), fmaxf(rd[2][2], rd[2][3]));
+      if (tid == 0) p.scale_out[b * p.scale_bs + r] = fp8_row_scale(amax);
+      const float inv = fp8_row_inv(amax);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        if (!in[i]) continue;
+        float o[8];
+        unpack8(keep[i], o);
+        *reinterpret_cast<uint2*>(qrow + (i * 128 + tid) * 8) = quant8(o, inv);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ FP8 row quantisation: one warp per row
 // x bf16 [batch][rows][K] -> q e4m3 [batch][rows][K] + scale fp32 [batch][rows].  Two passes over the row; the
 // second one hits L1 / L2 (a row is at most 30 KB), so HBM sees one bf16 read and one byte-wide write.
@@ -472,28 +604,57 @@ __global__ void groupnorm_finalize_kernel(const float* partials, float2* stats, 
   }
 }
 
+// apply: each thread owns ONE 8-channel slot and walks a slab of pixels: the per-channel affine (rstd * weight,
+// bias - mean * rstd * weight) is folded once into registers, so the inner loop is one 16-byte load, 8 FMAs (+ SiLU)
+// and one 16-byte store per pixel, four pixels in flight.  (The first version re-read statistics, weight and bias and
+// divided by the group size for every element: 1.65 TB/s in the bench.)
+constexpr int GN_APPLY_ROWS = 512;  // pixels per block
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* x, const float2* stats,
                                                               const __nv_bfloat16* weight, const __nv_bfloat16* bias,
                                                               __nv_bfloat16* out, long long hw, int C, int do_silu) {
   const int b = blockIdx.y;
-  const long long vec = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel vector index in image
-  const long long nvec = hw * (C / 8);
-  if (vec >= nvec) return;
-  const int c0 = int(vec % (C / 8)) * 8;
+  const int tpr = C / 8;                 // threads per pixel
+  const int rpi = 256 / tpr;             // pixels per iteration of the block
+  const int tr = threadIdx.x / tpr, c0 = (threadIdx.x % tpr) * 8;
   const int gs = C / 32;
-  float v[8], w[8], bb[8], o[8];
-  const long long off = (long long)b * hw * C + vec * 8;
-  load8(x + off, v);
-  load8(weight + c0, w);
-  load8(bias + c0, bb);
+  float A[8], Bc[8];
+  {
+    float w[8], bb[8];
+    load8(weight + c0, w);
+    load8(bias + c0, bb);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float2 st = __ldg(&stats[b * 32 + (c0 + j) / gs]);
-    float y = (v[j] - st.x) * st.y * w[j] + bb[j];
-    if (do_silu) y = silu(__bfloat162float(__float2bfloat16(y)));
-    o[j] = y;
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = __ldg(&stats[b * 32 + (c0 + j) / gs]);
+      A[j] = st.y * w[j];
+      Bc[j] = bb[j] - st.x * A[j];
+    }
   }
-  store8(out + off, o);
+  const long long r0 = (long long)blockIdx.x * GN_APPLY_ROWS;
+  const long long r1 = min(hw, r0 + GN_APPLY_ROWS);
+  const __nv_bfloat16* xb = x + (long long)b * hw * C + c0;
+  __nv_bfloat16* ob = out + (long long)b * hw * C + c0;
+  for (long long r = r0 + tr; r < r1; r += 4 * rpi) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long rr = r + (long long)k * rpi;
+      if (rr < r1) u[k] = *reinterpret_cast<const uint4*>(xb + rr * C);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long rr = r + (long long)k * rpi;
+      if (rr >= r1) break;
+      float v[8], o[8];
+      unpack8(u[k], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(v[j], A[j], Bc[j]);
+        if (do_silu) y = silu(__bfloat162float(__float2bfloat16(y)));
+        o[j] = y;
+      }
+      store8(ob + rr * C, o);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ nearest 2x upsample (NHWC)
@@ -647,6 +808,30 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
     if (persist > 0 && blocks > persist * num_sms()) blocks = persist * num_sms();
   }
   cudaStream_t st = (cudaStream_t)stream;
+  static int block_rows = -1;  // FX_ROWNORM_BLOCK=0: the warp-per-row kernel for every D (A/B)
+  if (block_rows < 0) {
+    const char* e = getenv("FX_ROWNORM_BLOCK");
+    block_rows = e ? atoi(e) : 1;
+  }
+  if (block_rows && a->D >= 1024 && rows < (1ll << 31)) {  // wide rows: one block per row
+    static int per_sm = -1;  // FX_ROWNORM_BLOCKS_PER_SM: resident 128-thread blocks per SM of the persistent grid
+    if (per_sm < 0) {
+      const char* e = getenv("FX_ROWNORM_BLOCKS_PER_SM");
+      per_sm = e ? atoi(e) : 4;  // 120 registers x 128 threads: four blocks are resident
+      if (per_sm < 1) per_sm = 1;
+    }
+    const long long cap = (long long)per_sm * num_sms();
+    const unsigned g = (unsigned)(rows < cap ? rows : cap);
+    const int vpt = (a->D + 1023) / 1024;
+#define FX_RB(V)                                                                     \
+  case V:                                                                            \
+    if (a->out_fp8) rownorm_block_kernel<V, true><<<g, 128, 0, st>>>(p);             \
+    else rownorm_block_kernel<V, false><<<g, 128, 0, st>>>(p);                       \
+    break;
+    switch (vpt) { FX_RB(1) FX_RB(2) FX_RB(3) FX_RB(4) }
+#undef FX_RB
+    return launched("rownorm_block_kernel");
+  }
   if (a->out_fp8) {
     switch ((a->D + 255) / 256) {
 #define FX_RN(I) case I: rownorm_kernel<I, true><<<blocks, 256, 0, st>>>(p); break;
@@ -778,11 +963,21 @@ extern "C" int fx_groupnorm_finalize(const float* partials, float* stats, int32_
   return launched("groupnorm_finalize_kernel");
 }
 
+extern "C" int fx_groupnorm_finalize_blocks(const float* partials, float* stats, int32_t batch, int64_t nblk, int64_t hw,
+                                            int32_t C, float eps, fx_stream stream) {
+  FX_REQUIRE(partials && stats && batch > 0 && hw > 0 && nblk > 0 && nblk < (1ll << 31) && C % 32 == 0,
+             "fx_groupnorm_finalize_blocks: bad arguments");
+  const int n = batch * 32;
+  groupnorm_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, (float2*)stats, n, (int)nblk,
+                                                                                 (double)hw * (C / 32), eps);
+  return launched("groupnorm_finalize_kernel");
+}
+
 extern "C" int fx_groupnorm_apply(const void* x, const float* stats, const void* weight, const void* bias, void* out,
                                   int32_t batch, int64_t hw, int32_t C, int32_t do_silu, fx_stream stream) {
   FX_REQUIRE(x && stats && weight && bias && out && batch > 0 && hw > 0 && C % 32 == 0 && C % 8 == 0, "fx_groupnorm_apply: bad arguments");
-  const long long nvec = hw * (C / 8);
-  dim3 grid((unsigned)((nvec + 255) / 256), batch);
+  FX_REQUIRE(C >= 64 && (C / 8) <= 256 && 256 % (C / 8) == 0, "fx_groupnorm_apply: unsupported channel count %d", C);
+  dim3 grid((unsigned)((hw + GN_APPLY_ROWS - 1) / GN_APPLY_ROWS), batch);
   groupnorm_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float2*)stats, (const __nv_bfloat16*)weight,
                                                               (const __nv_bfloat16*)bias, (__nv_bfloat16*)out, hw, C, do_silu);
   return launched("groupnorm_apply_kernel");

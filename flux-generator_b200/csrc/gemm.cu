@@ -234,6 +234,12 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = p.out_bs;
   fill_tiling(p, p.conv_tiles_x * p.conv_tiles_y, bn);
   fill_l2_policy(p, 2);
+  if (a->gn_partials) {
+    FX_REQUIRE(a->Cout % 128 == 0 && !a->out_f32, "fx_conv3x3: gn_partials needs Cout %% 128 == 0 and a bf16 output");
+    p.gn_partials = a->gn_partials;
+    p.gn_gs = a->Cout / 32;
+    p.gn_nblk = p.conv_tiles_x * p.conv_tiles_y * ncta * 4;
+  }
   CUtensorMap ta, tw;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin, (uint64_t)a->Wd, (uint64_t)a->H, (uint64_t)a->batch};
@@ -250,6 +256,11 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
     if (rc) return rc;
   }
   return launch_bn<EPI_GENERIC, true>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
+}
+
+extern "C" int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout) {
+  const int ncta = want_ncta(pick_bn(Cout));
+  return (int64_t)((Wd + 16 * ncta - 1) / (16 * ncta)) * ((H + 7) / 8) * ncta * 4;
 }
 
 // ------------------------------------------------------------------------------------------

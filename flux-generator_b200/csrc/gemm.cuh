@@ -69,7 +69,59 @@ struct GemmParams {
   int ls_group, ls_slack;  // wave lockstep: k-blocks per group (0 = off), groups a producer may run ahead
   // ---- 3x3 conv mode (A is [batch][H][W][C] NHWC, pad 1, stride 1)
   int conv_H, conv_W, conv_tiles_x, conv_tiles_y, cin_blocks;
+  // ---- conv mode: GroupNorm(32) statistics of the bf16 output, per 32-pixel block (one epilogue warp's rows):
+  //      gn_partials[batch][gn_nblk][32 groups][sum, sum of squares]; gn_gs = channels per group (4 / 8 / 16)
+  float* gn_partials;
+  int gn_gs, gn_nblk;
 };
+
+// (sum, sum of squares) of one 32-column chunk of a warp's 32 output rows for the GS-channel GroupNorm groups it
+// covers: per-thread sums over the row's channels, then a halving butterfly across the 32 lanes (2G values are reduced
+// with 2G-1+log2(32/2G) shuffles instead of 10 G) -- a fixed order, so the statistics are bit-reproducible.  The values
+// are the bf16-ROUNDED outputs: exactly what a separate statistics pass over the stored tensor would read.
+template <int GS>
+__device__ __forceinline__ void gn_chunk_partials_t(float* dst, const float* f, bool valid, int lane) {
+  constexpr int G = 32 / GS, NV = 2 * G;
+  float vals[NV];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < GS; ++j) {
+      const float v = valid ? __bfloat162float(__float2bfloat16(f[g * GS + j])) : 0.f;
+      s += v;
+      q += v * v;
+    }
+    vals[2 * g] = s;
+    vals[2 * g + 1] = q;
+  }
+  int n = NV, idx = 0;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const int h = n >> 1;
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < h) {
+          const float mine = up ? vals[h + i] : vals[i];
+          const float other = up ? vals[i] : vals[h + i];
+          vals[i] = mine + __shfl_xor_sync(0xffffffffu, other, off);
+        }
+      }
+      n = h;
+      if (up) idx += h;
+    } else {
+      vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+    }
+  }
+  if ((lane & (32 / NV - 1)) == 0) dst[idx] = vals[0];  // this lane ended up with value `idx` = 2 * group + statistic
+}
+__device__ __forceinline__ void gn_chunk_partials(float* dst, const float* f, bool valid, int lane, int gs) {
+  if (gs == 4) gn_chunk_partials_t<4>(dst, f, valid, lane);
+  else if (gs == 8) gn_chunk_partials_t<8>(dst, f, valid, lane);
+  else gn_chunk_partials_t<16>(dst, f, valid, lane);
+}
 
 template <int BN, int NCTA = 1>
 struct GemmCfg {
@@ -493,6 +545,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                                   vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs, wst, lane, vmask, valid,
                                   CONV ? ((long long)(lane & 15) + (long long)(lane >> 4) * p.conv_W) * p.ldo : -1,
                                   CONV ? (long long)p.conv_W * p.ldo : -1);
+            if (CONV && p.gn_partials != nullptr)  // f[] now holds the final values (bias, residual) of 32 channels
+              gn_chunk_partials(p.gn_partials + (((long long)b * p.gn_nblk + (long long)(tmb * NCTA + int(cta_rank)) * 4 + quarter) * 32 +
+                                                 n0 / p.gn_gs) * 2,
+                                f, valid, lane, p.gn_gs);
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];

@@ -4,11 +4,12 @@
 GEMMs on tcgen05 (4-D TMA boxes over the NHWC activation, OHWI weights = the reference's sanitized
 layout), GroupNorm(32)+SiLU as a two-pass HBM-bound kernel pair, the single-head 512-wide mid
 attention as two tcgen05 GEMMs around a row softmax.  Activations are bf16, accumulation fp32 (the
-reference promotes to the AE file's dtype; tolerance stated in tests/test_gpu_vae.py).
+reference promotes to the AE file's dtype; tolerance stated in tests/test_gpu_parity.py::test_vae_decode_vs_golden).
 Only the decoder is on the hot path; the encoder is training-only and not built.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -85,27 +86,35 @@ class AutoEncoder:
         return {"arena": self.arena.buffer}
 
     # ------------------------------------------------------------------ blocks
-    def _gn(self, x, key, silu):
-        return ops.groupnorm(x, self.arena[key + ".weight"], self.arena[key + ".bias"], 1e-6, silu)
+    # Every GroupNorm input except the one after the mid attention is the output of a 3x3 convolution: that
+    # convolution's epilogue accumulates the GroupNorm partial sums (ops.conv3x3(gn_stats=True)), so the statistics
+    # pass over the activation (a third of the GroupNorm time) disappears.  `st` carries (partials, blocks per image).
+    FUSE_GN_STATS = os.environ.get("FLUX_B200_GN_FUSED", "1") not in ("0", "")
 
-    def _conv(self, x, key, resid=None, out_dtype=bf16):
-        return ops.conv3x3(x, self.arena[key + ".weight"], self.arena[key + ".bias"], resid=resid, out_dtype=out_dtype)
+    def _gn(self, x, key, silu, st=None):
+        return ops.groupnorm(x, self.arena[key + ".weight"], self.arena[key + ".bias"], 1e-6, silu, partials=st)
 
-    def _resnet(self, x, key):
+    def _conv(self, x, key, resid=None, out_dtype=bf16, stats=False):
+        w = self.arena[key + ".weight"]
+        stats = stats and self.FUSE_GN_STATS and w.shape[0] % 128 == 0
+        r = ops.conv3x3(x, w, self.arena[key + ".bias"], resid=resid, out_dtype=out_dtype, gn_stats=stats)
+        return r if stats else (r, None)
+
+    def _resnet(self, x, key, st=None):
         # flux/autoencoder.py:85-98
-        h = self._conv(self._gn(x, key + ".norm1", True), key + ".conv1")
-        h = self._gn(h, key + ".norm2", True)
+        h, hst = self._conv(self._gn(x, key + ".norm1", True, st), key + ".conv1", stats=True)
+        h = self._gn(h, key + ".norm2", True, hst)
         if (key + ".nin_shortcut.weight") in self.arena:
             B, H, W, C = x.shape
             sk = key + ".nin_shortcut"
             x = ops.gemm(x.view(B, H * W, C), self.arena[sk + ".weight"], self.arena[sk + ".bias"]).view(B, H, W, -1)
-        return self._conv(h, key + ".conv2", resid=x)
+        return self._conv(h, key + ".conv2", resid=x, stats=True)
 
-    def _attn(self, x, key):
+    def _attn(self, x, key, st=None):
         # flux/autoencoder.py:41-52: single head, scale C^-0.5
         B, H, W, C = x.shape
         n = H * W
-        y = self._gn(x, key + ".norm", False).view(B, n, C)
+        y = self._gn(x, key + ".norm", False, st).view(B, n, C)
         qkv = ops.gemm(y, self.arena[key + ".qkv.weight"], self.arena[key + ".qkv.bias"])  # [B, n, 3C]
         o = torch.empty((B, n, C), device=x.device, dtype=bf16)
         s = torch.empty((n, n), device=x.device, dtype=torch.float32)
@@ -140,14 +149,14 @@ class AutoEncoder:
     def _decoder(self, z: torch.Tensor) -> torch.Tensor:
         # flux/autoencoder.py:271-297
         a = self.params
-        h = self._conv(z, "decoder.conv_in")
-        h = self._resnet(h, "decoder.mid.block_1")
-        h = self._attn(h, "decoder.mid.attn_1")
-        h = self._resnet(h, "decoder.mid.block_2")
+        h, st = self._conv(z, "decoder.conv_in", stats=True)
+        h, st = self._resnet(h, "decoder.mid.block_1", st)
+        h = self._attn(h, "decoder.mid.attn_1", st)
+        h, st = self._resnet(h, "decoder.mid.block_2")  # (its input comes from a GEMM epilogue: standalone statistics)
         for lvl in reversed(range(len(a.ch_mult))):
             for blk in range(a.num_res_blocks + 1):
-                h = self._resnet(h, f"decoder.up.{lvl}.block.{blk}")
+                h, st = self._resnet(h, f"decoder.up.{lvl}.block.{blk}", st)
             if lvl != 0:
-                h = self._conv(ops.upsample2x(h), f"decoder.up.{lvl}.upsample.conv")
-        h = self._gn(h, "decoder.norm_out", True)
-        return self._conv(h, "decoder.conv_out", out_dtype=torch.float32)
+                h, st = self._conv(ops.upsample2x(h), f"decoder.up.{lvl}.upsample.conv", stats=True)
+        h = self._gn(h, "decoder.norm_out", True, st)
+        return self._conv(h, "decoder.conv_out", out_dtype=torch.float32)[0]

@@ -131,8 +131,10 @@ def block_pe(pe: torch.Tensor) -> torch.Tensor:
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor] = None,
-            out_dtype: torch.dtype = bf16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [B,H,W,Cin] NHWC contiguous; w [Cout, 9*Cin] (OHWI flattened)."""
+            out_dtype: torch.dtype = bf16, out: Optional[torch.Tensor] = None, gn_stats: bool = False):
+    """x [B,H,W,Cin] NHWC contiguous; w [Cout, 9*Cin] (OHWI flattened).
+    gn_stats=True: the epilogue also accumulates the GroupNorm(32) partial sums of the output; returns
+    (out, (partials, blocks per image)) for groupnorm(..., partials=...)."""
     _chk(x), _chk(w)
     B, H, W, Cin = x.shape
     Cout = w.shape[0]
@@ -145,8 +147,13 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resi
     args.out_f32 = 1 if out.dtype == torch.float32 else 0
     args.resid = N.ptr(resid)
     args.batch, args.H, args.Wd, args.Cin, args.Cout = B, H, W, Cin, Cout
+    part = None
+    if gn_stats:
+        nblk = int(N.lib().fx_conv3x3_gn_blocks(H, W, Cout))
+        part = (torch.empty((B, nblk, 32, 2), device=x.device, dtype=torch.float32), nblk)
+        args.gn_partials = part[0].data_ptr()
     N.check(N.lib().fx_conv3x3(C.byref(args), N.stream()))
-    return out
+    return (out, part) if gn_stats else out
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
@@ -298,18 +305,23 @@ def unpatchify_scale(packed: torch.Tensor, latent_size, c_pad: int, scale_factor
 
 
 def groupnorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float, silu: bool,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(32) on NHWC-like [B, ..., C] contiguous (+ optional SiLU)."""
+              out: Optional[torch.Tensor] = None, partials=None) -> torch.Tensor:
+    """GroupNorm(32) on NHWC-like [B, ..., C] contiguous (+ optional SiLU).
+    partials: (tensor, blocks per image) written by the conv3x3 that produced x (gn_stats=True): the statistics pass
+    over x is skipped."""
     _chk(x)
     B, Cc = x.shape[0], x.shape[-1]
     hw = x.numel() // (B * Cc)
     l = N.lib()
-    sums = torch.empty((int(l.fx_groupnorm_partials_count(B, hw)),), device=x.device, dtype=torch.float32)
     if out is None:
         out = torch.empty_like(x)
-    N.check(l.fx_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, hw, Cc, N.stream()))
     stats = torch.empty((B, 32, 2), device=x.device, dtype=torch.float32)
-    N.check(l.fx_groupnorm_finalize(sums.data_ptr(), stats.data_ptr(), B, hw, Cc, eps, N.stream()))
+    if partials is not None:
+        N.check(l.fx_groupnorm_finalize_blocks(partials[0].data_ptr(), stats.data_ptr(), B, partials[1], hw, Cc, eps, N.stream()))
+    else:
+        sums = torch.empty((int(l.fx_groupnorm_partials_count(B, hw)),), device=x.device, dtype=torch.float32)
+        N.check(l.fx_groupnorm_stats(x.data_ptr(), sums.data_ptr(), B, hw, Cc, N.stream()))
+        N.check(l.fx_groupnorm_finalize(sums.data_ptr(), stats.data_ptr(), B, hw, Cc, eps, N.stream()))
     N.check(l.fx_groupnorm_apply(x.data_ptr(), stats.data_ptr(), weight.data_ptr(), bias.data_ptr(), out.data_ptr(),
                                  B, hw, Cc, int(silu), N.stream()))
     return out

@@ -101,8 +101,14 @@ typedef struct fx_conv3x3_args {
   void* out; int32_t out_f32;  /* [batch][H][W][Cout] */
   const void* resid;           /* [batch][H][W][Cout] or NULL */
   int32_t batch, H, Wd, Cin, Cout;
+  float* gn_partials;          /* NULL, or [batch][fx_conv3x3_gn_blocks(H, Wd, Cout)][32][2] floats: the epilogue also
+                                  writes per-pixel-block (sum, sum of squares) of the bf16 output for each of the 32
+                                  GroupNorm groups -- the statistics pass of the GroupNorm that consumes this output
+                                  (flux/autoencoder.py:88-94) folded into its producer; reduce with
+                                  fx_groupnorm_finalize_blocks.  Needs Cout % 128 == 0, bf16 output. */
 } fx_conv3x3_args;
 int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream);
+int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout);
 
 /* ---------------------------------------------------------------- attention
  * Non-causal softmax(q k^T * scale) v over head_dim 128 on tcgen05 (flash-style, online softmax);
@@ -206,6 +212,9 @@ int64_t fx_groupnorm_partials_count(int32_t batch, int64_t hw);
 int fx_groupnorm_stats(const void* x, float* partials, int32_t batch, int64_t hw, int32_t C, fx_stream stream);
 int fx_groupnorm_finalize(const float* partials, float* stats, int32_t batch, int64_t hw, int32_t C, float eps,
                           fx_stream stream);
+/* the same reduction over `nblk` partial blocks per image (the layout fx_conv3x3's gn_partials writes) */
+int fx_groupnorm_finalize_blocks(const float* partials, float* stats, int32_t batch, int64_t nblk, int64_t hw, int32_t C,
+                                 float eps, fx_stream stream);
 int fx_groupnorm_apply(const void* x, const float* stats, const void* weight, const void* bias, void* out,
                        int32_t batch, int64_t hw, int32_t C, int32_t silu, fx_stream stream);
 /* upsample_nearest(x, (2,2)) on NHWC (flux/autoencoder.py:122) */

@@ -85,6 +85,7 @@ def main(which, sweep=None):
         "fc1_f32out": (lambda: ops.gemm(xm[:, S:], wfc1, out=f32buf), 2.0 * B * L * M * D),
         "fc1_plain": (lambda: ops.gemm(xm[:, S:], wfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "attn": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5), 4.0 * B * H * N * N * 128),
+        "attn_p": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=7), 4.0 * B * H * N * N * 128),
         "attn_seq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=4), 4.0 * B * H * N * N * 128),
         "attn3": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=5), 4.0 * B * H * N * N * 128),
         "attn3_noseq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=6), 4.0 * B * H * N * N * 128),

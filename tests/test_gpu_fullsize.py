@@ -217,3 +217,21 @@ def test_fp8_full_depth_four_steps(schnell, vae):
     assert max(rep["bf16_vs_fp32_latent_rel_l2"]) <= 2e-2, rep
     assert max(rep["fp8_vs_fp32_latent_rel_l2"]) <= 8e-2, rep
     assert rep["bf16_image_mean_abs_255"] <= 2 and rep["fp8_image_mean_abs_255"] <= 4, rep
+
+
+@pytest.mark.parametrize("S", [512, 640])
+def test_t5_xxl_layer_shapes_vs_oracle(S):
+    """T5-v1.1-XXL layer shapes (d_model 4096, d_ff 10240, 64 heads of 64, flux/t5.py:34-48) on the GPU path, two
+    layers, S = 512 (dev's padded length) and S = 640 (> 512: an unpadded long prompt), vs the fp32 oracle."""
+    from flux.t5 import T5Encoder
+    cfg = specs.T5Config(num_layers=2)
+    sd = synthetic.synthetic_state_dict(specs.t5_manifest(cfg), device=dev)
+    t5 = T5Encoder(cfg, device=dev).load_weights(list(sd.items()))
+    tok = torch.randint(3, 32100, (1, S), generator=torch.Generator().manual_seed(S), dtype=torch.int32)
+    out = t5(tok)
+    ocfg = O.T5Config(**{k: v for k, v in vars(cfg).items() if k in O.T5Config.__dataclass_fields__})
+    with torch.device(dev):
+        ref = O.t5_encode(sd, ocfg, tok.to(dev))
+    e = rel_l2(out, ref)
+    report(**{f"t5_xxl_2layers_S{S}_rel_l2": e})
+    assert out.shape == (1, S, 4096) and e <= 1e-2, e

@@ -134,7 +134,7 @@ def test_conv3x3(B, H, W, Cin, Cout):
         ops.conv3x3(rnd(1, 4, 4, 16), rnd(8, 144), None)  # Cin must be a multiple of 64
 
 
-@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6])
+@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6, 7])
 @pytest.mark.parametrize("B,H,S", [(1, 1, 128), (2, 3, 512), (1, 2, 320), (1, 1, 77), (1, 2, 1280), (1, 1, 1)])
 def test_attention(variant, B, H, S):
     q, k, v = rnd(B, H, S, 128, seed=21), rnd(B, H, S, 128, seed=22), rnd(B, H, S, 128, seed=23)
@@ -145,7 +145,7 @@ def test_attention(variant, B, H, S):
     assert out[:, :, H * 128:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("variant", [0, 5, 6])
+@pytest.mark.parametrize("variant", [0, 5, 6, 7])
 def test_attention_sharp_softmax_and_properties(variant):
     q, k, v = rnd(1, 2, 512, 128, seed=24, scale=4), rnd(1, 2, 512, 128, seed=25, scale=4), rnd(1, 2, 512, 128, seed=26)
     out = torch.empty(1, 512, 256, device=dev, dtype=bf)
@@ -164,6 +164,62 @@ def test_attention_sharp_softmax_and_properties(variant):
     assert rel_l2(o2, o1) <= 5e-3
     ref = F.scaled_dot_product_attention(q[:, :2].float(), k[:, :2].float(), v[:, :2].float()).transpose(1, 2).reshape(1, 4352, 256)
     assert rel_l2(o1[:, :, :256], ref) <= 5e-3
+
+
+def test_persistent_attention_is_bit_identical_to_one_cta_per_item():
+    """variant 7 (attn_pkernel: one CTA per SM walking the (q-block, head, batch) items) runs the same arithmetic per
+    query row as the one-CTA-per-item kernel: same bits, with more items than SMs (several items per CTA), a ragged
+    last key tile, an odd number of key tiles and a single item."""
+    for B, H, S in [(2, 24, 4352), (3, 5, 1100), (1, 7, 640), (1, 1, 200)]:
+        q, k, v = rnd(B, H, S, 128, seed=51), rnd(B, H, S, 128, seed=52), rnd(B, H, S, 128, seed=53)
+        a = torch.zeros(B, S, H * 128, device=dev, dtype=bf)
+        b = torch.zeros_like(a)
+        ops.attention(q, k, v, a, 128 ** -0.5, variant=0)
+        ops.attention(q, k, v, b, 128 ** -0.5, variant=7)
+        assert torch.equal(a, b), (B, H, S)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 32, 128, 128), (1, 24, 40, 256, 256), (2, 13, 21, 512, 512), (1, 64, 64, 128, 256)])
+def test_conv3x3_groupnorm_partials(B, H, W, Cin, Cout):
+    """fx_conv3x3's gn_partials (GroupNorm statistics of the output accumulated in the epilogue) against the
+    standalone statistics pass over the stored output; ragged image sizes leave partly empty pixel blocks."""
+    x, w = rnd(B, H, W, Cin, seed=41), rnd(Cout, 9 * Cin, seed=42, scale=(9 * Cin) ** -0.5)
+    bias, res = rnd(Cout, seed=43, scale=0.5), rnd(B, H, W, Cout, seed=44)
+    gw, gb = (1 + rnd(Cout, seed=45, scale=0.1).float()).to(bf), rnd(Cout, seed=46, scale=0.1)
+    for resid in (None, res):
+        out, part = ops.conv3x3(x, w, bias, resid=resid, gn_stats=True)
+        assert torch.equal(out, ops.conv3x3(x, w, bias, resid=resid))          # the output itself is untouched
+        ref = F.group_norm(out.float().permute(0, 3, 1, 2), 32, gw.float(), gb.float(), eps=1e-6).permute(0, 2, 3, 1)
+        fused = ops.groupnorm(out, gw, gb, 1e-6, False, partials=part)
+        plain = ops.groupnorm(out, gw, gb, 1e-6, False)
+        assert rel_l2(fused, ref) <= 5e-3 and rel_l2(fused, plain) <= 1e-3
+        sums = part[0].double().sum(1)                                          # [B, 32, 2]
+        o = out.double().view(B, H * W, 32, Cout // 32)
+        assert torch.allclose(sums[..., 0], o.sum((1, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(sums[..., 1], (o * o).sum((1, 3)), rtol=1e-4, atol=1e-2)
+
+
+def test_rownorm_wide_rows_block_kernel():
+    """D >= 1024 runs one block per row (rownorm_block_kernel): all three modes, D = 1024 / 3072 / 4096 and a D that
+    leaves the last vector slot partly empty, strided views, and the e4m3 output against quantize_rows(bf16 output)."""
+    for D in (1024, 3072, 4096, 1536):
+        B, R = 2, 37
+        x, sh, sc = rnd(B, R, D, seed=61), rnd(B, D, seed=62, scale=0.1), rnd(B, D, seed=63, scale=0.1)
+        ref = (1 + sc.float()[:, None]) * F.layer_norm(x.float(), (D,), eps=1e-6) + sh.float()[:, None]
+        y = ops.rownorm(x, 0, sh, sc, 1e-6)
+        assert rel_l2(y, ref) <= 5e-3
+        w, b = (1 + rnd(D, seed=64, scale=0.1).float()).to(bf), rnd(D, seed=65, scale=0.1)
+        assert rel_l2(ops.rownorm(x, 1, w, b, 1e-5), F.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5)) <= 5e-3
+        ref2 = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6) * w.float()
+        assert rel_l2(ops.rownorm(x, 2, w, None, 1e-6), ref2) <= 5e-3
+        wide = rnd(B, R + 5, D + 64, seed=66)                                   # row / column slice of a wider buffer
+        view = wide[:, 3:3 + R, :D]
+        assert torch.equal(ops.rownorm(view, 0, sh, sc, 1e-6), ops.rownorm(view.contiguous(), 0, sh, sc, 1e-6))
+        q8 = torch.empty(B, R, D, device=dev, dtype=ops.fp8)
+        s8 = torch.empty(B, R, device=dev, dtype=torch.float32)
+        ops.rownorm(x, 0, sh, sc, 1e-6, out=q8, out_scale=s8)
+        qr, sr = ops.quantize_rows(y)
+        assert torch.equal(q8.view(torch.uint8), qr.view(torch.uint8)) and torch.equal(s8, sr)
 
 
 def test_rownorm_gemv_and_friends():
@@ -225,6 +281,24 @@ def test_groupnorm_softmax_attention_small():
     assert rel_l2(ops.attention_small(q, k, v, H, 1.0, bias=bias), ref) <= 5e-3
     ref = F.scaled_dot_product_attention(hd(q), hd(k), hd(v), is_causal=True).transpose(1, 2).reshape(Bq, S, -1)
     assert rel_l2(ops.attention_small(q, k, v, H, 0.125, causal=True), ref) <= 5e-3
+
+
+@pytest.mark.parametrize("S,causal", [(512, False), (700, False), (1300, True), (1030, False)])
+def test_attention_small_long_sequences(S, causal):
+    """fx_attention_small beyond 512 keys (online softmax over 512-key chunks): the reference's T5 tokenizer never
+    truncates (flux/tokenizers.py:160-173), so --no-t5-padding prompts longer than 512 tokens must encode."""
+    Bq, H = 1, 3
+    qkv = rnd(Bq, S, 3 * H * 64, seed=54)
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    hd = lambda t_: t_.float().reshape(Bq, S, H, 64).transpose(1, 2)  # noqa: E731
+    if causal:
+        ref = F.scaled_dot_product_attention(hd(q), hd(k), hd(v), is_causal=True)
+        out = ops.attention_small(q, k, v, H, 0.125, causal=True)
+    else:
+        bias = torch.randn(H, S, S, generator=torch.Generator().manual_seed(55)).to(dev)
+        ref = F.scaled_dot_product_attention(hd(q), hd(k), hd(v), attn_mask=bias[None], scale=1.0)
+        out = ops.attention_small(q, k, v, H, 1.0, bias=bias)
+    assert rel_l2(out, ref.transpose(1, 2).reshape(Bq, S, -1)) <= 5e-3
 
 
 def _philox4x32_10(ctr, key):

@@ -178,7 +178,7 @@ def test_argument_errors_surface_as_value_errors():
     with pytest.raises(ValueError):
         ops.rownorm(torch.zeros(2, 4, 12, device=dev, dtype=bf), 2, torch.ones(12, device=dev, dtype=bf), None, 1e-6)  # D % 8
     with pytest.raises(ValueError):
-        ops.attention_small(*(torch.zeros(1, 600, 64, device=dev, dtype=bf),) * 3, 1, 1.0)   # seq > 512
+        ops.attention_small(*(torch.zeros(1, 0, 64, device=dev, dtype=bf),) * 3, 1, 1.0)     # empty sequence
     with pytest.raises(ValueError):
         ops.gemm(torch.zeros(8, 64, device=dev, dtype=torch.float32), torch.zeros(8, 64, device=dev, dtype=bf))  # dtype
     q = torch.zeros(1, 2, 16, 128, device=dev, dtype=bf)
@@ -293,11 +293,17 @@ def test_cli_end_to_end_writes_images(tmp_path, monkeypatch):
     assert im.size == (2 * (96 + 8), 2 * (64 + 8))  # (W, H): 2 columns x 2 rows of 4-px padded images
     raw = tmp_path / "img.png"
     txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
-                    "--output", str(raw), "--model", "dev", "--guidance", "3.5"])
+                    "--output", str(raw), "--model", "dev", "--guidance", "3.5", "--seed", "7"])
     a, b = Image.open(tmp_path / "img.0.png"), Image.open(tmp_path / "img.1.png")
     assert a.size == (96, 64) and b.size == (96, 64)  # rounded UP to multiples of 16 (txt2image.py:14-25)
     assert a.tobytes() != b.tobytes()  # different prior per image
     # same seed, same images: the run is deterministic
     txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
-                    "--output", str(tmp_path / "again.png"), "--model", "dev", "--guidance", "3.5"])
+                    "--output", str(tmp_path / "again.png"), "--model", "dev", "--guidance", "3.5", "--seed", "7"])
     assert Image.open(tmp_path / "again.0.png").tobytes() == a.tobytes()
+    # no --seed: fresh noise every run, like the reference's un-reseeded global PRNG (flux/flux.py:138-139)
+    txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
+                    "--output", str(tmp_path / "u.png"), "--model", "dev", "--guidance", "3.5"])
+    txt2image.main(["a cat", "--synthetic", "--n-images", "2", "--image-size", "60x90", "--steps", "1", "--save-raw",
+                    "--output", str(tmp_path / "v.png"), "--model", "dev", "--guidance", "3.5"])
+    assert Image.open(tmp_path / "u.0.png").tobytes() != Image.open(tmp_path / "v.0.png").tobytes()
