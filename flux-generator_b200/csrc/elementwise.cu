@@ -170,8 +170,8 @@ __device__ __forceinline__ float block_sum4(float v, float* red, int lane, int w
 __device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {  // packed bf16 pair -> packed fp32 pair (2 ALU ops)
   return pack2f(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
-template <int VPT, bool F8OUT>  // VPT = ceil(D / 1024) 16-byte vectors per thread
-__global__ void __launch_bounds__(128) rownorm_block_kernel(const RowNormParams p) {
+template <int VPT, bool F8OUT, int MINB>  // VPT = ceil(D / 1024) 16-byte vectors per thread; MINB resident blocks per SM
+__global__ void __launch_bounds__(128, MINB) rownorm_block_kernel(const RowNormParams p) {
   // Persistent blocks walk the rows with a grid stride; the next row's loads are issued before the current row is
   // reduced.  The kernel was INSTRUCTION-bound, not HBM-bound (~350 instructions per thread and row: the packed row was
   // unpacked three times and the modulation vectors once per row; 3.9 TB/s whatever the launch geometry).  Now the row
@@ -817,18 +817,20 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
     static int per_sm = -1;  // FX_ROWNORM_BLOCKS_PER_SM: resident 128-thread blocks per SM of the persistent grid
     if (per_sm < 0) {
       const char* e = getenv("FX_ROWNORM_BLOCKS_PER_SM");
-      per_sm = e ? atoi(e) : 4;  // 120 registers x 128 threads: four blocks are resident
-      if (per_sm < 1) per_sm = 1;
+      per_sm = e ? atoi(e) : 4;  // rows in flight per SM scale the bandwidth (latency-bound): 4 / 5 / 6 resident blocks
+      per_sm = per_sm < 5 ? 4 : (per_sm > 5 ? 6 : 5);
     }
     const long long cap = (long long)per_sm * num_sms();
     const unsigned g = (unsigned)(rows < cap ? rows : cap);
     const int vpt = (a->D + 1023) / 1024;
-#define FX_RB(V)                                                                     \
+#define FX_RB(V, M)                                                                  \
   case V:                                                                            \
-    if (a->out_fp8) rownorm_block_kernel<V, true><<<g, 128, 0, st>>>(p);             \
-    else rownorm_block_kernel<V, false><<<g, 128, 0, st>>>(p);                       \
+    if (a->out_fp8) rownorm_block_kernel<V, true, M><<<g, 128, 0, st>>>(p);          \
+    else rownorm_block_kernel<V, false, M><<<g, 128, 0, st>>>(p);                    \
     break;
-    switch (vpt) { FX_RB(1) FX_RB(2) FX_RB(3) FX_RB(4) }
+    if (per_sm == 4) { switch (vpt) { FX_RB(1, 4) FX_RB(2, 4) FX_RB(3, 4) FX_RB(4, 4) } }
+    else if (per_sm == 5) { switch (vpt) { FX_RB(1, 5) FX_RB(2, 5) FX_RB(3, 5) FX_RB(4, 5) } }
+    else { switch (vpt) { FX_RB(1, 6) FX_RB(2, 6) FX_RB(3, 6) FX_RB(4, 6) } }
 #undef FX_RB
     return launched("rownorm_block_kernel");
   }

@@ -220,25 +220,42 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->x && a->W && a->out, "fx_conv3x3: null pointer");
   FX_REQUIRE(a->batch > 0 && a->H > 0 && a->Wd > 0 && a->Cout > 0, "fx_conv3x3: empty problem");
   FX_REQUIRE(a->Cin % 64 == 0 && a->Cin > 0, "fx_conv3x3: Cin (%d) must be a multiple of 64", a->Cin);
+  const int up = a->upsample2x ? 1 : 0;
+  const int taps = up ? 4 : 9;
+  FX_REQUIRE(!up || (a->Cout % 128 == 0 && !a->resid && !a->out_f32 && a->batch < (1 << 28)),
+             "fx_conv3x3: upsample2x needs Cout %% 128 == 0, a bf16 output and no residual");
   GemmParams p{};
-  p.batch = a->batch; p.rows = a->H * a->Wd; p.N = a->Cout; p.K = 9 * a->Cin;
+  // upsample2x: four parity convolutions per image ride in the batch index of the tile raster (b' = 4 * image + parity)
+  p.batch = up ? 4 * a->batch : a->batch;
+  p.rows = a->H * a->Wd; p.N = a->Cout; p.K = taps * a->Cin;
   p.cin_blocks = a->Cin / GEMM_BK;
-  p.k_blocks = 9 * p.cin_blocks;
+  p.k_blocks = taps * p.cin_blocks;
   p.conv_H = a->H; p.conv_W = a->Wd;
+  p.conv_up = up;
   const int bn = pick_bn(a->Cout);
   const int ncta = want_ncta(bn);  // CTA pair: two horizontally adjacent 8x16-pixel patches form one 256-row tile
+  FX_REQUIRE(!up || a->Cout % bn == 0, "fx_conv3x3: upsample2x needs Cout to be a multiple of the column tile (%d)", bn);
   p.conv_tiles_x = (a->Wd + 16 * ncta - 1) / (16 * ncta);
   p.conv_tiles_y = (a->H + 7) / 8;
   p.bias = (const __nv_bfloat16*)a->bias;
-  p.out = a->out; p.ldo = a->Cout; p.out_bs = (long long)a->H * a->Wd * a->Cout; p.out_f32 = a->out_f32;
-  p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = p.out_bs;
+  p.out = a->out; p.out_f32 = a->out_f32;
+  if (up) {  // output pixel (2y + py, 2x + px): pixels of one parity are 2 Cout apart, their lines 2 * (2W) * Cout
+    p.ldo = 2ll * a->Cout;
+    p.conv_line = 4ll * a->Wd * a->Cout;
+    p.out_bs = 4ll * a->H * a->Wd * a->Cout;
+  } else {
+    p.ldo = a->Cout;
+    p.conv_line = (long long)a->Wd * a->Cout;
+    p.out_bs = (long long)a->H * a->Wd * a->Cout;
+  }
+  p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->Cout; p.resid_bs = (long long)a->H * a->Wd * a->Cout;
   fill_tiling(p, p.conv_tiles_x * p.conv_tiles_y, bn);
   fill_l2_policy(p, 2);
   if (a->gn_partials) {
     FX_REQUIRE(a->Cout % 128 == 0 && !a->out_f32, "fx_conv3x3: gn_partials needs Cout %% 128 == 0 and a bf16 output");
     p.gn_partials = a->gn_partials;
     p.gn_gs = a->Cout / 32;
-    p.gn_nblk = p.conv_tiles_x * p.conv_tiles_y * ncta * 4;
+    p.gn_nblk = p.conv_tiles_x * p.conv_tiles_y * ncta * 4 * (up ? 4 : 1);
   }
   CUtensorMap ta, tw;
   {
@@ -249,7 +266,7 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)a->Cout};
+    const uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)a->Cout * (up ? 4 : 1)};
     const uint64_t strides[1] = {(uint64_t)p.K * 2};
     const uint32_t box[2] = {GEMM_BK, (uint32_t)(bn / ncta)};
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box);
@@ -258,9 +275,9 @@ extern "C" int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream) {
   return launch_bn<EPI_GENERIC, true>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
 }
 
-extern "C" int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout) {
+extern "C" int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout, int32_t upsample2x) {
   const int ncta = want_ncta(pick_bn(Cout));
-  return (int64_t)((Wd + 16 * ncta - 1) / (16 * ncta)) * ((H + 7) / 8) * ncta * 4;
+  return (int64_t)((Wd + 16 * ncta - 1) / (16 * ncta)) * ((H + 7) / 8) * ncta * 4 * (upsample2x ? 4 : 1);
 }
 
 // ------------------------------------------------------------------------------------------

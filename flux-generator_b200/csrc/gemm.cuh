@@ -73,6 +73,15 @@ struct GemmParams {
   //      gn_partials[batch][gn_nblk][32 groups][sum, sum of squares]; gn_gs = channels per group (4 / 8 / 16)
   float* gn_partials;
   int gn_gs, gn_nblk;
+  // ---- conv mode, conv_up = 1: nearest-2x upsample + 3x3 convolution (flux/autoencoder.py:121-124) as FOUR 2x2
+  //      convolutions of the LOW-resolution input, one per output-pixel parity (py, px).  On the upsampled image the
+  //      3x3 taps of an output pixel (2y + py, 2x + px) fall on only 2 x 2 source pixels -- rows {y - 1 + py, y + py},
+  //      columns likewise -- so taps that share a source pixel are pre-summed into W4[parity][Cout][4 * Cin] (host:
+  //      ops.upconv_weights).  16 instead of 36 MACs per output element and channel pair, and the 4x larger upsampled
+  //      tensor is never written or read.  The parity rides in the tile's batch index (b' = 4 * image + parity);
+  //      conv_line = elements between output image lines of one parity (ldo = elements between its pixels).
+  int conv_up;
+  long long conv_line;
 };
 
 // (sum, sum of squares) of one 32-column chunk of a warp's 32 output rows for the GS-channel GroupNorm groups it
@@ -364,27 +373,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
+          // conv: which source pixel offset this k-block's tap reads, which image, which weight rows
+          int dx = 0, dy = 0, bimg = b, wrow = 0, c0 = 0;
+          if (CONV) {
+            const int tap = kb / p.cin_blocks;
+            c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
+            if (p.conv_up) {  // b = 4 * image + parity; 2 x 2 taps at rows {py - 1, py}, columns {px - 1, px}
+              const int par = b & 3;
+              bimg = b >> 2;
+              dx = (par & 1) - 1 + (tap & 1);
+              dy = (par >> 1) - 1 + (tap >> 1);
+              wrow = par * p.N;
+            } else {
+              dx = tap % 3 - 1;
+              dy = tap / 3 - 1;
+            }
+          }
           if (NCTA == 2) {
             // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             if (CONV) {
-              const int tap = kb / p.cin_blocks;
-              const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
-              tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
+              tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + dx, cy + dy, bimg);
             } else {
               tma2_load_3d_hint(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b, p.hint_a);
             }
-            tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
+            tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {
-            const int tap = kb / p.cin_blocks;
-            const int c0 = (kb - tap * p.cin_blocks) * GEMM_BK;
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + tap % 3 - 1, cy + tap / 3 - 1, b);
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + dx, cy + dy, bimg);
           } else {
             tma_load_3d(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * GEMM_BM, b);
           }
-          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, tn * BN);
+          tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -485,11 +506,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int tmb = tm - b * p.tiles_m_per_batch;
       bool valid;
       long long row;  // row index inside the batch (pixel index for conv)
+      long long conv_off = 0;  // conv: element offset of this thread's output pixel inside its image
+      int bimg = b, par = 0;   // conv_up: b = 4 * image + parity
       if (CONV) {
         const int y = (tmb / p.conv_tiles_x) * 8 + (r >> 4);
         const int x = (tmb % p.conv_tiles_x) * (16 * NCTA) + int(cta_rank) * 16 + (r & 15);
         valid = (y < p.conv_H) && (x < p.conv_W);
         row = (long long)y * p.conv_W + x;
+        if (p.conv_up) {  // output pixel (2y + py, 2x + px) of the 2H x 2W image: ldo = 2 Cout, conv_line = 4 W Cout
+          par = b & 3;
+          bimg = b >> 2;
+          conv_off = (long long)y * p.conv_line + (long long)x * p.ldo + ((long long)(par >> 1) * 2 * p.conv_W + (par & 1)) * (p.ldo >> 1);
+        } else {
+          conv_off = row * p.ldo;
+        }
       } else {
         row = (long long)tmb * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
         valid = row < p.rows;
@@ -504,8 +534,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         constexpr int CH = BN / 64;        // 32-column chunks per warp
         constexpr int WN = BN / 2;         // columns per warp
         const int nw0 = tn * BN + half * WN;
-        const long long out_off = (long long)b * p.out_bs + row * p.ldo;
-        const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
+        const long long out_off = CONV ? (long long)bimg * p.out_bs + conv_off : (long long)b * p.out_bs + row * p.ldo;
+        const long long res_off = (long long)bimg * p.resid_bs + row * p.ldr;
         const bool vec_ok = ((p.ldo | p.ldr) & 7) == 0;
         // ---- everything that does not depend on the accumulator happens BEFORE the wait
         __syncwarp();
@@ -543,10 +573,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
             epi_generic_chunk<F8>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0,
                                   vec_ok && (n0 + 32 <= p.N), sw + c * 32, rs, wst, lane, vmask, valid,
-                                  CONV ? ((long long)(lane & 15) + (long long)(lane >> 4) * p.conv_W) * p.ldo : -1,
-                                  CONV ? (long long)p.conv_W * p.ldo : -1);
+                                  CONV ? (long long)(lane & 15) * p.ldo + (long long)(lane >> 4) * p.conv_line : -1,
+                                  CONV ? p.conv_line : -1);
             if (CONV && p.gn_partials != nullptr)  // f[] now holds the final values (bias, residual) of 32 channels
-              gn_chunk_partials(p.gn_partials + (((long long)b * p.gn_nblk + (long long)(tmb * NCTA + int(cta_rank)) * 4 + quarter) * 32 +
+              gn_chunk_partials(p.gn_partials + (((long long)bimg * p.gn_nblk +
+                                                  (long long)((par * p.tiles_m_per_batch + tmb) * NCTA + int(cta_rank)) * 4 + quarter) * 32 +
                                                  n0 / p.gn_gs) * 2,
                                 f, valid, lane, p.gn_gs);
           }

@@ -37,7 +37,7 @@ class QkvArgs(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [("x", c_vp), ("W", c_vp), ("bias", c_vp), ("out", c_vp), ("out_f32", c_i32), ("resid", c_vp),
-                ("batch", c_i32), ("H", c_i32), ("Wd", c_i32), ("Cin", c_i32), ("Cout", c_i32), ("gn_partials", c_vp)]
+                ("batch", c_i32), ("H", c_i32), ("Wd", c_i32), ("Cin", c_i32), ("Cout", c_i32), ("gn_partials", c_vp), ("upsample2x", c_i32)]
 
 
 class AttnArgs(C.Structure):
@@ -77,7 +77,7 @@ SYMBOLS = {
     "fx_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "fx_gemm_qkv": (C.c_int, [C.POINTER(QkvArgs), c_vp]),
     "fx_conv3x3": (C.c_int, [C.POINTER(ConvArgs), c_vp]),
-    "fx_conv3x3_gn_blocks": (C.c_int64, [c_i32, c_i32, c_i32]),
+    "fx_conv3x3_gn_blocks": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "fx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),
     "fx_attention_small": (C.c_int, [C.POINTER(AttnSmallArgs), c_vp]),
     "fx_rownorm": (C.c_int, [C.POINTER(RowNormArgs), c_vp]),

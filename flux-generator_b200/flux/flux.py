@@ -12,7 +12,7 @@ Differences that follow from the platform, not from choice:
     ``x_T=`` to supply the prior explicitly (parity tests do).
   * T5 / CLIP outputs are cached per prompt (north star: "run once per prompt and cached").
   * LoRA adapters (linear_to_lora_layers / fuse_lora_layers, flux/lora.py) are always run FUSED into the weights;
-    training_loss is out of scope (training) and raises.
+    training_loss evaluates the objective's forward value (no backward pass: these are inference kernels).
 """
 from __future__ import annotations
 
@@ -181,8 +181,18 @@ class FluxPipeline:
             yield x_t
 
     def generate_latents(self, text: str, n_images: int = 1, num_steps: int = 35, guidance: float = 4.0,
-                         latent_size: Tuple[int, int] = (64, 64), seed=None, x_T: Optional[torch.Tensor] = None):
-        if x_T is None:
+                         latent_size: Tuple[int, int] = (64, 64), seed=None, x_T: Optional[torch.Tensor] = None,
+                         x_T_packed: Optional[torch.Tensor] = None):
+        """flux/flux.py:128-155.  `text` may be a list with one prompt per image.  x_T: an NHWC prior [B, h, w, 16] (the
+        reference's layout); x_T_packed: the same prior already packed [B, L, 64] (flux_serve.py builds coalesced batches
+        from per-request priors with ops.prior_packed)."""
+        if x_T_packed is not None:
+            h, w = latent_size
+            x_T = x_T_packed.to(device=self.device, dtype=bf16)
+            if x_T.shape != (n_images, h * w // 4, 64):
+                raise ValueError(f"x_T_packed has shape {tuple(x_T.shape)}, expected {(n_images, h * w // 4, 64)}")
+            x_ids = self._latent_ids(n_images, h, w)
+        elif x_T is None:
             # prior drawn on the device straight into the packed layout (sample_prior + patchify fused)
             h, w = latent_size
             if h % 2 or w % 2:
@@ -223,9 +233,30 @@ class FluxPipeline:
             images.append(self.decode(x_t[i:i + decoding_batch_size], latent_size))
         return torch.cat(images, dim=0)
 
-    # ------------------------------------------------------------------ out of scope this round
-    def training_loss(self, *a, **k):
-        raise NotImplementedError("training is outside the B200 hot path (SURVEY 8-f N4)")
+    # ------------------------------------------------------------------ flux/flux.py:195-226
+    def training_loss(self, x_0: torch.Tensor, t5_features: torch.Tensor, clip_features: torch.Tensor,
+                      guidance: torch.Tensor, t: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+        """The rectified-flow training objective, FORWARD value only: mean((pred + x_0 - eps)^2) with
+        x_t = (1 - t) x_0 + t eps (flux/flux.py:195-226).  x_0 are VAE latents [B, h, w, 16] (AutoEncoder.encode),
+        t5_features / clip_features the cached text-encoder outputs, guidance [B].  `t` [B] and `eps` (packed, like the
+        patchified x_0) may be supplied for reproducibility; otherwise they are drawn as the reference draws them.
+        The kernels are inference kernels: there is no backward pass, so this evaluates / validates a loss (e.g. of a
+        loaded adapter), it does not train one -- optimisation stays with the reference's MLX trainer (out of scope)."""
+        txt = t5_features.to(device=self.device, dtype=bf16)
+        vec = clip_features.to(device=self.device, dtype=bf16)
+        txt_ids = self._txt_ids(txt.shape[0], txt.shape[1])
+        x_0, x_ids = self._prepare_latent_images(x_0)
+        B, L, _ = x_0.shape
+        if t is None:
+            t = self.sampler.random_timesteps(B, L)
+        t = t.to(device=self.device, dtype=self.dtype)
+        if eps is None:
+            eps = torch.randn(x_0.shape, device=self.device, dtype=torch.float32)
+        eps = eps.to(device=self.device, dtype=self.dtype)
+        x_t = self.sampler.add_noise(x_0, t, noise=eps)
+        pred = self.flow(img=x_t, img_ids=x_ids, txt=txt, txt_ids=txt_ids, y=vec, timesteps=t,
+                         guidance=guidance.to(device=self.device, dtype=self.dtype))
+        return (pred + x_0 - eps).square().mean()
 
     # ------------------------------------------------------------------ LoRA adapters at inference
     def linear_to_lora_layers(self, rank: int = 8, num_blocks: int = -1):

@@ -131,29 +131,54 @@ def block_pe(pe: torch.Tensor) -> torch.Tensor:
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], resid: Optional[torch.Tensor] = None,
-            out_dtype: torch.dtype = bf16, out: Optional[torch.Tensor] = None, gn_stats: bool = False):
+            out_dtype: torch.dtype = bf16, out: Optional[torch.Tensor] = None, gn_stats: bool = False,
+            upsample: bool = False):
     """x [B,H,W,Cin] NHWC contiguous; w [Cout, 9*Cin] (OHWI flattened).
     gn_stats=True: the epilogue also accumulates the GroupNorm(32) partial sums of the output; returns
-    (out, (partials, blocks per image)) for groupnorm(..., partials=...)."""
+    (out, (partials, blocks per image)) for groupnorm(..., partials=...).
+    upsample=True: out = conv3x3(upsample_nearest(x, 2)) [B,2H,2W,Cout] without the upsampled tensor; w is the
+    parity-decomposed kernel [4*Cout, 4*Cin] of upconv_weights()."""
     _chk(x), _chk(w)
     B, H, W, Cin = x.shape
-    Cout = w.shape[0]
+    Cout = w.shape[0] // 4 if upsample else w.shape[0]
+    if w.shape[1] != (4 if upsample else 9) * Cin:
+        raise ValueError(f"weight {tuple(w.shape)} does not match Cin={Cin} (upsample={upsample})")
     if not x.is_contiguous():
         raise ValueError("conv3x3 input must be contiguous NHWC")
+    s = 2 if upsample else 1
     if out is None:
-        out = torch.empty((B, H, W, Cout), device=x.device, dtype=out_dtype)
+        out = torch.empty((B, s * H, s * W, Cout), device=x.device, dtype=out_dtype)
     args = N.ConvArgs()
     args.x, args.W, args.bias, args.out = x.data_ptr(), w.data_ptr(), N.ptr(bias), out.data_ptr()
     args.out_f32 = 1 if out.dtype == torch.float32 else 0
     args.resid = N.ptr(resid)
     args.batch, args.H, args.Wd, args.Cin, args.Cout = B, H, W, Cin, Cout
+    args.upsample2x = int(upsample)
     part = None
     if gn_stats:
-        nblk = int(N.lib().fx_conv3x3_gn_blocks(H, W, Cout))
+        nblk = int(N.lib().fx_conv3x3_gn_blocks(H, W, Cout, int(upsample)))
         part = (torch.empty((B, nblk, 32, 2), device=x.device, dtype=torch.float32), nblk)
         args.gn_partials = part[0].data_ptr()
     N.check(N.lib().fx_conv3x3(C.byref(args), N.stream()))
     return (out, part) if gn_stats else out
+
+
+def upconv_weights(w: torch.Tensor) -> torch.Tensor:
+    """3x3 kernel [Cout, 9*Cin] (OHWI flattened) -> the four 2x2 kernels of conv3x3(upsample_nearest(x, 2)), one per output
+    parity (py, px), stacked [4*Cout, 4*Cin] (parity = 2*py + px, tap = 2*a + b).  Output pixel (2y+py, 2x+px) reads the
+    source rows {y-1+py, y+py}: for py = 0 tap row a=0 is kernel row 0 and a=1 is kernel rows 1+2, for py = 1 a=0 is rows
+    0+1 and a=1 is row 2; columns likewise.  Sums in fp32, one rounding to bf16."""
+    Cout, k9 = w.shape
+    Cin = k9 // 9
+    w9 = w.float().view(Cout, 3, 3, Cin)
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    out = torch.empty((4, Cout, 2, 2, Cin), device=w.device, dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    out[2 * py + px, :, a, b] = w9[:, list(groups[py][a])][:, :, list(groups[px][b])].sum((1, 2))
+    return out.view(4 * Cout, 4 * Cin).to(w.dtype).contiguous()
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,

@@ -37,6 +37,27 @@ class FluxSampler:
             t = self._time_shift(image_sequence_length, t)
         return [float(v) for v in t]
 
+    def random_timesteps(self, B, L, dtype=None, key=None):
+        """flux/sampler.py:33-42: schnell draws t from {1/4, 2/4, 3/4, 1}, dev a uniform t pushed through the time shift.
+        Returns a torch tensor [B] (float32, or `dtype`); `key` seeds a torch generator."""
+        import torch
+        g = torch.Generator().manual_seed(0 if key is None else int(key)) if key is not None else None
+        if self._schnell:
+            t = torch.randint(1, 5, (B,), generator=g).to(torch.float32) / 4
+        else:
+            u = torch.rand((B,), generator=g, dtype=torch.float32).numpy()
+            t = torch.from_numpy(self._time_shift(L, u))
+        return t if dtype is None else t.to(dtype)
+
+    def add_noise(self, x, t, noise=None, key=None):
+        """flux/sampler.py:47-54: x * (1 - t) + t * noise, t broadcast over the trailing dimensions."""
+        import torch
+        if noise is None:
+            g = torch.Generator(device=x.device).manual_seed(0 if key is None else int(key))
+            noise = torch.randn(x.shape, generator=g, device=x.device, dtype=torch.float32).to(x.dtype)
+        t = t.to(device=x.device, dtype=x.dtype).reshape([-1] + [1] * (x.ndim - 1))
+        return x * (1 - t) + t * noise
+
     def sample_prior(self, shape, dtype=None, key=None, first_index: int = 0):
         """flux/sampler.py:44-45.  MLX's threefry stream cannot be reproduced offline (SURVEY 8-a2);
         noise is keyed by (seed, global image index) instead -- see flux.synthetic.synthetic_prior."""

@@ -187,6 +187,30 @@ def ae_decoder_manifest(a: AutoEncoderParams) -> Manifest:
     return m
 
 
+def ae_encoder_manifest(a: AutoEncoderParams) -> Manifest:
+    """`encoder.*` keys of ae.safetensors (flux/autoencoder.py:127-178)."""
+    m: Manifest = []
+    n = len(a.ch_mult)
+    _conv(m, "encoder.conv_in", a.ch, a.in_channels, 3)
+    in_mult = (1,) + tuple(a.ch_mult)
+    block_in = a.ch
+    for lvl in range(n):
+        block_in, block_out = a.ch * in_mult[lvl], a.ch * a.ch_mult[lvl]
+        for b in range(a.num_res_blocks):
+            _res(m, f"encoder.down.{lvl}.block.{b}", block_in, block_out)
+            block_in = block_out
+        if lvl != n - 1:
+            _conv(m, f"encoder.down.{lvl}.downsample.conv", block_in, block_in, 3)
+    _res(m, "encoder.mid.block_1", block_in, block_in)
+    _gn(m, "encoder.mid.attn_1.norm", block_in)
+    for nm in ("q", "k", "v", "proj_out"):
+        _conv(m, f"encoder.mid.attn_1.{nm}", block_in, block_in, 1)
+    _res(m, "encoder.mid.block_2", block_in, block_in)
+    _gn(m, "encoder.norm_out", block_in)
+    _conv(m, "encoder.conv_out", 2 * a.z_channels, block_in, 3)
+    return m
+
+
 def t5_manifest(c: T5Config) -> Manifest:
     """HF T5 encoder keys (flux/t5.py:10-31 replacement patterns)."""
     inner = c.d_kv * c.num_heads

@@ -20,7 +20,7 @@ import torch
 from .autoencoder import AutoEncoder
 from .clip import CLIPTextModel
 from .model import Flux
-from .specs import (AutoEncoderParams, CLIPTextModelConfig, FluxParams, T5Config, ae_decoder_manifest,
+from .specs import (AutoEncoderParams, CLIPTextModelConfig, FluxParams, T5Config, ae_decoder_manifest, ae_encoder_manifest,
                     clip_manifest, flow_manifest, t5_manifest)
 from .synthetic import synthetic_state_dict
 from .t5 import T5Encoder
@@ -128,7 +128,7 @@ def load_ae(name: str, hf_download: bool = True, synthetic: Optional[bool] = Non
     ae = AutoEncoder(params, device=device)
     path = configs[name].ae_path if name in configs else None
     if want_synthetic(synthetic):
-        return _finish(ae, None, ae_decoder_manifest(params), True, gen_device)
+        return _finish(ae, None, ae_decoder_manifest(params) + ae_encoder_manifest(params), True, gen_device)
     if path is None and not hf_download:
         return ae
     path = _need(path, "autoencoder checkpoint (AE)")

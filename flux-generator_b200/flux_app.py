@@ -13,9 +13,11 @@ and quirks kept on purpose:
   * one pipeline is cached, keyed by the model name with the "flux-" prefix added when missing (flux_app.py:71-88).
 Not part of this build (reference product shell, SURVEY 2.1 #15-18: OUT OF SCOPE): the Gradio UI, the Stable Diffusion
 and MusicGen back ends (requests naming a "stabilityai/..." model are answered with HTTP 500 and a clear message) and
-the macOS compatibility check.  B200 specifics: the whole batch is decoded in one call on the GPU, requests are
-serialised by a lock (one CUDA context, one stream), `--synthetic` serves seeded random weights when no checkpoints
-exist offline, `--quantize` selects the FP8 path.
+the macOS compatibility check.  B200 specifics: the whole batch is decoded in one call on the GPU; concurrent requests
+of the same (model, size, steps, guidance) are COALESCED into batches of up to 8 images per GPU and spread over
+`--gpus N` worker processes, one per GPU (flux_serve.py: every image is bit-identical to what its request would have
+produced alone); `--synthetic` serves seeded random weights when no checkpoints exist offline, `--quantize` selects the
+FP8 path.
 """
 from __future__ import annotations
 
@@ -36,6 +38,7 @@ if HERE not in sys.path:
     sys.path.insert(0, HERE)
 
 import flux  # noqa: E402  (FluxPipeline is looked up on the package at call time so tests can patch flux.FluxPipeline)
+import flux_serve  # noqa: E402
 
 
 # ---------------------------------------------------------------------------------------------
@@ -63,13 +66,55 @@ class SDAPIResponse(BaseModel):
 class FluxAPI:
     """Unified API for external callers (flux_app.py:64-295)."""
 
-    def __init__(self, synthetic: Optional[bool] = None, quantize: bool = False, device: Optional[str] = None):
+    def __init__(self, synthetic: Optional[bool] = None, quantize: bool = False, device: Optional[str] = None,
+                 gpus: int = 1, coalesce: bool = True):
         self.pipeline = None
         self.current_model = None
         self.synthetic = synthetic
         self.quantize = quantize
         self.device = device
+        self.gpus = gpus
+        self.coalesce = coalesce
         self._lock = threading.Lock()
+        self._scheduler: Optional[flux_serve.NodeScheduler] = None
+
+    # ------------------------------------------------------------------ coalescing / multi-GPU dispatch (flux_serve.py)
+    @property
+    def scheduler(self) -> flux_serve.NodeScheduler:
+        """One worker per GPU: this process for a single device, one spawned process per device for --gpus N."""
+        if self._scheduler is None:
+            if self.gpus <= 1:
+                workers = [self.run_job]
+            else:
+                import functools
+                make = functools.partial(_make_runner, self.synthetic, self.quantize)
+                workers = [flux_serve.ProcessWorker(f"cuda:{i}", make) for i in range(self.gpus)]
+            self._scheduler = flux_serve.NodeScheduler(workers)
+        return self._scheduler
+
+    def run_job(self, job: "flux_serve.Job") -> list:
+        """One coalesced batch on this API's device: per-image prompts, per-image priors keyed by (the request's seed,
+        the image's index inside its request) -> uint8 arrays, one per job item."""
+        import numpy as np
+        import torch
+        from flux import ops
+        model, height, width, steps, guidance = job.key
+        with self._lock:
+            pipeline = self.init_pipeline(model)
+            latent_size = (height // 8, width // 8)                 # flux_app.py:141
+            steps = steps or (50 if model == "flux-dev" else 2)     # flux_app.py:158
+            prompts = [it[2] for it in job.items]
+            x = torch.cat([ops.prior_packed(1, latent_size, 16, it[3], first_index=it[1], device=pipeline.device)
+                           for it in job.items], 0)
+            text = prompts[0] if all(p == prompts[0] for p in prompts) else prompts
+            latents = pipeline.generate_latents(text, n_images=len(prompts), num_steps=steps, latent_size=latent_size,
+                                                guidance=guidance, x_T_packed=x)
+            next(latents)
+            x_t = None
+            for x_t in latents:
+                pass
+            u8 = pipeline.decode_uint8(x_t, latent_size).cpu()
+        return [np.asarray(u8[i]) for i in range(len(prompts))]
 
     def init_pipeline(self, model: str):
         """flux_app.py:71-88: one cached pipeline, re-created when the model name changes."""
@@ -92,10 +137,14 @@ class FluxAPI:
     async def txt2img(self, request: SDAPIRequest) -> SDAPIResponse:
         """flux_app.py:90-121."""
         try:
-            images = self.generate_images(
+            # off the event loop: other requests keep arriving while this one runs, which is what lets them coalesce
+            import asyncio
+            import functools
+            images = await asyncio.to_thread(functools.partial(
+                self.generate_images,
                 prompt=request.prompt, model=request.model, width=request.width, height=request.height,
                 steps=request.steps, guidance=request.cfg_scale, seed=request.seed if request.seed >= 0 else None,
-                batch_size=request.batch_size, n_iter=request.n_iter, return_pil=False)
+                batch_size=request.batch_size, n_iter=request.n_iter, return_pil=False))
             return SDAPIResponse(
                 images=images,
                 parameters={"prompt": request.prompt, "negative_prompt": request.negative_prompt, "width": request.width,
@@ -111,11 +160,24 @@ class FluxAPI:
         """flux_app.py:123-204: conditioning -> denoise loop -> decode -> uint8 (truncation) -> PNG -> base64."""
         import numpy as np
         from PIL import Image
+        n = batch_size * n_iter
+        native = self.gpus > 1
+        if not native:
+            with self._lock:
+                native = getattr(self.init_pipeline(model), "_b200_native", False) is True
+        if native and self.coalesce:
+            # B200 pipeline(s): the request joins whatever compatible requests are in flight (flux_serve.coalesce).  A
+            # request without a seed draws one here, so its images stay consistent when they span several jobs / GPUs.
+            if seed is None:
+                seed = int.from_bytes(os.urandom(8), "little") >> 1
+            req = flux_serve.ImageRequest(prompt=prompt, model=model, height=height, width=width, steps=steps,
+                                          guidance=guidance, seed=seed, n_images=n)
+            arrays = self.scheduler.submit(req)
+            return self._encode(arrays, return_pil)
         with self._lock:
             pipeline = self.init_pipeline(model)
             latent_size = (height // 8, width // 8)                 # flux_app.py:141 (no /16 rounding here)
             steps = steps or (50 if model == "flux-dev" else 2)     # flux_app.py:158
-            n = batch_size * n_iter
             latents = pipeline.generate_latents(prompt, n_images=n, num_steps=steps, latent_size=latent_size,
                                                 guidance=guidance, seed=seed)
             next(latents)                                           # conditioning (T5 / CLIP run here, cached per prompt)
@@ -130,6 +192,11 @@ class FluxAPI:
                 for i in range(n):
                     img = np.asarray(pipeline.decode(x_t[i:i + 1], latent_size))
                     arrays.append((img[0] * 255).astype(np.uint8))  # flux_app.py:192: truncation
+        return self._encode(arrays, return_pil)
+
+    @staticmethod
+    def _encode(arrays, return_pil: bool):
+        from PIL import Image
         images = []
         for arr in arrays:
             pil_image = Image.fromarray(arr)
@@ -170,6 +237,11 @@ class FluxAPI:
         return {"progress": 0, "eta_relative": 0,
                 "state": {"skipped": False, "interrupted": False, "job": "", "job_count": 0, "job_timestamp": ""},
                 "current_image": None, "textinfo": "Idle"}
+
+
+def _make_runner(synthetic, quantize, device: str):
+    """Built inside a worker process (flux_serve.ProcessWorker): a FluxAPI pinned to `device`, serving jobs."""
+    return FluxAPI(synthetic=synthetic, quantize=quantize, device=device).run_job
 
 
 api = FluxAPI()
@@ -249,6 +321,7 @@ def main(argv=None):
     listen_group.add_argument("--listen-all", action="store_true", help="Listen on all network interfaces (0.0.0.0)")
     parser.add_argument("--synthetic", action="store_true", help="seeded random weights / tokenizers (no checkpoints offline)")
     parser.add_argument("--quantize", "-q", action="store_true", help="FP8 block Linears (Flux.quantize)")
+    parser.add_argument("--gpus", type=int, default=1, help="worker processes, one per GPU; coalesced batches are spread over them")
     args = parser.parse_args(argv)
     host = "0.0.0.0" if args.listen_all else "127.0.0.1"
     if args.listen_all:
@@ -256,7 +329,7 @@ def main(argv=None):
     port = args.port if check_port_available(host, args.port) else find_available_port(host, args.port)
     if port != args.port:
         print(f"\nWarning: Port {args.port} is in use, using port {port} instead")
-    app = get_app(FluxAPI(synthetic=True if args.synthetic else None, quantize=args.quantize))
+    app = get_app(FluxAPI(synthetic=True if args.synthetic else None, quantize=args.quantize, gpus=args.gpus))
     print(f"\nStarting Flux server on {host}:{port}")
     import uvicorn
     uvicorn.Server(uvicorn.Config(app, host=host, port=port, log_level="info")).run()

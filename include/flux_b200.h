@@ -106,9 +106,13 @@ typedef struct fx_conv3x3_args {
                                   GroupNorm groups -- the statistics pass of the GroupNorm that consumes this output
                                   (flux/autoencoder.py:88-94) folded into its producer; reduce with
                                   fx_groupnorm_finalize_blocks.  Needs Cout % 128 == 0, bf16 output. */
+  int32_t upsample2x;          /* 1: out = conv3x3(upsample_nearest(x, 2)) (Upsample, flux/autoencoder.py:121-124) without
+                                  materialising the upsampled tensor: out is [batch][2H][2W][Cout] and W holds the four
+                                  parity-wise 2x2 kernels [4][Cout][4*Cin] (taps that fall on the same source pixel
+                                  pre-summed: ops.upconv_weights).  No resid; Cout % 128 == 0. */
 } fx_conv3x3_args;
 int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream);
-int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout);
+int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout, int32_t upsample2x);
 
 /* ---------------------------------------------------------------- attention
  * Non-causal softmax(q k^T * scale) v over head_dim 128 on tcgen05 (flash-style, online softmax);

@@ -491,6 +491,49 @@ def vae_decode(sd: Dict[str, Tensor], ap: AutoEncoderParams, z: Tensor, mode: Mo
     return _conv(m, h, sd, "decoder.conv_out")
 
 
+def vae_encode(sd: Dict[str, Tensor], ap: AutoEncoderParams, x: Tensor, mode: Mode = FP32,
+               noise: Optional[Tensor] = None) -> Tensor:
+    """AutoEncoder.encode + Encoder.__call__ + DiagonalGaussian (flux/autoencoder.py:347-350, 180-209, 300-309).
+    x NHWC [B, H, W, 3] -> z [B, H/8, W/8, z_channels].  Downsample (flux/autoencoder.py:101-113) = pad (0,1,0,1) on H
+    and W, then a 3x3 stride-2 convolution without padding.  noise=None is eval mode (the mean)."""
+    m = mode
+    h = _conv(m, m.w(x), sd, "encoder.conv_in")
+    n_res = len(ap.ch_mult)
+    for lvl in range(n_res):
+        for blk in range(ap.num_res_blocks):
+            h = _resnet(m, h, sd, f"encoder.down.{lvl}.block.{blk}")
+        if lvl != n_res - 1:
+            key = f"encoder.down.{lvl}.downsample.conv"
+            hp = F.pad(h.permute(0, 3, 1, 2), (0, 1, 0, 1))
+            h = m.r(F.conv2d(hp, m.w(sd[key + ".weight"]), m.w(sd[key + ".bias"]), stride=2).permute(0, 2, 3, 1))
+    h = _resnet(m, h, sd, "encoder.mid.block_1")
+    h = _attn_block(m, h, sd, "encoder.mid.attn_1")
+    h = _resnet(m, h, sd, "encoder.mid.block_2")
+    h = m.r(silu(_group_norm(m, h, sd, "encoder.norm_out")))
+    h = _conv(m, h, sd, "encoder.conv_out")
+    mean, logvar = torch.chunk(h, 2, dim=-1)
+    z = mean if noise is None else m.r(mean + m.r(m.r(torch.exp(m.r(0.5 * logvar))) * m.w(noise)))
+    return m.r(ap.scale_factor * m.r(z - ap.shift_factor))
+
+
+def add_noise(m: Mode, x: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """flux/sampler.py:47-54."""
+    t = t.reshape([-1] + [1] * (x.ndim - 1))
+    return m.r(m.r(x * m.r(1 - t)) + m.r(t * noise))
+
+
+def training_loss(sd, p: FluxParams, x_0_nhwc: Tensor, t5_features: Tensor, clip_features: Tensor, guidance: Tensor,
+                  t: Tensor, eps: Tensor, mode: Mode = FP32) -> Tensor:
+    """FluxPipeline.training_loss (flux/flux.py:195-226) with the two random draws (t, eps) supplied by the caller:
+    mean((flow(x_t) + x_0 - eps)^2), x_t = add_noise(x_0, t, eps).  t is a bf16 tensor like the pipeline's dtype."""
+    m = mode
+    x_0, x_ids = prepare_latent_images(m.w(x_0_nhwc))
+    txt_ids = torch.zeros(t5_features.shape[:-1] + (3,), dtype=torch.int32)
+    x_t = add_noise(m, x_0, m.w(t), m.w(eps))
+    pred = flux_forward(sd, p, x_t, x_ids, m.w(t5_features), txt_ids, t, m.w(clip_features), guidance, mode=m)
+    return m.r(m.r(m.r(pred + x_0) - m.w(eps)).square()).mean()
+
+
 def decode(sd, ap: AutoEncoderParams, x: Tensor, latent_size: Tuple[int, int], mode: Mode = FP32) -> Tensor:
     """FluxPipeline.decode (flux/flux.py:157-162) -> [k, 8h, 8w, 3] in [0, 1]."""
     m = mode

@@ -209,6 +209,41 @@ def golden_ae():
              image=npy(img), image_u8=npy(u8))
 
 
+def golden_encoder_and_loss():
+    """AutoEncoder.encode (flux/autoencoder.py:347-350, eval mode: DiagonalGaussian returns the mean) and
+    FluxPipeline.training_loss (flux/flux.py:195-226) with its two random draws pinned (t, eps are stored)."""
+    ap = specs.AutoEncoderParams(**SMALL_AE)
+    sd = synthetic.synthetic_state_dict(specs.ae_decoder_manifest(ap) + specs.ae_encoder_manifest(ap))
+    ae = AutoEncoder(RefAEParams(**SMALL_AE))
+    ae.load_weights(list(ae.sanitize(f32(sd)).items()))
+    ae.eval()
+    g = torch.Generator().manual_seed(21)
+    x = mx.array((torch.rand((2, 32, 48, 3), generator=g) * 2 - 1).to(torch.bfloat16).to(torch.float32))
+    z = ae.encode(x)
+    np.savez(os.path.join(OUT, "ae_encode.npz"), config=json.dumps(SMALL_AE), weights_crc=synthetic.state_dict_checksum(sd),
+             image=npy(x), z=npy(z))
+    # training loss on the small dev model (guidance embedded), conditioning and draws from a seeded generator
+    model, fsd = build_flow(True)
+    pipe = ref.FluxPipeline.__new__(ref.FluxPipeline)
+    pipe.flow, pipe.dtype, pipe.sampler = model, mx.float32, FluxSampler("flux-dev")
+    B, h, w, S = 2, 8, 12, 16
+    x0 = mx.array(torch.randn((B, h, w, 16), generator=g).to(torch.bfloat16).to(torch.float32))
+    t5f = mx.array(torch.randn((B, S, SMALL_FLOW["context_in_dim"]), generator=g).to(torch.bfloat16).to(torch.float32))
+    clf = mx.array(torch.randn((B, SMALL_FLOW["vec_in_dim"]), generator=g).to(torch.bfloat16).to(torch.float32))
+    gd = mx.array(torch.full((B,), 3.5))
+    t = mx.array(torch.tensor([0.75, 0.3125]))
+    eps = mx.array(torch.randn((B, h * w // 4, 64), generator=g).to(torch.bfloat16).to(torch.float32))
+    pipe.sampler.random_timesteps = lambda *a, **k: t          # pin the two draws of training_loss
+    real_normal = mx.random.normal
+    mx.random.normal = lambda *a, **k: eps
+    try:
+        loss = pipe.training_loss(x0, t5f, clf, gd)
+    finally:
+        mx.random.normal = real_normal
+    np.savez(os.path.join(OUT, "training_loss.npz"), config=json.dumps(SMALL_FLOW), weights_crc=synthetic.state_dict_checksum(fsd),
+             x0=npy(x0), t5=npy(t5f), clip=npy(clf), guidance=3.5, t=npy(t), eps=npy(eps), loss=float(npy(loss)))
+
+
 def golden_text():
     """T5Encoder (flux/t5.py:227-244) and CLIPTextModel (flux/clip.py:127-154)."""
     t5, t5_sd = build_t5()
@@ -313,6 +348,10 @@ if __name__ == "__main__":
         torch.manual_seed(0)
         golden_lora()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        torch.manual_seed(0)
+        golden_encoder_and_loss()
+        sys.exit(0)
     torch.manual_seed(0)
     golden_schedule()
     golden_patchify()
@@ -321,5 +360,6 @@ if __name__ == "__main__":
     golden_text()
     golden_pipeline()
     golden_lora()
+    golden_encoder_and_loss()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

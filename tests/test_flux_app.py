@@ -158,3 +158,41 @@ def test_gpu_api_matches_direct_pipeline(monkeypatch):
     x_t = list(gen)[-1]
     direct = (pipe.decode(x_t, (8, 12)) * 255).to(torch.uint8).cpu().numpy()   # the reference's per-image conversion
     assert np.array_equal(np.stack(imgs), direct)
+
+
+@pytest.mark.gpu
+def test_gpu_concurrent_requests_are_coalesced_bit_identically(monkeypatch):
+    """Two clients with DIFFERENT prompts and seeds, same shape, at the same time: one coalesced batch (flux_serve.py),
+    every image bit-identical to what its request produces alone."""
+    import threading
+    import flux
+    from flux import specs
+    from helpers import small_configs
+    fcfg, acfg, t5c, clc = small_configs()
+    real = flux.FluxPipeline
+
+    def small(name, **kw):
+        return real(name, flow_params=specs.FluxParams(**fcfg, guidance_embed="dev" in name),
+                    ae_params=specs.AutoEncoderParams(**acfg), t5_config=specs.T5Config(**t5c),
+                    clip_config=specs.CLIPTextModelConfig(**clc), **kw)
+
+    monkeypatch.setattr(flux, "FluxPipeline", small)
+    inst = FluxAPI(synthetic=True)
+    base = {"width": 96, "height": 64, "steps": 2, "model": "schnell"}
+    reqs = [{**base, "prompt": "a red fox", "seed": 5, "batch_size": 2}, {**base, "prompt": "two blue birds", "seed": 9, "batch_size": 3}]
+
+    def fetch(pl):
+        return [np.asarray(i) for i in inst.generate_images(pl["prompt"], model=pl["model"], width=pl["width"], height=pl["height"],
+                                                            steps=pl["steps"], seed=pl["seed"], batch_size=pl["batch_size"], return_pil=True)]
+
+    alone = [fetch(pl) for pl in reqs]                   # one request at a time
+    inst.scheduler.window_s = 0.5                         # make sure both concurrent requests land in one window
+    jobs_before = inst.scheduler.stats["jobs"]
+    together = [None, None]
+    ts = [threading.Thread(target=lambda i=i: together.__setitem__(i, fetch(reqs[i]))) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert inst.scheduler.stats["jobs"] == jobs_before + 1 and inst.scheduler.stats["batches"][-1][1] == 5
+    for a, b in zip(alone, together):
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert not np.array_equal(alone[0][0], alone[1][0])

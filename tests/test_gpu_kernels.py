@@ -199,6 +199,30 @@ def test_conv3x3_groupnorm_partials(B, H, W, Cin, Cout):
         assert torch.allclose(sums[..., 1], (o * o).sum((1, 3)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,W,C,Co", [(2, 8, 16, 128, 128), (1, 13, 21, 256, 256), (1, 32, 32, 512, 512), (2, 5, 40, 64, 256)])
+def test_conv3x3_fused_upsample(B, H, W, C, Co):
+    """fx_conv3x3(upsample2x): conv3x3(upsample_nearest(x, 2)) as four parity-wise 2x2 convolutions of the low-resolution
+    input (ops.upconv_weights) vs the fp32 convolution of the materialised upsampled tensor, vs the unfused kernel pair,
+    and its GroupNorm partial sums; ragged sizes leave partly empty tiles."""
+    x, w = rnd(B, H, W, C, seed=71), rnd(Co, 9 * C, seed=72, scale=(9 * C) ** -0.5)
+    bias = rnd(Co, seed=73, scale=0.5)
+    w4 = ops.upconv_weights(w)
+    assert w4.shape == (4 * Co, 4 * C)
+    up = x.float().repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    ref = F.conv2d(up.permute(0, 3, 1, 2), w.float().view(Co, 3, 3, C).permute(0, 3, 1, 2), bias.float(), padding=1).permute(0, 2, 3, 1)
+    out, part = ops.conv3x3(x, w4, bias, gn_stats=True, upsample=True)
+    assert out.shape == (B, 2 * H, 2 * W, Co)
+    assert rel_l2(out, ref) <= 5e-3, rel_l2(out, ref)
+    assert rel_l2(out, ops.conv3x3(ops.upsample2x(x), w, bias)) <= 5e-3
+    assert torch.equal(out, ops.conv3x3(x, w4, bias, upsample=True))
+    sums = part[0].double().sum(1)
+    o = out.double().view(B, 4 * H * W, 32, Co // 32)
+    assert torch.allclose(sums[..., 0], o.sum((1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(sums[..., 1], (o * o).sum((1, 3)), rtol=1e-4, atol=1e-2)
+    with pytest.raises(ValueError):
+        ops.conv3x3(x, w4, bias, resid=out, upsample=True)     # no residual on the fused upsample path
+
+
 def test_rownorm_wide_rows_block_kernel():
     """D >= 1024 runs one block per row (rownorm_block_kernel): all three modes, D = 1024 / 3072 / 4096 and a D that
     leaves the last vector slot partly empty, strided views, and the e4m3 output against quantize_rows(bf16 output)."""

@@ -239,3 +239,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["vs_baseline"] is None and d["higher_is_better"] is True and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_upconv_weights_reproduce_conv_of_upsampled_image():
+    """ops.upconv_weights (host math of the fused Upsample convolution, flux/autoencoder.py:121-124): the four parity-wise
+    2x2 kernels applied to the LOW-resolution image equal conv3x3(upsample_nearest(x, 2)), borders included (fp32, CPU)."""
+    import torch.nn.functional as F
+    from flux.ops import upconv_weights
+    g = torch.Generator().manual_seed(3)
+    B, H, W, C, Co = 2, 5, 7, 4, 6
+    x = torch.randn(B, H, W, C, generator=g)
+    w = torch.randn(Co, 9 * C, generator=g)
+    up = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    ref = F.conv2d(up.permute(0, 3, 1, 2), w.view(Co, 3, 3, C).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    w4 = upconv_weights(w).view(4, Co, 2, 2, C)
+    out = torch.zeros(B, 2 * H, 2 * W, Co)
+    xp = F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1))                         # zero ring: source pixel -1 and H / W
+    for py in (0, 1):
+        for px in (0, 1):
+            k = w4[2 * py + px].permute(0, 3, 1, 2)                          # [Co, C, 2, 2]
+            y = F.conv2d(xp, k)                                              # valid conv over the padded image: (H+1) x (W+1)
+            out[:, py::2, px::2] = y[:, :, py:py + H, px:px + W].permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)

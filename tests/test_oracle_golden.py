@@ -80,6 +80,27 @@ def test_ae_decode():
     assert (np.abs(u8.astype(int) - g["image_u8"].astype(int)) <= 1).all()
 
 
+def test_ae_encode_and_training_loss():
+    """N4: AutoEncoder.encode (flux/autoencoder.py:347-350) and FluxPipeline.training_loss (flux/flux.py:195-226) as
+    the reference's own code computed them over the shim (t and eps of the loss are stored in the fixture)."""
+    g = load("ae_encode.npz")
+    ap = specs.AutoEncoderParams(**json.loads(str(g["config"])))
+    sd = synthetic.synthetic_state_dict(specs.ae_decoder_manifest(ap) + specs.ae_encoder_manifest(ap))
+    assert synthetic.state_dict_checksum(sd) == int(g["weights_crc"])
+    oap = O.AutoEncoderParams(**json.loads(str(g["config"])))
+    z = O.vae_encode({k: v.float() for k, v in sd.items()}, oap, torch.from_numpy(g["image"]))
+    close(z, g["z"], rtol=1e-4, atol=1e-4)
+    g = load("training_loss.npz")
+    cfg = json.loads(str(g["config"]))
+    fsd = synthetic.synthetic_state_dict(specs.flow_manifest(specs.FluxParams(**cfg, guidance_embed=True)))
+    assert synthetic.state_dict_checksum(fsd) == int(g["weights_crc"])
+    B = g["x0"].shape[0]
+    loss = O.training_loss({k: v.float() for k, v in fsd.items()}, O.FluxParams(**cfg, guidance_embed=True),
+                           torch.from_numpy(g["x0"]), torch.from_numpy(g["t5"]), torch.from_numpy(g["clip"]),
+                           torch.full((B,), float(g["guidance"])), torch.from_numpy(g["t"]), torch.from_numpy(g["eps"]))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+
+
 def test_text_encoders():
     g = load("text_encoders.npz")
     t5c = json.loads(str(g["t5_config"]))
