@@ -572,19 +572,53 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 // transposition buffer -- it is full of the next item's tiles -- and gets 16 KB of its own).
 // Barrier phases are tracked with running counters (n = tile steps so far), so any kv_tiles parity works.
 // ------------------------------------------------------------------------------------------
+// F8 (--quantize): q, k, v are e4m3 (written by the FP8 QKV epilogue) and P is handed to the P.V product as e4m3:
+// both products run on tcgen05.mma.kind::f8f6f4 (K = 32 per instruction: 4 instead of 8 MMAs per 128 x 128 x 128
+// product), a tile is 16 KB (ONE 128-byte-wide swizzle atom: 128 e4m3 per row) and P takes 32 TMEM columns.  The per-tile
+// dependency loop of a query tile is  softmax -> P.V -> Q K^T  (S and P alias in TMEM), so halving the tensor time of
+// the two products shortens the loop itself, not just the tensor pipe's share.  P is scaled by 2^P_SHIFT before the
+// conversion (e4m3 resolves 2^-9 .. 448; the row sum l is accumulated from the same scaled fp32 values, so O / l is
+// unaffected) and the lazy running maximum may lag by at most 2^LAZY: P_SHIFT + LAZY <= 8 keeps every p representable.
+template <bool F8>
 struct AttnPCfg {
-  static constexpr int KV_STAGES = 4;
+  static constexpr int TILE_BYTES = F8 ? ATT_TILE_BYTES / 2 : ATT_TILE_BYTES;
+  static constexpr int KV_STAGES = F8 ? 8 : 4;
   static constexpr int Q_OFF = 0;
-  static constexpr int KV_OFF = 2 * ATT_TILE_BYTES;
-  static constexpr int ST_OFF = KV_OFF + KV_STAGES * ATT_TILE_BYTES;  // 8 warps x 2 KB store transposition buffers
+  static constexpr int KV_OFF = 2 * TILE_BYTES;
+  static constexpr int ST_OFF = KV_OFF + KV_STAGES * TILE_BYTES;  // 8 warps x 2 KB store transposition buffers
   static constexpr int BAR_OFF = ST_OFF + 8 * 2048;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
 };
+constexpr float ATT_F8_P_SHIFT = 4.0f, ATT_F8_LAZY = 4.0f;
 
+// four fp32 -> four e4m3 bytes (round to nearest, saturating), element 0 in the low byte
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  return uint32_t(lo) | (uint32_t(hi) << 16);
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// A (= P, e4m3) from TMEM x B (= V, e4m3, shared memory): kind::f8f6f4
+__device__ __forceinline__ void umma_ts_f8(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool F8>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
              const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, const int q_blocks, const int items) {
-  using Cfg = AttnPCfg;
+  using Cfg = AttnPCfg<F8>;
+  constexpr int TILE = Cfg::TILE_BYTES;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -642,48 +676,66 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           const int qb = w % q_blocks, bh = w / q_blocks;
           const int q0 = qb * 256;
           mbar_wait(q_empty, (it & 1) ^ 1);  // the previous item's Q K^T products are done with the Q buffer
-          mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-          for (int i = 0; i < 2; ++i)
-            for (int hf = 0; hf < 2; ++hf)
-              tma_load_3d(smem + Cfg::Q_OFF + i * ATT_TILE_BYTES + hf * 16384, &tmap_q, q_full, hf * 64, q0 + i * 128, bh);
+          mbar_arrive_expect_tx(q_full, 2 * TILE);
+          for (int i = 0; i < 2; ++i) {
+            if (F8) {  // one 128-byte-wide atom per tile
+              tma_load_3d(smem + Cfg::Q_OFF + i * TILE, &tmap_q, q_full, 0, q0 + i * 128, bh);
+            } else {
+              for (int hf = 0; hf < 2; ++hf)
+                tma_load_3d(smem + Cfg::Q_OFF + i * TILE + hf * 16384, &tmap_q, q_full, hf * 64, q0 + i * 128, bh);
+            }
+          }
           for (int t = 0; t < 2 * T; ++t) {
             const CUtensorMap* m = (t & 1) ? &tmap_v : &tmap_k;
             const int row = (t >> 1) * 128;
             mbar_wait(&kv_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&kv_full[stage], ATT_TILE_BYTES);
-            uint8_t* dst = smem + Cfg::KV_OFF + stage * ATT_TILE_BYTES;
+            mbar_arrive_expect_tx(&kv_full[stage], TILE);
+            uint8_t* dst = smem + Cfg::KV_OFF + stage * TILE;
             tma_load_3d(dst, m, &kv_full[stage], 0, row, bh);
-            tma_load_3d(dst + 16384, m, &kv_full[stage], 64, row, bh);
+            if (!F8) tma_load_3d(dst + 16384, m, &kv_full[stage], 64, row, bh);
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
       }
     } else if (warp == ATT_WARP_MMA) {
       // ---------------- MMA issuer (whole warp, warp-uniform control flow, one elected lane issues: see attn_kernel)
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
+      constexpr uint32_t idesc_qk = F8 ? make_idesc_f8(128, 128) : make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = F8 ? (make_idesc_f8(128, 128) | (1u << 16)) : make_idesc_bf16(128, 128, 0, 1);  // B (= V) is MN-major
       const uint32_t q_lo = (smem_u32(smem + Cfg::Q_OFF) >> 4) | (1u << 16);
       const uint32_t k_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1u << 16);
       const uint32_t v_lo0 = (smem_u32(smem + Cfg::KV_OFF) >> 4) | (1024u << 16);
-      constexpr uint32_t TILE16 = ATT_TILE_BYTES >> 4;
+      constexpr uint32_t TILE16 = TILE >> 4;
       int stage = 0;
       uint32_t phase = 0;
       uint32_t n = 0;   // tile steps so far (parity of the s_full / p_full phases)
       uint32_t it = 0;  // items so far (parity of q_full / o_full)
       auto issue_qk = [&](int i, int kslot) {
         const uint32_t a_lo = q_lo + i * TILE16, b_lo = k_lo0 + kslot * TILE16;
+        if (F8) {  // 4 x (K = 32 e4m3 = 32 bytes of the 128-byte rows)
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;
-          umma_ss(tmem + i * 128, make_desc(a_lo + off, kDescHiSw128), make_desc(b_lo + off, kDescHiSw128), idesc_qk, ks != 0);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss_f8(tmem + i * 128, make_desc(a_lo + ks * 2, kDescHiSw128), make_desc(b_lo + ks * 2, kDescHiSw128), idesc_qk, ks != 0);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;
+            umma_ss(tmem + i * 128, make_desc(a_lo + off, kDescHiSw128), make_desc(b_lo + off, kDescHiSw128), idesc_qk, ks != 0);
+          }
         }
       };
       auto issue_pv = [&](int i, int vslot, bool acc, int hf) {
         const uint32_t b_lo = v_lo0 + vslot * TILE16;
+        if (F8) {  // a 64-key half = 2 x (K = 32 keys): P columns ks * 8, V rows ks * 32 (4096 B)
 #pragma unroll
-        for (int ks = hf * 4; ks < hf * 4 + 4; ++ks)
-          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, make_desc(b_lo + ks * 128, kDescHiSw128), idesc_pv,
-                  (acc || ks != 0) ? 1u : 0u);
+          for (int ks = hf * 2; ks < hf * 2 + 2; ++ks)
+            umma_ts_f8(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, make_desc(b_lo + ks * 256, kDescHiSw128), idesc_pv,
+                       (acc || ks != 0) ? 1u : 0u);
+        } else {
+#pragma unroll
+          for (int ks = hf * 4; ks < hf * 4 + 4; ++ks)
+            umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, make_desc(b_lo + ks * 128, kDescHiSw128), idesc_pv,
+                    (acc || ks != 0) ? 1u : 0u);
+        }
       };
       for (int w = blockIdx.x; w < items; w += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
@@ -797,11 +849,19 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             }
             dst[e] = __float_as_uint(p0);
             dst[e + 1] = __float_as_uint(p1);
-            pk[e >> 1] = pack_bf16(p0, p1);
+            if (!F8) pk[e >> 1] = pack_bf16(p0, p1);
+          }
+          if (F8) {  // 32 probabilities -> 8 words of four e4m3
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              pk[e >> 2] = pack_e4m3x4(__uint_as_float(dst[e]), __uint_as_float(dst[e + 1]), __uint_as_float(dst[e + 2]),
+                                       __uint_as_float(dst[e + 3]));
           }
         };
+        // F8: p = 2^(s - m_run + P_SHIFT); the running maximum may lag the true one by at most 2^LAZY
+        constexpr float P_SHIFT = F8 ? ATT_F8_P_SHIFT : 0.0f, LAZY = F8 ? ATT_F8_LAZY : 8.0f;
         // speculative first chunk against the lazy running max (see attn_kernel)
-        uint64_t nm2 = pack2(-m_run, -m_run);
+        uint64_t nm2 = pack2(P_SHIFT - m_run, P_SHIFT - m_run);
         uint32_t pa[32], pk0[16];
         exp_chunk(0, pa, pk0, nm2);
         float mx = fmaxf(__uint_as_float(sv[0]), __uint_as_float(sv[1]));
@@ -813,7 +873,7 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         }
         mx = fmaxf(mx, mxb);
         const float m_new = fmaxf(m_run, mx * sl2);
-        const bool need = (m_new - m_run) > 8.0f;
+        const bool need = (m_new - m_run) > LAZY;
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? fast_exp2(m_run - m_new) : 1.0f;
           if (need) {
@@ -833,7 +893,7 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
             }
             tmem_st_wait();
           }
-          nm2 = pack2(-m_run, -m_run);
+          nm2 = pack2(P_SHIFT - m_run, P_SHIFT - m_run);
           exp_chunk(0, pa, pk0, nm2);
         }
 #pragma unroll
@@ -847,7 +907,8 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           } else {
             exp_chunk(c, sv + c * 32, pk, nm2);
           }
-          tmem_st_x16(s_addr + c * 16, pk);
+          if (F8) tmem_st_x8(s_addr + c * 8, pk);
+          else tmem_st_x16(s_addr + c * 16, pk);
           if (c & 1) {  // a 64-key half of P is complete: hand it to the MMA warp
             tmem_st_wait();
             tc_fence_before();
@@ -1420,24 +1481,33 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out; p.out_bs = a->out_bs;
   CUtensorMap tq, tk, tv;
+  const uint64_t esz = a->fp8 ? 1 : 2;  // fp8: e4m3 q / k / v, one 128-byte row per token and head
   const uint64_t dims[3] = {128, (uint64_t)a->seq, (uint64_t)a->batch * a->heads};
-  const uint64_t strides[2] = {256, (uint64_t)a->seq * 256};
-  const uint32_t box[3] = {64, 128, 1};
+  const uint64_t strides[2] = {128 * esz, (uint64_t)a->seq * 128 * esz};
+  const uint32_t box[3] = {a->fp8 ? 128u : 64u, 128, 1};
   int rc;
-  if ((rc = make_tmap_bf16(&tq, a->q, 3, dims, strides, box))) return rc;
-  if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box))) return rc;
-  if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box))) return rc;
-  if (a->variant == 7 || (a->variant == 0 && persistent_default())) {
+  if ((rc = make_tmap_bf16(&tq, a->q, 3, dims, strides, box, a->fp8 != 0))) return rc;
+  if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box, a->fp8 != 0))) return rc;
+  if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box, a->fp8 != 0))) return rc;
+  FX_REQUIRE(!a->fp8 || a->variant == 0 || a->variant == 7, "fx_attention: fp8 operands run on the persistent kernel only (variant 0 / 7)");
+  if (a->variant == 7 || a->fp8 || (a->variant == 0 && persistent_default())) {
     // persistent work loop (attn_pkernel): one CTA per SM over the (q-block, head, batch) items
     static std::once_flag oncep;
     static cudaError_t attrp_err = cudaSuccess;
-    std::call_once(oncep, [&] { attrp_err = cudaFuncSetAttribute(attn_pkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPCfg::SMEM_BYTES); });
+    std::call_once(oncep, [&] {
+      attrp_err = cudaFuncSetAttribute(attn_pkernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPCfg<false>::SMEM_BYTES);
+      if (attrp_err == cudaSuccess)
+        attrp_err = cudaFuncSetAttribute(attn_pkernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPCfg<true>::SMEM_BYTES);
+    });
     if (attrp_err != cudaSuccess) return fail(FX_ERR_CUDA, "attention smem attribute: %s", cudaGetErrorString(attrp_err));
     const int q_blocks = (a->seq + 255) / 256;
     const long long items = (long long)q_blocks * a->heads * a->batch;
     FX_REQUIRE(items < (1ll << 31), "fx_attention: too many work items");
     const int grid = (int)(items < num_sms() ? items : num_sms());
-    attn_pkernel<<<grid, ATT_THREADS, AttnPCfg::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p, q_blocks, (int)items);
+    if (a->fp8)
+      attn_pkernel<true><<<grid, ATT_THREADS, AttnPCfg<true>::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p, q_blocks, (int)items);
+    else
+      attn_pkernel<false><<<grid, ATT_THREADS, AttnPCfg<false>::SMEM_BYTES, (cudaStream_t)stream>>>(tq, tk, tv, p, q_blocks, (int)items);
     return launched("attn_pkernel");
   }
   if (a->variant == 5 || a->variant == 6) {

@@ -107,6 +107,201 @@ __global__ void __launch_bounds__(128, 1) dbg_umma_kernel(const DbgUmmaParams p)
 
 
 // ------------------------------------------------------------------------------------------
+// Byte-operand probe: one CTA, 8-bit / 4-bit operands laid out by hand, one of
+//   kind 0  tcgen05.mma.kind::f8f6f4                         e4m3 x e4m3 (A from shared memory or from TMEM; B K- or MN-major)
+//   kind 1  tcgen05.mma.kind::mxf8f6f4.block_scale           e4m3, one UE8M0 scale per 32 elements of K
+//   kind 2  tcgen05.mma.kind::mxf4nvf4.block_scale.block16   e2m1 (two per byte), one UE4M3 scale per 16 elements (NVFP4)
+//   kind 3  tcgen05.mma.kind::mxf4nvf4.block_scale.block32   e2m1, one UE8M0 scale per 32 elements (MXFP4)
+// Every MMA consumes 32 bytes of K per operand row.  Scale factors are staged the way the block-scaled GEMM stages
+// them: 512-byte atoms of 128 rows x 4 scales in shared memory, byte (r % 32) * 16 + (r / 32) * 4 + s, copied with
+// tcgen05.cp.32x128b.warpx4 into 4 TMEM columns (lane r % 32 of every sub-partition, column r / 32, byte s).
+// ------------------------------------------------------------------------------------------
+struct DbgBsParams {
+  const uint8_t *A, *B, *SFA, *SFB;  // A [128][kbytes]; B [N][kbytes] (or, b_mn_major, [K][N]); SF [rows][nsf]
+  float* D;                          // [128][N]
+  int N, kbytes, kind, a_tmem, b_mn_major, nsf;
+  uint32_t b_lbo, b_sbo, b_kstep, cp_lbo, cp_sbo;
+};
+__device__ __forceinline__ uint64_t make_smem_desc_plain(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;  // no swizzle (layout type 0), descriptor version 1
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  return d;
+}
+__device__ __forceinline__ void tc_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// block-scaled instruction descriptor (cute::UMMA::InstrDescriptorBlockScaled bit layout)
+__device__ __forceinline__ uint32_t make_idesc_bs(int M, int N, int ab_fmt, int scale_fmt, int b_major, int a_sf_id, int b_sf_id) {
+  return (uint32_t(b_sf_id) << 4) | (uint32_t(ab_fmt) << 7) | (uint32_t(ab_fmt) << 10) | (uint32_t(b_major) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(scale_fmt) << 23) | (uint32_t(M >> 4) << 24) | (uint32_t(a_sf_id) << 29);
+}
+template <int KIND>
+__device__ __forceinline__ void umma_bs(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc, uint32_t sfa, uint32_t sfb) {
+  if (KIND == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d), "l"(ad), "l"(bd),
+                 "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+  else if (KIND == 2)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d), "l"(ad),
+                 "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d), "l"(ad),
+                 "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+}
+__device__ __forceinline__ void umma_ts_f8(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1) dbg_bs_kernel(const DbgBsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int atoms = p.kbytes / 128;                 // 128-byte K atoms per row
+  uint8_t* sa = smem;                               // atoms x [128 rows x 128 B]
+  uint8_t* sb = sa + atoms * 16384;                 // K-major: atoms x [N rows x 128 B]; MN-major: [K rows x 128 B]
+  uint8_t* ssfa = sb + (p.b_mn_major ? p.kbytes * 128 : atoms * p.N * 128);
+  const int g4n = (p.nsf + 3) / 4, nrb = (p.N + 127) / 128;
+  uint8_t* ssfb = ssfa + g4n * 512;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int idx = tid; idx < 128 * (p.kbytes / 16); idx += 128) {  // A: K-major SW128
+    const int r = idx / (p.kbytes / 16), ch = idx % (p.kbytes / 16);
+    const int at = ch / 8, c = ch % 8;
+    *reinterpret_cast<uint4*>(sa + at * 16384 + r * 128 + ((c ^ (r & 7)) * 16)) =
+        *reinterpret_cast<const uint4*>(p.A + (long long)r * p.kbytes + ch * 16);
+  }
+  if (p.b_mn_major) {  // B [K][N = 128] bytes: one MN atom of 128 B per k-row, chunk ^= (k & 7)
+    for (int idx = tid; idx < p.kbytes * 8; idx += 128) {
+      const int k = idx / 8, c = idx % 8;
+      *reinterpret_cast<uint4*>(sb + k * 128 + ((c ^ (k & 7)) * 16)) = *reinterpret_cast<const uint4*>(p.B + (long long)k * p.N + c * 16);
+    }
+  } else {
+    for (int idx = tid; idx < p.N * (p.kbytes / 16); idx += 128) {
+      const int n = idx / (p.kbytes / 16), ch = idx % (p.kbytes / 16);
+      const int at = ch / 8, c = ch % 8;
+      *reinterpret_cast<uint4*>(sb + at * (p.N * 128) + n * 128 + ((c ^ (n & 7)) * 16)) =
+          *reinterpret_cast<const uint4*>(p.B + (long long)n * p.kbytes + ch * 16);
+    }
+  }
+  if (p.kind != 0) {  // scale-factor atoms
+    for (int idx = tid; idx < 128 * p.nsf; idx += 128) {
+      const int r = idx / p.nsf, s = idx % p.nsf;
+      ssfa[(s / 4) * 512 + (r % 32) * 16 + (r / 32) * 4 + (s % 4)] = p.SFA[(long long)r * p.nsf + s];
+    }
+    for (int idx = tid; idx < nrb * 128 * p.nsf; idx += 128) {
+      const int n = idx / p.nsf, s = idx % p.nsf;
+      const int rb = n / 128, r = n % 128;
+      ssfb[((s / 4) * nrb + rb) * 512 + (r % 32) * 16 + (r / 32) * 4 + (s % 4)] = n < p.N ? p.SFB[(long long)n * p.nsf + s] : 0;
+    }
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  constexpr uint32_t A_COL = 256, SFA_COL = 384, SFB_COL = 448;
+  if (p.a_tmem) {  // row tid -> TMEM lane tid, byte k at column k / 4
+    for (int c = 0; c < p.kbytes / 128; ++c) {
+      uint32_t v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = *reinterpret_cast<const uint32_t*>(p.A + (long long)tid * p.kbytes + c * 128 + e * 4);
+      tmem_st_x32(tmem + lane_base + A_COL + c * 32, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (tid == 0) {
+    const uint32_t a_base = smem_u32(sa), b_base = smem_u32(sb);
+    if (p.kind != 0) {
+      for (int g = 0; g < g4n; ++g) {
+        tc_cp_32x128b_warpx4(tmem + SFA_COL + g * 4, make_smem_desc_plain(smem_u32(ssfa + g * 512), p.cp_lbo, p.cp_sbo));
+        for (int rb = 0; rb < nrb; ++rb)
+          tc_cp_32x128b_warpx4(tmem + SFB_COL + (g * nrb + rb) * 4, make_smem_desc_plain(smem_u32(ssfb + (g * nrb + rb) * 512), p.cp_lbo, p.cp_sbo));
+      }
+    }
+    for (int ks = 0; ks < p.kbytes / 32; ++ks) {
+      const uint64_t ad = make_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+      uint64_t bd;
+      if (p.b_mn_major) bd = make_smem_desc_sw128(b_base + ks * p.b_kstep, p.b_lbo, p.b_sbo);
+      else bd = make_smem_desc_sw128(b_base + (ks >> 2) * (p.N * 128) + (ks & 3) * 32, 16, 1024);
+      const uint32_t acc = ks != 0;
+      if (p.kind == 0) {
+        const uint32_t idesc = make_idesc_f8(128, p.N) | (uint32_t(p.b_mn_major) << 16);
+        if (p.a_tmem) umma_ts_f8(tmem, tmem + A_COL + ks * 8, bd, idesc, acc);
+        else umma_ss_f8(tmem, ad, bd, idesc, acc);
+      } else if (p.kind == 1) {  // one scale per MMA: byte ks % 4 of the group's columns
+        umma_bs<1>(tmem, ad, bd, make_idesc_bs(128, p.N, 0, 1, 0, ks & 3, ks & 3), acc, tmem + SFA_COL + (ks >> 2) * 4,
+                   tmem + SFB_COL + (ks >> 2) * nrb * 4);
+      } else if (p.kind == 2) {  // four scales per MMA: the whole 32-bit column
+        umma_bs<2>(tmem, ad, bd, make_idesc_bs(128, p.N, 1, 0, 0, 0, 0), acc, tmem + SFA_COL + ks * 4, tmem + SFB_COL + ks * nrb * 4);
+      } else {                   // two scales per MMA: bytes 0-1 or 2-3
+        umma_bs<3>(tmem, ad, bd, make_idesc_bs(128, p.N, 1, 1, 0, (ks & 1) * 2, (ks & 1) * 2), acc, tmem + SFA_COL + (ks >> 1) * 4,
+                   tmem + SFB_COL + (ks >> 1) * nrb * 4);
+      }
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < p.N / 32; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(tmem + lane_base + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) p.D[(long long)tid * p.N + c * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace fx
+
+extern "C" int fx_dbg_bs_tile(const void* A, const void* B, const void* SFA, const void* SFB, float* D, int32_t N, int32_t kbytes,
+                              int32_t kind, int32_t a_tmem, int32_t b_mn_major, int32_t nsf, uint32_t b_lbo, uint32_t b_sbo,
+                              uint32_t b_kstep, uint32_t cp_lbo, uint32_t cp_sbo, fx_stream stream) {
+  FX_REQUIRE(A && B && D && N % 32 == 0 && N >= 32 && N <= 256 && kbytes % 128 == 0 && kbytes >= 128 && kbytes <= 512 && kind >= 0 && kind <= 3,
+             "fx_dbg_bs_tile: bad arguments");
+  FX_REQUIRE(kind == 0 || (SFA && SFB && nsf > 0), "fx_dbg_bs_tile: block-scaled kinds need scale factors");
+  FX_REQUIRE(!b_mn_major || N == 128, "fx_dbg_bs_tile: the MN-major probe is for N = 128");
+  fx::DbgBsParams p{(const uint8_t*)A, (const uint8_t*)B, (const uint8_t*)SFA, (const uint8_t*)SFB, D, N, kbytes, kind, a_tmem, b_mn_major,
+                    nsf, b_lbo, b_sbo, b_kstep, cp_lbo, cp_sbo};
+  const int atoms = kbytes / 128;
+  const int smem = atoms * 16384 + (b_mn_major ? kbytes * 128 : atoms * N * 128) + ((nsf + 3) / 4) * 512 * (1 + (N + 127) / 128) + 2048;
+  static bool attr = false;
+  if (!attr) {
+    FX_CUDA(cudaFuncSetAttribute(fx::dbg_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  fx::dbg_bs_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  return fx::launched("dbg_bs_kernel");
+}
+
+namespace fx {
+
+// ------------------------------------------------------------------------------------------
 // Tensor-pipe pattern micro-benchmark (profiling only): one thread per CTA issues a fixed sequence of
 // 128x128x16 tcgen05.mma -- the attention kernel's QK (A, B from shared memory) and PV (A from TMEM,
 // B MN-major) instructions on the attention kernel's own shared-memory / TMEM layout, without any

@@ -205,6 +205,8 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   p.pe = (const uint32_t*)a->pe;
   p.pe_blocked = a->pe_blocked;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
+  p.qkv_f8 = a->qkv_fp8 ? 1 : 0;
+  FX_REQUIRE(!p.qkv_f8 || (aligned16(a->q) && aligned16(a->k) && aligned16(a->v)), "fx_gemm_qkv: q/k/v must be 16-byte aligned");
   const int ncta = want_ncta(256);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);
   fill_l2_policy(p, esz);

@@ -6,6 +6,8 @@
 // epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each owning half the columns).  smem ring of 128B-swizzled K-major tiles filled by TMA;
 // accumulators double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
+#include <cuda_fp8.h>
+
 #include "sm100.cuh"
 
 namespace fx {
@@ -58,6 +60,7 @@ struct GemmParams {
   const uint32_t* pe;  // [seq_total][64] (cos, sin) bf16 pairs; or, pe_blocked, [seq/32][16 pieces][32 rows][16 B]
   int pe_blocked;      // blocked layout: the 32 rows of a warp read each 16-byte piece as ONE 512-byte coalesced request
   __nv_bfloat16 *q, *k, *v;  // [batch][heads][seq_total][128]
+  int qkv_f8;                // q, k, v are e4m3 bytes in the same [batch][heads][seq_total][128] order (FP8 attention)
   // ---- FP8 mode (F8): A, W are e4m3 with per-row / per-output-channel dequantisation scales,
   //      acc * a_scale[b][row] * w_scale[n] enters the epilogue in place of the raw accumulator
   const float* a_scale;
@@ -706,7 +709,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     }
                   }
                 }
-                store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask, p.stream_out != 0);
+                if (p.qkv_f8) {  // 32 e4m3 bytes of this row: two full 16-byte vectors (rows are 128 bytes apart)
+                  if (valid) {
+                    uint32_t w8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i], f[4 * i + 1]), __NV_SATFINITE, __NV_E4M3);
+                      const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2], f[4 * i + 3]), __NV_SATFINITE, __NV_E4M3);
+                      w8[i] = uint32_t(lo) | (uint32_t(hi) << 16);
+                    }
+                    uint8_t* d8 = reinterpret_cast<uint8_t*>(which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
+                                  (((long long)b * p.heads + head) * p.seq_total + pos) * 128 + c * 32;
+                    *reinterpret_cast<uint4*>(d8) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                    *reinterpret_cast<uint4*>(d8 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                  }
+                } else {
+                  store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask, p.stream_out != 0);
+                }
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];

@@ -32,7 +32,8 @@ class QkvArgs(C.Structure):
                 ("mlp_out", c_vp), ("ld_mlp", c_i64), ("mlp_bs", c_i64), ("rms_eps", c_f32),
                 ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32), ("heads", c_i32),
                 ("seq_total", c_i32), ("seq_off", c_i32),
-                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp), ("pe_blocked", c_i32)]
+                ("fp8", c_i32), ("a_scale", c_vp), ("a_scale_bs", c_i64), ("w_scale", c_vp), ("pe_blocked", c_i32),
+                ("qkv_fp8", c_i32)]
 
 
 class ConvArgs(C.Structure):
@@ -42,7 +43,7 @@ class ConvArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("out", c_vp), ("ld_out", c_i64), ("out_bs", c_i64),
-                ("scale", c_f32), ("batch", c_i32), ("heads", c_i32), ("seq", c_i32), ("variant", c_i32)]
+                ("scale", c_f32), ("batch", c_i32), ("heads", c_i32), ("seq", c_i32), ("variant", c_i32), ("fp8", c_i32)]
 
 
 class AttnSmallArgs(C.Structure):
@@ -108,6 +109,8 @@ DBG_SYMBOLS = {
     "fx_dbg_umma_tile": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, C.c_uint32, C.c_uint32,
                                    C.c_uint32, c_vp]),
     "fx_dbg_mma_pattern": (C.c_int, [c_i32, c_i32, c_vp, c_vp]),
+    "fx_dbg_bs_tile": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, C.c_uint32, C.c_uint32,
+                                 C.c_uint32, C.c_uint32, C.c_uint32, c_vp]),
 }
 _dbg = None
 

@@ -112,6 +112,7 @@ class Flux:
         self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._txt_cache: Optional[tuple] = None
         self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
+        self._q8_attention = False                                  # --quantize: Q K^T and P V in FP8 as well
         self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
         self._lora_pending: Dict[str, torch.Tensor] = {}       # adapter tensors loaded but not yet fused
 
@@ -162,7 +163,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:  # weights changed under a quantised model: requantise
             self._q8 = {}
-            self.quantize()
+            self.quantize(self._q8_attention)
         return self
 
     # ------------------------------------------------------------------ LoRA adapters (txt2image.py:32-39)
@@ -190,7 +191,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:
             self._q8 = {}
-            self.quantize()
+            self.quantize(self._q8_attention)
         return len(deltas)
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
@@ -208,10 +209,13 @@ class Flux:
             keys += [f"single_blocks.{i}.linear1", f"single_blocks.{i}.linear2"]
         return keys
 
-    def quantize(self) -> "Flux":
+    def quantize(self, attention: bool = True) -> "Flux":
         """Quantise the block Linears to FP8 e4m3 with one scale per output channel (fx_quantize_rows) and switch
         forward() to the FP8 tcgen05 path: activations are row-quantised by the producing norm kernel (or one
-        extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16."""
+        extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16.
+        attention=True: the QKV epilogue writes q, k, v as e4m3 and the attention kernel runs Q K^T and P V on
+        kind::f8f6f4 too (P converted to e4m3 with a 2^4 scale; softmax statistics stay fp32)."""
+        self._q8_attention = bool(attention)
         keys = self.quantized_keys()
         total = sum(self._shape(k + ".weight")[0] * self._shape(k + ".weight")[1] for k in keys)
         rows = sum(self._shape(k + ".weight")[0] for k in keys)
@@ -232,6 +236,7 @@ class Flux:
     def dequantize(self) -> "Flux":
         """Back to the bf16 Linears (drops the FP8 copies; the bf16 arena was never modified)."""
         self._q8 = {}
+        self._q8_attention = False
         self._graphs.clear()
         self._ws.clear()
         return self
@@ -274,7 +279,10 @@ class Flux:
             ws = dict(x=e(B, N, D), xm=e(B, N, D), q=e(B, H, N, 128), k=e(B, H, N, 128), v=e(B, H, N, 128),
                       cat=e(B, N, D + M), mod=e(B, self._mod_total), vec=e(B, D), h=e(B, D), h2=e(B, D),
                       pred=e(B, L, self.in_channels))
-            if self._q8:  # FP8 operand buffers + per-row scales
+            if self._q8:  # FP8 operand buffers + per-row scales (+ e4m3 q / k / v for the FP8 attention)
+                if self._q8_attention:
+                    e8 = lambda *s: torch.empty(s, device=dev, dtype=ops.fp8)  # noqa: E731
+                    ws.update(q8=e8(B, H, N, 128), k8=e8(B, H, N, 128), v8=e8(B, H, N, 128))
                 ws.update(xm8=torch.empty((B, N, D), device=dev, dtype=ops.fp8),
                           cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
                           xs=torch.empty((B, N), device=dev, dtype=torch.float32),
@@ -455,6 +463,8 @@ class Flux:
         p = self.params
         D = self.hidden_size
         x, q, k, v, cat = ws["x"], ws["q"], ws["k"], ws["v"], ws["cat"]
+        if self._q8_attention:
+            q, k, v = ws["q8"], ws["k8"], ws["v8"]
         xm, xm8, cat8, xs, cs = ws["xm"], ws["xm8"], ws["cat8"], ws["xs"], ws["cs"]
         for i in range(p.depth):
             pre = f"double_blocks.{i}."

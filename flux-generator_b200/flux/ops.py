@@ -99,7 +99,9 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_s
     """Fused QKV(+MLP-in) projection; q/k/v are [B, H, seq_total, 128]; pe [seq_total, 64, 2] bf16, or the blocked
     layout of block_pe() with pe_blocked=True.  a / w may be float8_e4m3fn with a_scale / w_scale (see gemm)."""
     is8 = a.dtype == fp8
-    _chk(a, fp8 if is8 else bf16), _chk(w, fp8 if is8 else bf16), _chk(q), _chk(k), _chk(v), _chk(pe)
+    out8 = q.dtype == fp8  # e4m3 q / k / v for the FP8 attention (any operand precision of the projection itself)
+    _chk(a, fp8 if is8 else bf16), _chk(w, fp8 if is8 else bf16), _chk(pe)
+    _chk(q, fp8 if out8 else bf16), _chk(k, fp8 if out8 else bf16), _chk(v, fp8 if out8 else bf16)
     B, R, K, lda, abs_ = _as3(a)
     H, seq_total = q.shape[1], q.shape[2]
     args = N.QkvArgs()
@@ -115,6 +117,7 @@ def gemm_qkv(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], q_s
     args.batch, args.rows, args.N, args.K = B, R, w.shape[0], K
     args.heads, args.seq_total, args.seq_off = H, seq_total, seq_off
     args.pe_blocked = int(pe_blocked)
+    args.qkv_fp8 = int(out8)
     if is8:
         _fp8_operands(args, a, w, a_scale, w_scale, B, R)
     N.check(N.lib().fx_gemm_qkv(C.byref(args), N.stream()))
@@ -183,8 +186,12 @@ def upconv_weights(w: torch.Tensor) -> torch.Tensor:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
               variant: int = 0) -> torch.Tensor:
-    """q,k,v [B,H,S,128] contiguous; out [B,S,>=H*128] view (head h -> columns h*128..)."""
-    _chk(q), _chk(k), _chk(v), _chk(out)
+    """q,k,v [B,H,S,128] contiguous (bf16, or all three float8_e4m3fn: both products then run in FP8);
+    out [B,S,>=H*128] bf16 view (head h -> columns h*128..)."""
+    is8 = q.dtype == fp8
+    _chk(q, fp8 if is8 else bf16), _chk(k, fp8 if is8 else bf16), _chk(v, fp8 if is8 else bf16), _chk(out)
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise ValueError("attention operands must be contiguous [B, H, S, 128]")
     B, H, S, D = q.shape
     if D != 128:
         raise ValueError("attention kernel is specialised for head_dim 128")
@@ -193,6 +200,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     args.q, args.k, args.v, args.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     args.ld_out, args.out_bs, args.scale = ldo, obs, scale
     args.batch, args.heads, args.seq, args.variant = B, H, S, variant
+    args.fp8 = int(is8)
     N.check(N.lib().fx_attention(C.byref(args), N.stream()))
     return out
 

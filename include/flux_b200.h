@@ -88,6 +88,9 @@ typedef struct fx_qkv_args {
   /* pe_blocked != 0: `pe` is laid out [ceil(seq_total / 32)][16 pieces][32 rows][16 bytes] (piece = 4 (cos, sin) pairs)
    * so that the 32 rows a warp owns read every piece as one coalesced 512-byte request; needs seq_off % 32 == 0. */
   int32_t pe_blocked;
+  /* qkv_fp8 != 0: q, k, v are written as e4m3 bytes [batch][heads][seq_total][128] (round to nearest, saturating, no
+   * scale: after QK-RMSNorm and RoPE the values are O(1)) -- the operands of fx_attention's fp8 mode */
+  int32_t qkv_fp8;
 } fx_qkv_args;
 int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream);
 
@@ -125,7 +128,10 @@ typedef struct fx_attn_args {
   int32_t batch, heads, seq;
   int32_t variant;             /* 0 = default; 1 = P via shared memory (coupled schedule); 4 = default with
                                   exp-phase turn taking between the softmax warpgroups; 5 / 6 = decoupled schedule with P through shared memory (attn3_kernel), with / without
-                                  turn taking (tests / A-B) */
+                                  turn taking (tests / A-B); 7 = persistent work loop (what 0 runs unless
+                                  FX_ATTN_PERSISTENT=0) */
+  int32_t fp8;                 /* 1: q, k, v are e4m3 [batch][heads][seq][128] bytes (written by fx_gemm_qkv with qkv_fp8);
+                                  both products run in FP8 (P is converted to e4m3), fp32 softmax, bf16 output */
 } fx_attn_args;
 int fx_attention(const fx_attn_args* a, fx_stream stream);
 

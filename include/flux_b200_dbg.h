@@ -27,6 +27,16 @@ int fx_dbg_umma_tile(const void* A, const void* B, float* D, int32_t K, int32_t 
  * kernel's shared-memory / TMEM layout; writes the SM-clock count of CTA 0 to clocks_out[0]. */
 int fx_dbg_mma_pattern(int32_t pattern, int32_t iters, int64_t* clocks_out, fx_stream stream);
 
+/* Byte-operand probe for the 8-bit / 4-bit tensor-core kinds (one CTA, operands laid out by hand, 32 bytes of K per
+ * MMA): kind 0 kind::f8f6f4 (A from shared memory or, a_tmem, from TMEM; B K-major or, b_mn_major, MN-major with the
+ * caller's LBO / SBO / per-MMA byte step), kind 1 kind::mxf8f6f4.block_scale (UE8M0 per 32), kind 2
+ * kind::mxf4nvf4.block_scale.block16 (NVFP4: e2m1, UE4M3 per 16), kind 3 ...block32 (MXFP4).  A [128][kbytes],
+ * B [N][kbytes] (or [K][N]), SFA [128][nsf], SFB [N][nsf] bytes; D float [128][N].  Scale factors travel through
+ * shared-memory atoms + tcgen05.cp.32x128b.warpx4 (descriptor LBO / SBO from the caller). */
+int fx_dbg_bs_tile(const void* A, const void* B, const void* SFA, const void* SFB, float* D, int32_t N, int32_t kbytes,
+                   int32_t kind, int32_t a_tmem, int32_t b_mn_major, int32_t nsf, uint32_t b_lbo, uint32_t b_sbo,
+                   uint32_t b_kstep, uint32_t cp_lbo, uint32_t cp_sbo, fx_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

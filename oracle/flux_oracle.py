@@ -43,10 +43,14 @@ class Mode:
     """fp32: every op in float32.  fp64: float64.  bf16: float32 math, result of every reference
     op rounded to bfloat16 (how an unfused bf16 MLX graph behaves: flux/flux.py:24)."""
 
-    def __init__(self, name: str = "fp32", quantize: bool = False):
+    def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None):
         assert name in ("fp32", "fp64", "bf16")
         self.name = name
         self.dtype = torch.float64 if name == "fp64" else torch.float32
+        # quantize_attention (default: follows `quantize`): restates Flux.quantize(attention=True) -- q, k (after
+        # QK-norm and RoPE) and v are cast to e4m3 without a scale, the softmax numerators are cast to e4m3 after a
+        # 2^4 scale (fx_attention fp8 mode), the row sum and everything else stay fp32
+        self.quantize_attention = quantize if quantize_attention is None else quantize_attention
         # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
         # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
         # e4m3 activations and weights (fx_quantize_rows in include/flux_b200.h), everything else is unchanged.
@@ -223,12 +227,28 @@ def sdpa(m: Mode, q: Tensor, k: Tensor, v: Tensor, scale: float, mask: Optional[
     return m.r(torch.matmul(p, v))
 
 
+def _e4m3(x: Tensor) -> Tensor:
+    return x.to(torch.float32).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).to(x.dtype)
+
+
+def sdpa_fp8(m: Mode, q: Tensor, k: Tensor, v: Tensor, scale: float) -> Tensor:
+    """THIS repo's FP8 attention (fx_attention, fp8 = 1), not a reference function: e4m3 q / k / v, fp32 scores and softmax
+    statistics, numerators exp(s - max) * 2^4 cast to e4m3 for the P V product, the row sum taken from the unrounded
+    numerators.  (The kernel's running maximum may lag the true one by up to 2^4, which moves some roundings by a
+    binade; the tolerance of the tests covers it.)"""
+    q, k, v = _e4m3(q), _e4m3(k), _e4m3(v)
+    s = torch.matmul(q, k.transpose(-1, -2)) * scale
+    e = torch.exp(s - s.amax(dim=-1, keepdim=True))
+    p8 = _e4m3(e * 16.0) / 16.0
+    return m.r(torch.matmul(p8, v) / e.sum(dim=-1, keepdim=True))
+
+
 def attention(m: Mode, q: Tensor, k: Tensor, v: Tensor, pe: Tensor) -> Tensor:
     """flux/layers.py:36-43."""
     B, H, L, D = q.shape
     q = apply_rope(m, q, pe)
     k = apply_rope(m, k, pe)
-    x = sdpa(m, q, k, v, D ** (-0.5))
+    x = sdpa_fp8(m, q, k, v, D ** (-0.5)) if m.quantize_attention else sdpa(m, q, k, v, D ** (-0.5))
     return x.transpose(1, 2).reshape(B, L, -1)
 
 

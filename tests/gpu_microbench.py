@@ -67,7 +67,8 @@ def main(which, sweep=None):
     gate = r(B, D, sc=0.1)
     shift, scale = r(B, D, sc=0.1), r(B, D, sc=0.1)
     f32buf = torch.empty(B, L, M, device=dev, dtype=torch.float32) if 'fc1_f32out' in which else None
-    f8 = any(n.endswith("_f8") for n in which)
+    q8, k8, v8 = (t.to(ops.fp8) for t in (q, k, v)) if "attn_f8" in which else (None, None, None)
+    f8 = any(n.endswith("_f8") and n != "attn_f8" for n in which)
     if f8:  # --quantize operands
         xm8, xs = ops.quantize_rows(xm)
         cat8, cs = ops.quantize_rows(cat)
@@ -86,6 +87,7 @@ def main(which, sweep=None):
         "fc1_plain": (lambda: ops.gemm(xm[:, S:], wfc1, out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "attn": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5), 4.0 * B * H * N * N * 128),
         "attn_p": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=7), 4.0 * B * H * N * N * 128),
+        "attn_f8": (lambda: ops.attention(q8, k8, v8, cat[:, :, :D], 128 ** -0.5), 4.0 * B * H * N * N * 128),
         "attn_seq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=4), 4.0 * B * H * N * N * 128),
         "attn3": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=5), 4.0 * B * H * N * N * 128),
         "attn3_noseq": (lambda: ops.attention(q, k, v, cat[:, :, :D], 128 ** -0.5, variant=6), 4.0 * B * H * N * N * 128),

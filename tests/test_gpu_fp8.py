@@ -153,18 +153,71 @@ def _full_width(quantize):
     return model, sd, args
 
 
+@pytest.mark.parametrize("B,H,S", [(1, 2, 512), (2, 3, 1100), (1, 1, 77), (1, 24, 4352)])
+def test_attention_fp8_vs_fp32_on_the_same_e4m3_operands(B, H, S):
+    """fx_attention fp8 mode (e4m3 q / k / v, e4m3 P, fp32 softmax statistics) against softmax(q k^T / sqrt(128)) v in fp32
+    on the SAME e4m3 operands: what is left is the rounding of P to e4m3 (3 mantissa bits, averaged over the keys) -- stated
+    tolerance rel-L2 <= 4e-2 -- and against the oracle's restatement of the P rounding (sdpa_fp8)."""
+    q, k, v = (rnd(B, H, S, 128, seed=s_).to(ops.fp8) for s_ in (81, 82, 83))
+    out = torch.zeros(B, S, H * 128 + 64, device=dev, dtype=bf)
+    ops.attention(q, k, v, out[:, :, :H * 128], 128 ** -0.5)
+    qf, kf, vf = q.float(), k.float(), v.float()
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, S, -1)
+    e = rel_l2(out[:, :, :H * 128], ref)
+    orc = O.sdpa_fp8(O.FP32, qf.cpu(), kf.cpu(), vf.cpu(), 128 ** -0.5).transpose(1, 2).reshape(B, S, -1) if S <= 1100 else None
+    print(f"fp8 attention B={B} H={H} S={S}: rel-L2 vs fp32 {e:.3e}" + ("" if orc is None else f", vs oracle sdpa_fp8 {rel_l2(out[:, :, :H * 128], orc):.3e}"))
+    assert e <= 4e-2 and out[:, :, H * 128:].abs().max().item() == 0
+    if orc is not None:
+        assert rel_l2(out[:, :, :H * 128], orc) <= 4e-2
+    with pytest.raises(ValueError):  # fp8 operands run on the persistent kernel only
+        ops.attention(q, k, v, out[:, :, :H * 128], 128 ** -0.5, variant=1)
+
+
+def test_gemm_qkv_writes_e4m3_q_k_v():
+    """fx_gemm_qkv with e4m3 q / k / v outputs (the operands of the FP8 attention): the same values as the bf16 outputs,
+    rounded to e4m3 (within one e4m3 step: rel-L2 <= 4e-2), for bf16 and for FP8 projections."""
+    B, R, H, K, off = 2, 200, 3, 256, 32
+    D = H * 128
+    a, w = rnd(B, R, K, seed=11), rnd(3 * D, K, seed=12, scale=K ** -0.5)
+    bias, qs, ks = rnd(3 * D, seed=13, scale=0.1), (1 + rnd(128, seed=14, scale=0.1).float()).to(bf), (1 + rnd(128, seed=15, scale=0.1).float()).to(bf)
+    ang = torch.rand(R + off, 64, generator=torch.Generator().manual_seed(16)) * 6.28
+    pe = torch.stack([torch.cos(ang), torch.sin(ang)], -1).to(bf).to(dev)
+    ref = [torch.zeros(B, H, R + off, 128, device=dev, dtype=bf) for _ in range(3)]
+    ops.gemm_qkv(a, w, bias, qs, ks, pe, *ref, off)
+    got = [torch.zeros(B, H, R + off, 128, device=dev, dtype=ops.fp8) for _ in range(3)]
+    ops.gemm_qkv(a, w, bias, qs, ks, pe, *got, off)
+    for g8, r16 in zip(got, ref):
+        assert rel_l2(g8.float()[:, :, off:], r16[:, :, off:]) <= 4e-2
+        assert g8.view(torch.uint8)[:, :, :off].max().item() == 0          # rows before seq_off untouched
+        step = (g8.float() - r16.float().to(ops.fp8).float()).abs()[:, :, off:]
+        assert (step <= 0.13 * r16.float().abs()[:, :, off:] + 2e-3).all()  # at most one e4m3 step apart
+    qa, sa = ops.quantize_rows(a)
+    qw, sw = ops.quantize_rows(w)
+    got8 = [torch.zeros(B, H, R + off, 128, device=dev, dtype=ops.fp8) for _ in range(3)]
+    ops.gemm_qkv(qa, qw, bias, qs, ks, pe, *got8, off, a_scale=sa, w_scale=sw)
+    for g8, r16 in zip(got8, ref):
+        assert rel_l2(g8.float()[:, :, off:], r16[:, :, off:]) <= 8e-2
+    with pytest.raises(ValueError):
+        ops.gemm_qkv(a, w, bias, qs, ks, pe, got[0], ref[1], ref[2], off)    # q / k / v must agree in dtype
+
+
 def test_flow_fp8_full_width_vs_quantised_oracle():
-    """hidden 3072 / 24 heads, depth 1+1, batch 2: quantised CUDA forward vs the quantised and the plain oracle."""
+    """hidden 3072 / 24 heads, depth 1+1, batch 2: quantised CUDA forward vs the quantised and the plain oracle, with the
+    FP8 attention (the default of Flux.quantize) and without it."""
     model, sd, (img, ids, txt, tids, ts, y, gd) = _full_width(True)
     assert model.quantized and len(model.quantized_keys()) == 2 * 4 + 2
     op = O.FluxParams(depth=1, depth_single_blocks=1, guidance_embed=True)
-    ref_q = O.flux_forward(sd, op, img.float(), ids, txt.float(), tids, ts, y.float(), gd, mode=O.Mode("fp32", quantize=True))
     ref = O.flux_forward(sd, op, img.float(), ids, txt.float(), tids, ts, y.float(), gd)
-    out = model(img.to(dev), ids.to(dev), txt.to(dev), tids.to(dev), ts.to(dev), y.to(dev), gd.to(dev))
-    print("fp8 vs quantised oracle", rel_l2(out, ref_q), cosine(out, ref_q), "| vs fp32 oracle", rel_l2(out, ref), cosine(out, ref),
-          "| oracle fp8 vs fp32", rel_l2(ref_q, ref))
-    assert rel_l2(out, ref_q) <= 2e-2 and cosine(out, ref_q) >= 0.9995
-    assert rel_l2(out, ref) <= 8e-2 and cosine(out, ref) >= 0.997
+    for attn8, tol in ((True, 3e-2), (False, 2e-2)):
+        model.quantize(attention=attn8)
+        ref_q = O.flux_forward(sd, op, img.float(), ids, txt.float(), tids, ts, y.float(), gd,
+                               mode=O.Mode("fp32", quantize=True, quantize_attention=attn8))
+        out = model(img.to(dev), ids.to(dev), txt.to(dev), tids.to(dev), ts.to(dev), y.to(dev), gd.to(dev))
+        print(f"fp8 (attention fp8={attn8}) vs quantised oracle", rel_l2(out, ref_q), cosine(out, ref_q), "| vs fp32 oracle",
+              rel_l2(out, ref), cosine(out, ref), "| oracle fp8 vs fp32", rel_l2(ref_q, ref))
+        assert rel_l2(out, ref_q) <= tol and cosine(out, ref_q) >= 0.9995
+        assert rel_l2(out, ref) <= 8e-2 and cosine(out, ref) >= 0.997
+    model.quantize()
     # graph replay of the quantised forward is bit-identical to eager
     a = [t_.to(dev) for t_ in (img, ids, txt, tids, ts, y, gd)]
     e = model.forward(*a).clone()

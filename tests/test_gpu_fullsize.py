@@ -200,8 +200,10 @@ def test_fp8_full_depth_four_steps(schnell, vae):
             xo = O.euler_step(O.FP32, pred, xo, times[i], times[i + 1])
             lo.append(xo)
         oim = O.decode(ae_sd, O.AutoEncoderParams(), lo[-1], (128, 128))
-    model.quantize()
     try:
+        model.quantize(attention=False)                 # FP8 Linears, bf16 attention
+        l8lin = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
+        model.quantize()                                # + FP8 attention (the default --quantize)
         l8 = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
     finally:
         model.dequantize()
@@ -210,6 +212,7 @@ def test_fp8_full_depth_four_steps(schnell, vae):
     rep = dict(bf16_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l16, lo)],
                fp8_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l8, lo)],
                fp8_vs_bf16_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l8, l16)],
+               fp8_linears_only_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l8lin, lo)],
                bf16_image_mean_abs_255=(im16 - oim).abs().mean().item() * 255,
                fp8_image_mean_abs_255=(im8 - oim).abs().mean().item() * 255,
                fp8_vs_bf16_image_mean_abs_255=(im8 - im16).abs().mean().item() * 255)
