@@ -40,6 +40,7 @@ static void fill_l2_policy(GemmParams& p, int esz) {
   p.ls_group = ls > 0 ? ls : 0;
   (void)esz;
   p.ls_slack = slack < 1 ? 1 : slack;
+  p.dbg_skip_w = env_int("FX_GEMM_DBG_SKIP_W", 0);
 }
 
 static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {

@@ -38,7 +38,7 @@ struct LockstepSlots {
   unsigned int count[LS_RING];
   unsigned int gen[LS_RING];
 };
-__device__ LockstepSlots g_lockstep;
+static __device__ LockstepSlots g_lockstep;  // (static: the header is included by several translation units)
 
 struct GemmParams {
   int batch, rows, N, K;
@@ -85,6 +85,9 @@ struct GemmParams {
   //      conv_line = elements between output image lines of one parity (ldo = elements between its pixels).
   int conv_up;
   long long conv_line;
+  // ---- timing experiment only (FX_GEMM_DBG_SKIP_W=1, wrong results): the W tile load of every other k-block is skipped,
+  //      i.e. 25 % less L2 -> SM traffic at the same MMA work: what sharing operand tiles across CTAs could buy at most
+  int dbg_skip_w;
 };
 
 // (sum, sum of squares) of one 32-column chunk of a warp's 32 output rows for the GS-channel GroupNorm groups it
@@ -394,13 +397,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (NCTA == 2) {
             // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
-            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const bool skip_w = p.dbg_skip_w && (kb & 1);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
             if (CONV) {
               tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + dx, cy + dy, bimg);
             } else {
               tma2_load_3d_hint(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b, p.hint_a);
             }
-            tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
+            if (!skip_w) tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {

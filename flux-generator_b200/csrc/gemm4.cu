@@ -1,0 +1,385 @@
+// NVFP4 (W4A4) GEMM for the K-long projections of the MMDiT under `--quantize 4`, and its activation quantiser.
+//   out = epilogue( (A4 . W4^T) * a_scale[row] * w_scale[col] ),   A4, W4: e2m1 (two per byte, K contiguous) with one
+//   UE4M3 scale per 16 elements of K -- tcgen05.mma.kind::mxf4nvf4.block_scale.block16: the tensor core applies the
+//   block scales itself, from TMEM, at four times the bf16 MAC rate.
+// The honest Blackwell analogue of the reference's 4-bit `nn.quantize(group_size=64)` of the Linear layers
+// (txt2image.py:28-29,79-82): there 4-bit weights are dequantised into a bf16 matmul, here both operands stay 4-bit.
+//
+// Layouts (validated on hardware with tests/gpu_bs_probe.py, profiles/r02_blockscale_probe.txt):
+//   data     [rows][K / 2] bytes, element 2i in the low nibble; a 128-byte row segment = 256 elements = 4 MMAs (K = 64)
+//   scales   512-byte atoms of 128 rows x 4 scales: byte (r % 32) * 16 + (r / 32) * 4 + s.  One tcgen05.cp.32x128b.warpx4
+//            drops an atom into 4 TMEM columns (lane r % 32 of every sub-partition, column r / 32, byte s), which is
+//            where the MMA reads the four scales of its 64 elements of K for row r.
+//            A: atoms [row block of 128][K / 64]; W: atoms [192-row column tile][K / 64][2] (rows 0-127, 128-191 of the tile)
+//   a_scale  fp32 per row, w_scale fp32 per output channel: the second quantisation level (see fx_quantize_rows_fp4)
+// Kernel: one CTA per SM, 128 x 192 tiles (192 so that two accumulators AND two scale-factor slots fit the 512 TMEM
+// columns: 2 x 192 + 2 x 48), 4-stage TMA ring (A 16 KB + W 24 KB + scales 6 KB per stage), warp roles as gemm_kernel.
+#include <cuda_fp4.h>
+#include <cuda_fp8.h>
+
+#include <mutex>
+
+#include "api_common.cuh"
+#include "gemm.cuh"
+#include "tmap.cuh"
+
+namespace fx {
+
+constexpr int G4_BN = 192;
+constexpr int G4_STAGES = 4;
+constexpr int G4_A_BYTES = 128 * 128;           // 128 rows x 256 e2m1
+constexpr int G4_B_BYTES = G4_BN * 128;
+constexpr int G4_SFA_BYTES = 4 * 512;           // 4 K-groups (of 64 elements) x one 128-row atom
+constexpr int G4_SFB_BYTES = 4 * 2 * 512;       // 4 K-groups x two atoms (192 rows)
+constexpr int G4_STAGE_BYTES = G4_A_BYTES + G4_B_BYTES + G4_SFA_BYTES + G4_SFB_BYTES;
+constexpr int G4_EPI_OFF = G4_STAGES * G4_STAGE_BYTES + 256;
+constexpr int G4_STORE_OFF = G4_EPI_OFF + 8 * 384 * 4;
+constexpr int G4_SMEM = G4_STORE_OFF + 8 * 2048 + 1024;
+constexpr int G4_TMEM_SF = 2 * G4_BN;           // scale-factor slots start behind the two accumulators
+constexpr int G4_SF_SLOT = 48;                  // 16 columns of A scales + 32 of W scales per stage
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sf(uint32_t smem_addr) {  // no swizzle, SBO = 128 B (8 rows x 16 B), version 1
+  return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
+}
+__device__ __forceinline__ void tc_cp_sf(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_nvf4(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc, uint32_t sfa, uint32_t sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
+      "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+      : "memory");
+}
+// cute::UMMA::InstrDescriptorBlockScaled: a/b format E2M1 (1) at [7,10) / [10,13), N >> 3 at [17,23), scale format UE4M3 (0)
+// at [23], M >> 4 at [24,29), scale-factor ids 0
+__host__ __device__ constexpr uint32_t make_idesc_nvf4(int M, int N) {
+  return (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+struct Gemm4Params {
+  GemmParams g;              // shapes, raster, generic epilogue (a_scale / w_scale = the second-level scales)
+  const uint8_t* sfa;        // A scale atoms [row blocks][K / 64][512]
+  const uint8_t* sfb;        // W scale atoms [column tiles][K / 64][2][512]
+  int k_groups;              // K / 64
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const Gemm4Params q) {
+  const GemmParams& p = q.g;
+  constexpr int BN = G4_BN, STAGES = G4_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G4_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first_tile = blockIdx.x, tile_stride = gridDim.x;
+
+  if (warp == GEMM_WARP_TMA && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == GEMM_WARP_MMA) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= GEMM_CTRL0 && warp < GEMM_CTRL0 + 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == GEMM_WARP_TMA) {
+      // ================= TMA producer: A tile, W tile, their scale atoms (plain bulk copies: already in atom order)
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
+          int tm, tn;
+          gemm_tile_coords(p, tile, tm, tn);
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * G4_STAGE_BYTES;
+            uint8_t* sb = sa + G4_A_BYTES;
+            uint8_t* ssfa = sb + G4_B_BYTES;
+            uint8_t* ssfb = ssfa + G4_SFA_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], G4_STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * 128, tm * GEMM_BM);
+            tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * 128, tn * BN);
+            bulk_load(ssfa, q.sfa + ((long long)tm * q.k_groups + kb * 4) * 512, G4_SFA_BYTES, &full_bar[stage]);
+            bulk_load(ssfb, q.sfb + ((long long)tn * q.k_groups + kb * 4) * 1024, G4_SFB_BYTES, &full_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == GEMM_WARP_MMA) {
+      // ================= MMA issuer: per stage 12 scale-atom copies into the stage's TMEM slot, then 4 MMAs (K = 64 each)
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_nvf4(GEMM_BM, BN);
+        int stage = 0;
+        uint32_t phase = 0, n = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * G4_STAGE_BYTES);
+            const uint32_t sb = sa + G4_A_BYTES;
+            const uint32_t ssfa = sb + G4_B_BYTES, ssfb = ssfa + G4_SFA_BYTES;
+            // tcgen05.cp and tcgen05.mma execute in issue order: slot (n & 1) was last read by the MMAs of stage n - 2
+            const uint32_t t_sfa = tmem_base + G4_TMEM_SF + (n & 1) * G4_SF_SLOT, t_sfb = t_sfa + 16;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              tc_cp_sf(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
+              tc_cp_sf(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
+              tc_cp_sf(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_nvf4(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
+                        (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
+            tc_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(&tfull_bar[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (the generic epilogue of gemm_kernel in its dequantising form)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int quarter = warp & 3;
+    const int half = (warp - GEMM_EPI0) >> 2;
+    const int r = quarter * 32 + lane;
+    float* sb = reinterpret_cast<float*>(smem + G4_EPI_OFF) + (warp - GEMM_EPI0) * 384;
+    float* sg = sb + 128;
+    float* sw = sb + 256;
+    uint8_t* wst = smem + G4_STORE_OFF + (warp - GEMM_EPI0) * 2048;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int CH = BN / 64, WN = BN / 2;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
+      int tm, tn;
+      gemm_tile_coords(p, tile, tm, tn);
+      const int b = tm / p.tiles_m_per_batch;
+      const int tmb = tm - b * p.tiles_m_per_batch;
+      const long long row = (long long)tmb * GEMM_BM + r;
+      const bool valid = row < p.rows;
+      const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
+      const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+      const int nw0 = tn * BN + half * WN;
+      const long long out_off = (long long)b * p.out_bs + row * p.ldo;
+      const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
+      const bool vec_ok = ((p.ldo | p.ldr) & 7) == 0;
+      __syncwarp();
+      stage_vec(sb, p.bias, nw0, WN, p.N, 0.f, lane);
+      if (p.gate) stage_vec(sg, p.gate + (long long)b * p.gate_bs, nw0, WN, p.N, 1.f, lane);
+      stage_vec_f32(sw, p.w_scale, nw0, WN, p.N, 0.f, lane);
+      const float rs = valid ? __ldg(p.a_scale + (long long)b * p.a_scale_bs + row) : 1.f;
+      const bool rr_ok = p.resid != nullptr && valid && vec_ok && (nw0 + WN <= p.N);
+      uint4 rcur[4], rnxt[4];
+      if (rr_ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rcur[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + nw0 + i * 8);
+      }
+      __syncwarp();
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < CH; ++c) {
+        const int n0 = nw0 + c * 32;
+        if (n0 >= p.N) break;
+        if (rr_ok && c + 1 < CH) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rnxt[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + n0 + 32 + i * 8);
+        }
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_x32(taddr + half * WN + c * 32, v);
+        tmem_ld_wait();
+        {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          epi_generic_chunk<true>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0, vec_ok && (n0 + 32 <= p.N),
+                                  sw + c * 32, rs, wst, lane, vmask, valid);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == GEMM_WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------ NVFP4 row quantiser: one 256-thread block per row
+// x bf16 [rows][K] (K % 64 == 0, K <= 16384) -> e2m1 bytes [rows][K / 2], UE4M3 block scales in atom order, fp32 row scale.
+// Two levels, every step a single IEEE fp32 operation so that the CPU oracle reproduces bytes and scales exactly:
+//   g  = absmax(row) * (1 / 2688)                 (2688 = 6 * 448: the largest block scale then encodes as 448)
+//   sf = e4m3_rn(absmax(block of 16) * (1 / 6) * rcp(g)),   d = float(sf) * g
+//   q  = e2m1_rn_sat(x * rcp(d))   (0 when d == 0);    x ~= q * float(sf) * g      (rcp = correctly rounded 1 / x)
+struct Quant4Params {
+  const __nv_bfloat16* x; long long ldx, x_bs;
+  uint8_t* q;        // [batch * rows][K / 2]
+  uint8_t* sf;       // atoms [ceil(batch * rows / 128)][K / 64][512]
+  float* scale;      // [batch * rows]
+  int batch, rows, K;
+};
+template <int ITERS>  // ITERS = ceil(K / 2048)
+__global__ void __launch_bounds__(256) quantize_rows_fp4_kernel(const Quant4Params p) {
+  __shared__ float s_max[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long m = blockIdx.x;  // flattened row
+  const int b = int(m / p.rows);
+  const long long r = m - (long long)b * p.rows;
+  const __nv_bfloat16* xr = p.x + b * p.x_bs + r * p.ldx;
+  float v[ITERS][8];
+  float bmax[ITERS];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 2048 + tid * 8;
+    uint4 raw = (c < p.K) ? *reinterpret_cast<const uint4*>(xr + c) : make_uint4(0, 0, 0, 0);
+    float2 a0 = unpack_bf16(raw.x), a1 = unpack_bf16(raw.y), a2 = unpack_bf16(raw.z), a3 = unpack_bf16(raw.w);
+    v[i][0] = a0.x; v[i][1] = a0.y; v[i][2] = a1.x; v[i][3] = a1.y; v[i][4] = a2.x; v[i][5] = a2.y; v[i][6] = a3.x; v[i][7] = a3.y;
+    float mx = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(v[i][j]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  // a block of 16 = two neighbouring threads
+    bmax[i] = mx;
+    amax = fmaxf(amax, mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if (lane == 0) s_max[warp] = amax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) amax = fmaxf(amax, s_max[w]);
+  const float g = amax > 0.f ? __fmul_rn(amax, 1.0f / 2688.0f) : 1.0f;
+  const float rg = __frcp_rn(g);
+  if (tid == 0) p.scale[m] = g;
+  const long long rb = m >> 7;
+  const int rr = int(m & 127);
+  uint8_t* sf_row = p.sf + rb * (long long)(p.K / 64) * 512 + (rr & 31) * 16 + (rr >> 5) * 4;
+  uint8_t* qr = p.q + m * (long long)(p.K / 2);
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int c = i * 2048 + tid * 8;
+    if (c >= p.K) continue;
+    const float u = __fmul_rn(__fmul_rn(bmax[i], 1.0f / 6.0f), rg);
+    const __nv_fp8_storage_t sf8 = __nv_cvt_float_to_fp8(u, __NV_SATFINITE, __NV_E4M3);
+    const float d = __fmul_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(sf8, __NV_E4M3))), g);
+    const int j = c >> 4;  // scale index in the row
+    if ((tid & 1) == 0) sf_row[(j >> 2) * 512 + (j & 3)] = sf8;
+    const float rd = d > 0.f ? __frcp_rn(d) : 0.f;
+    uint32_t w = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e += 2)
+      w |= uint32_t(__nv_cvt_float2_to_fp4x2(make_float2(__fmul_rn(v[i][e], rd), __fmul_rn(v[i][e + 1], rd)), __NV_E2M1, cudaRoundNearest))
+           << (4 * e);
+    *reinterpret_cast<uint32_t*>(qr + (c >> 1)) = w;
+  }
+}
+
+}  // namespace fx
+
+using namespace fx;
+
+extern "C" int fx_quantize_rows_fp4(const fx_quant4_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->x && a->q && a->sf && a->scale, "fx_quantize_rows_fp4: null pointer");
+  FX_REQUIRE(a->K > 0 && a->K % 64 == 0 && a->K <= 16384 && a->ldx % 8 == 0 && a->x_bs % 8 == 0,
+             "fx_quantize_rows_fp4: K (%d) must be a multiple of 64 up to 16384, strides multiples of 8 elements", a->K);
+  FX_REQUIRE(aligned16(a->x) && (reinterpret_cast<uintptr_t>(a->q) & 3) == 0, "fx_quantize_rows_fp4: unaligned pointers");
+  if (a->batch <= 0 || a->rows <= 0) return FX_OK;
+  const long long rows = (long long)a->batch * a->rows;
+  FX_REQUIRE(rows < (1ll << 31), "fx_quantize_rows_fp4: too many rows");
+  Quant4Params p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, (uint8_t*)a->q, (uint8_t*)a->sf, a->scale, a->batch, a->rows, a->K};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch ((a->K + 2047) / 2048) {
+#define FX_Q4(I) case I: quantize_rows_fp4_kernel<I><<<(unsigned)rows, 256, 0, st>>>(p); break;
+    FX_Q4(1) FX_Q4(2) FX_Q4(3) FX_Q4(4) FX_Q4(5) FX_Q4(6) FX_Q4(7) FX_Q4(8)
+#undef FX_Q4
+  }
+  return launched("quantize_rows_fp4_kernel");
+}
+
+extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && a->out, "fx_gemm_fp4: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm_fp4: empty problem");
+  FX_REQUIRE(a->K % 256 == 0, "fx_gemm_fp4: K (%d) must be a multiple of 256", a->K);
+  FX_REQUIRE(a->rows % 128 == 0 || a->batch == 1, "fx_gemm_fp4: rows per batch element (%d) must be a multiple of 128", a->rows);
+  FX_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->sfa) && aligned16(a->sfw), "fx_gemm_fp4: operands must be 16-byte aligned");
+  Gemm4Params q{};
+  GemmParams& p = q.g;
+  p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
+  p.k_blocks = a->K / 256;
+  q.k_groups = a->K / 64;
+  q.sfa = (const uint8_t*)a->sfa; q.sfb = (const uint8_t*)a->sfw;
+  p.a_scale = a->a_scale; p.a_scale_bs = a->rows; p.w_scale = a->w_scale;
+  p.bias = (const __nv_bfloat16*)a->bias;
+  p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
+  p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
+  p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
+  p.tiles_m_per_batch = (a->rows + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_m = p.tiles_m_per_batch * a->batch;
+  p.tiles_n = (a->N + G4_BN - 1) / G4_BN;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  p.group_m = p.tiles_m < 8 ? p.tiles_m : 8;
+  p.group_n = 0;
+  p.stream_out = 1;
+  CUtensorMap ta, tw;
+  {  // A: flattened rows [batch * rows][K / 2] bytes (the quantiser writes a compact operand)
+    const uint64_t dims[2] = {(uint64_t)a->K / 2, (uint64_t)a->batch * a->rows};
+    const uint64_t strides[1] = {(uint64_t)a->K / 2};
+    const uint32_t box[2] = {128, GEMM_BM};
+    int rc = make_tmap_bf16(&ta, a->A, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a->K / 2, (uint64_t)a->N};
+    const uint64_t strides[1] = {(uint64_t)a->K / 2};
+    const uint32_t box[2] = {128, G4_BN};
+    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(gemm_nvfp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM); });
+  if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm_fp4 smem attribute: %s", cudaGetErrorString(attr_err));
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  gemm_nvfp4_kernel<<<grid, GEMM_THREADS, G4_SMEM, (cudaStream_t)stream>>>(ta, tw, q);
+  return launched("gemm_nvfp4_kernel");
+}

@@ -63,6 +63,18 @@ class QuantArgs(C.Structure):
                 ("scale", c_vp), ("scale_bs", c_i64), ("batch", c_i32), ("rows", c_i32), ("K", c_i32)]
 
 
+class Quant4Args(C.Structure):
+    _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_bs", c_i64), ("q", c_vp), ("sf", c_vp), ("scale", c_vp),
+                ("batch", c_i32), ("rows", c_i32), ("K", c_i32)]
+
+
+class Gemm4Args(C.Structure):
+    _fields_ = [("A", c_vp), ("sfa", c_vp), ("a_scale", c_vp), ("W", c_vp), ("sfw", c_vp), ("w_scale", c_vp), ("bias", c_vp),
+                ("out", c_vp), ("ldo", c_i64), ("out_bs", c_i64), ("out_f32", c_i32), ("act", c_i32),
+                ("gate", c_vp), ("gate_bs", c_i64), ("resid", c_vp), ("ldr", c_i64), ("resid_bs", c_i64),
+                ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32)]
+
+
 class GemvArgs(C.Structure):
     _fields_ = [("in_", c_vp), ("ld_in", c_i64), ("W", c_vp), ("ldw", c_i64), ("bias", c_vp), ("add", c_vp),
                 ("ld_add", c_i64), ("out", c_vp), ("ld_out", c_i64), ("batch", c_i32), ("N", c_i32), ("K", c_i32),
@@ -77,6 +89,8 @@ SYMBOLS = {
     "fx_check_device": (C.c_int, [C.c_int]),
     "fx_gemm": (C.c_int, [C.POINTER(GemmArgs), c_vp]),
     "fx_gemm_qkv": (C.c_int, [C.POINTER(QkvArgs), c_vp]),
+    "fx_quantize_rows_fp4": (C.c_int, [C.POINTER(Quant4Args), c_vp]),
+    "fx_gemm_fp4": (C.c_int, [C.POINTER(Gemm4Args), c_vp]),
     "fx_conv3x3": (C.c_int, [C.POINTER(ConvArgs), c_vp]),
     "fx_conv3x3_gn_blocks": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "fx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

@@ -113,6 +113,7 @@ class Flux:
         self._txt_cache: Optional[tuple] = None
         self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
         self._q8_attention = False                                  # --quantize: Q K^T and P V in FP8 as well
+        self._q4: Dict[str, tuple] = {}   # --quantize 4: key -> (e2m1 weight, scale atoms, fp32 row scales) of the K-long Linears
         self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
         self._lora_pending: Dict[str, torch.Tensor] = {}       # adapter tensors loaded but not yet fused
 
@@ -163,7 +164,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:  # weights changed under a quantised model: requantise
             self._q8 = {}
-            self.quantize(self._q8_attention)
+            self.quantize(self._q8_attention, 4 if self._q4 else 8)
         return self
 
     # ------------------------------------------------------------------ LoRA adapters (txt2image.py:32-39)
@@ -191,7 +192,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:
             self._q8 = {}
-            self.quantize(self._q8_attention)
+            self.quantize(self._q8_attention, 4 if self._q4 else 8)
         return len(deltas)
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
@@ -209,13 +210,31 @@ class Flux:
             keys += [f"single_blocks.{i}.linear1", f"single_blocks.{i}.linear2"]
         return keys
 
-    def quantize(self, attention: bool = True) -> "Flux":
+    def fp4_keys(self) -> List[str]:
+        """The Linears that run in NVFP4 under quantize(bits=4): the ones that consume the attention | GELU(mlp) buffer
+        (`proj`, `mlp.2`, `linear2`: K = 3072 / 12288 / 15360) -- the operand that needs its own quantisation pass anyway
+        and the K-long products where the 4-bit MAC rate is not hidden behind the epilogue."""
+        p = self.params
+        keys = []
+        for i in range(p.depth):
+            for s in ("img", "txt"):
+                keys += [f"double_blocks.{i}.{s}_attn.proj", f"double_blocks.{i}.{s}_mlp.2"]
+        keys += [f"single_blocks.{i}.linear2" for i in range(p.depth_single_blocks)]
+        return keys
+
+    def quantize(self, attention: bool = True, bits: int = 8) -> "Flux":
         """Quantise the block Linears to FP8 e4m3 with one scale per output channel (fx_quantize_rows) and switch
         forward() to the FP8 tcgen05 path: activations are row-quantised by the producing norm kernel (or one
         extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16.
         attention=True: the QKV epilogue writes q, k, v as e4m3 and the attention kernel runs Q K^T and P V on
-        kind::f8f6f4 too (P converted to e4m3 with a 2^4 scale; softmax statistics stay fp32)."""
+        kind::f8f6f4 too (P converted to e4m3 with a 2^4 scale; softmax statistics stay fp32).
+        bits=4: additionally the Linears of fp4_keys() run as NVFP4 W4A4 (e2m1 + UE4M3 block scales + fp32 row scales,
+        tcgen05.mma.kind::mxf4nvf4.block_scale; csrc/gemm4.cu) -- the analogue of the reference's 4-bit
+        nn.quantize(group_size=64) (txt2image.py:28-29,79-82); everything else stays FP8."""
+        if bits not in (4, 8):
+            raise ValueError("quantize(bits=...) must be 8 or 4")
         self._q8_attention = bool(attention)
+        self._q4 = {k: ops.fp4_weight(self._w(k)) for k in self.fp4_keys()} if bits == 4 else {}
         keys = self.quantized_keys()
         total = sum(self._shape(k + ".weight")[0] * self._shape(k + ".weight")[1] for k in keys)
         rows = sum(self._shape(k + ".weight")[0] for k in keys)
@@ -236,6 +255,7 @@ class Flux:
     def dequantize(self) -> "Flux":
         """Back to the bf16 Linears (drops the FP8 copies; the bf16 arena was never modified)."""
         self._q8 = {}
+        self._q4 = {}
         self._q8_attention = False
         self._graphs.clear()
         self._ws.clear()
@@ -283,6 +303,9 @@ class Flux:
                 if self._q8_attention:
                     e8 = lambda *s: torch.empty(s, device=dev, dtype=ops.fp8)  # noqa: E731
                     ws.update(q8=e8(B, H, N, 128), k8=e8(B, H, N, 128), v8=e8(B, H, N, 128))
+                if self._q4 and N % 128 == 0 and L % 128 == 0 and S % 128 == 0:  # NVFP4 operand of proj / mlp.2 / linear2
+                    u8 = lambda n: torch.empty((n,), device=dev, dtype=torch.uint8)  # noqa: E731
+                    ws.update(a4=(u8(B * N * (D + M) // 2), u8(B * N * (D + M) // 16), torch.empty((B * N,), device=dev, dtype=torch.float32)))
                 ws.update(xm8=torch.empty((B, N, D), device=dev, dtype=ops.fp8),
                           cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
                           xs=torch.empty((B, N), device=dev, dtype=torch.float32),
@@ -483,17 +506,11 @@ class Flux:
                 ak = pre + name + "_attn."
                 mlp = pre + name + "_mlp."
                 xr = x[:, rows]
-                ops.quantize_rows(cat[:, rows, :D], out=cat8[:, rows, :D], out_scale=cs[:, rows])
-                w8, wsc = self._q8[ak + "proj"]
-                ops.gemm(cat8[:, rows, :D], w8, self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xr, out=xr,
-                         a_scale=cs[:, rows], w_scale=wsc)
+                self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
                 ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
                 w8, wsc = self._q8[mlp + "0"]
                 ops.gemm(xm8[:, rows], w8, self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:], a_scale=xs[:, rows], w_scale=wsc)
-                ops.quantize_rows(cat[:, rows, D:], out=cat8[:, rows, D:], out_scale=cs[:, rows])
-                w8, wsc = self._q8[mlp + "2"]
-                ops.gemm(cat8[:, rows, D:], w8, self._b(mlp + "2"), gate=self._mod(ws, mk, 5), resid=xr, out=xr,
-                         a_scale=cs[:, rows], w_scale=wsc)
+                self._cat_gemm(ws, mlp + "2", cat[:, rows, D:], cat8[:, rows, D:], cs[:, rows], self._mod(ws, mk, 5), xr)
         for i in range(p.depth_single_blocks):
             pre = f"single_blocks.{i}."
             mk = pre + "modulation.lin"
@@ -503,9 +520,20 @@ class Flux:
                          self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
                          a_scale=xs, w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
-            ops.quantize_rows(cat, out=cat8, out_scale=cs)
-            w8, wsc = self._q8[pre + "linear2"]
-            ops.gemm(cat8, w8, self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x, a_scale=cs, w_scale=wsc)
+            self._cat_gemm(ws, pre + "linear2", cat, cat8, cs, self._mod(ws, mk, 2), x)
+
+    def _cat_gemm(self, ws: dict, key: str, a: torch.Tensor, a8: torch.Tensor, a8_scale: torch.Tensor, gate: torch.Tensor,
+                  x: torch.Tensor) -> None:
+        """x += gate * Linear_key(a) for the Linears that consume the attention | GELU(mlp) buffer: quantise `a` (one pass),
+        then the FP8 GEMM -- or, under quantize(bits=4) and a row count the NVFP4 kernel tiles (multiples of 128), NVFP4."""
+        if key in self._q4 and "a4" in ws:
+            a4, sfa, sa = ops.quantize_rows_fp4(a, out=ws["a4"])
+            w4, sfw, sw = self._q4[key]
+            ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, a.shape[0], bias=self._b(key), gate=gate, resid=x, out=x)
+            return
+        ops.quantize_rows(a, out=a8, out_scale=a8_scale)
+        w8, wsc = self._q8[key]
+        ops.gemm(a8, w8, self._b(key), gate=gate, resid=x, out=x, a_scale=a8_scale, w_scale=wsc)
 
     def forward_graphed(self, img: torch.Tensor, img_ids: torch.Tensor, txt: torch.Tensor, txt_ids: torch.Tensor,
                         timesteps: torch.Tensor, y: torch.Tensor, guidance: Optional[torch.Tensor] = None,
@@ -526,7 +554,7 @@ class Flux:
         S = txt.shape[1]
         pe, _ = self._pe(txt_ids, img_ids)
         temb = self._txt_in(txt.to(bf16) if txt.dtype != bf16 else txt)
-        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8))
+        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8), bool(self._q4))
         g = self._graphs.get(key)
         if g is None:
             D = self.hidden_size

@@ -271,6 +271,104 @@ def quantize_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None,
     return out, out_scale
 
 
+# ---------------------------------------------------------------------------------------------
+# NVFP4 (W4A4): e2m1 + UE4M3 block scales (per 16) + fp32 row scales  (include/flux_b200.h: fx_quantize_rows_fp4 / fx_gemm_fp4)
+# ---------------------------------------------------------------------------------------------
+def sf_atoms_to_matrix(sf: torch.Tensor, K: int) -> torch.Tensor:
+    """Scale-factor atoms (512 bytes = 128 rows x 4 scales, byte (r % 32) * 16 + (r / 32) * 4 + s; [row block][K / 64]) ->
+    the plain [row blocks * 128, K / 16] byte matrix."""
+    G = K // 64
+    rb = sf.numel() // (G * 512)
+    return sf.view(rb, G, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(rb * 128, G * 4)
+
+
+def sf_matrix_to_atoms(m: torch.Tensor) -> torch.Tensor:
+    """Inverse of sf_atoms_to_matrix: [R (multiple of 128), nsf (multiple of 4)] bytes -> atoms [R / 128][nsf / 4][512]."""
+    R, nsf = m.shape
+    return m.view(R // 128, 4, 32, nsf // 4, 4).permute(0, 3, 2, 1, 4).contiguous().view(R // 128, nsf // 4, 512)
+
+
+def quantize_rows_fp4(x: torch.Tensor, out=None):
+    """x bf16 [B,R,K] | [R,K] -> (q uint8 [rows, K/2], sf uint8 atoms [ceil(rows/128), K/64, 512], scale fp32 [rows]);
+    rows = B*R flattened.  x ~= e2m1 * ue4m3 * scale (two-level NVFP4 quantisation, see the header).
+    out: (q, sf, scale) flat uint8 / uint8 / fp32 buffers to carve the results from (no allocation: hot path);
+    the scale-atom buffer then must not need padding rows (rows % 128 == 0)."""
+    _chk(x)
+    B, R, K, ldx, xbs = _as3(x)
+    rows = B * R
+    if out is not None:
+        if rows % 128:
+            raise ValueError("quantize_rows_fp4(out=...) needs a multiple of 128 rows")
+        q = out[0][:rows * (K // 2)].view(rows, K // 2)
+        sf = out[1][:(rows // 128) * (K // 64) * 512].view(rows // 128, K // 64, 512)
+        scale = out[2][:rows]
+    else:
+        q = torch.empty((rows, K // 2), device=x.device, dtype=torch.uint8)
+        sf = torch.zeros(((rows + 127) // 128, K // 64, 512), device=x.device, dtype=torch.uint8)
+        scale = torch.empty((rows,), device=x.device, dtype=torch.float32)
+    args = N.Quant4Args()
+    args.x, args.ldx, args.x_bs = x.data_ptr(), ldx, xbs
+    args.q, args.sf, args.scale = q.data_ptr(), sf.data_ptr(), scale.data_ptr()
+    args.batch, args.rows, args.K = B, R, K
+    N.check(N.lib().fx_quantize_rows_fp4(C.byref(args), N.stream()))
+    return q, sf, scale
+
+
+FP4_TILE_N = 192  # column tile of the NVFP4 GEMM (csrc/gemm4.cu)
+
+
+def fp4_weight(w: torch.Tensor):
+    """Linear weight bf16 [N, K] -> (w4 uint8 [N, K/2], scale atoms regrouped per 192-row column tile
+    [ceil(N/192), K/64, 2, 512], w_scale fp32 [N]) for gemm_fp4 (done once, at Flux.quantize)."""
+    Nn, K = w.shape
+    q, sf, scale = quantize_rows_fp4(w)
+    m = sf_atoms_to_matrix(sf, K)[:Nn]                                   # [N, K/16]
+    tiles = (Nn + FP4_TILE_N - 1) // FP4_TILE_N
+    pad = torch.zeros((tiles, 256, K // 16), device=w.device, dtype=torch.uint8)
+    full = torch.zeros((tiles * FP4_TILE_N, K // 16), device=w.device, dtype=torch.uint8)
+    full[:Nn] = m
+    pad[:, :FP4_TILE_N] = full.view(tiles, FP4_TILE_N, K // 16)
+    atoms = sf_matrix_to_atoms(pad.view(tiles * 256, K // 16))          # [tiles * 2, K/64, 512]
+    atoms = atoms.view(tiles, 2, K // 64, 512).permute(0, 2, 1, 3).contiguous()
+    return q, atoms, scale
+
+
+def gemm_fp4(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4: torch.Tensor, sfw: torch.Tensor,
+             w_scale: torch.Tensor, batch: int, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             act=None, gate: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+             out_dtype: torch.dtype = bf16) -> torch.Tensor:
+    """out = resid + gate * act((a4 @ w4.T) * a_scale[:, None] * w_scale + bias) on tcgen05 kind::mxf4nvf4.block_scale.
+    a4 / sfa / a_scale from quantize_rows_fp4 (rows = batch * rows_per_batch), w4 / sfw / w_scale from fp4_weight."""
+    _chk(a4, torch.uint8), _chk(w4, torch.uint8), _chk(sfa, torch.uint8), _chk(sfw, torch.uint8)
+    _chk(a_scale, torch.float32), _chk(w_scale, torch.float32)
+    rows_total, kb = a4.shape
+    K, Nn = 2 * kb, w4.shape[0]
+    if w4.shape[1] != kb or rows_total % batch:
+        raise ValueError("fp4 operands do not match")
+    R = rows_total // batch
+    if out is None:
+        out = torch.empty((batch, R, Nn), device=a4.device, dtype=out_dtype)
+    _chk(out, out.dtype)
+    _, _, _, ldo, obs = _as3(out)
+    args = N.Gemm4Args()
+    args.A, args.sfa, args.a_scale = a4.data_ptr(), sfa.data_ptr(), a_scale.data_ptr()
+    args.W, args.sfw, args.w_scale = w4.data_ptr(), sfw.data_ptr(), w_scale.data_ptr()
+    args.bias = N.ptr(bias)
+    args.out, args.ldo, args.out_bs = out.data_ptr(), ldo, obs
+    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    args.act = ACT[act]
+    if gate is not None:
+        _chk(gate)
+        args.gate, args.gate_bs = gate.data_ptr(), (gate.stride(0) if gate.dim() == 2 else 0)
+    if resid is not None:
+        _chk(resid)
+        _, _, _, ldr, rbs = _as3(resid)
+        args.resid, args.ldr, args.resid_bs = resid.data_ptr(), ldr, rbs
+    args.batch, args.rows, args.N, args.K = batch, R, Nn, K
+    N.check(N.lib().fx_gemm_fp4(C.byref(args), N.stream()))
+    return out
+
+
 def gemv(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,
          silu_in: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b] = W @ f(x[b]) + bias (+ add[b]);  x [B,K] (row stride arbitrary), w [N,K]."""

@@ -117,6 +117,39 @@ typedef struct fx_conv3x3_args {
 int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream);
 int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout, int32_t upsample2x);
 
+/* ---------------------------------------------------------------- NVFP4 (W4A4) projections: `--quantize 4`
+ * The Blackwell analogue of the reference's 4-bit `nn.quantize(group_size=64)` of the Linear layers
+ * (txt2image.py:28-29,79-82): e2m1 values (two per byte) with one UE4M3 scale per 16 elements of K, consumed by
+ * tcgen05.mma.kind::mxf4nvf4.block_scale, plus one fp32 scale per row (activations) / output channel (weights).
+ *
+ * fx_quantize_rows_fp4: x bf16 [batch][rows][K] (K % 64 == 0, K <= 16384) ->
+ *   q     [batch * rows][K / 2] bytes, element 2i in the low nibble
+ *   sf    UE4M3 block scales as 512-byte atoms [ceil(batch * rows / 128)][K / 64]: the scale of elements
+ *         [16 j, 16 j + 16) of row m sits in atom (m / 128, j / 4) at byte (m % 32) * 16 + ((m % 128) / 32) * 4 + j % 4
+ *         (the order tcgen05.cp.32x128b.warpx4 expects; the buffer must cover whole 128-row blocks)
+ *   scale fp32 [batch * rows]:  x ~= e2m1 * ue4m3 * scale;  scale = absmax(row) / 2688, ue4m3 = rn(absmax(block) / 6 / scale) */
+typedef struct fx_quant4_args {
+  const void* x; int64_t ldx; int64_t x_bs;
+  void* q; void* sf; float* scale;
+  int32_t batch, rows, K;
+} fx_quant4_args;
+int fx_quantize_rows_fp4(const fx_quant4_args* a, fx_stream stream);
+
+/* out = resid + gate * act((A4 . W4^T) * a_scale[row] * w_scale[col] + bias): A4 / sfa / a_scale as written by
+ * fx_quantize_rows_fp4 for the flattened [batch * rows] activation rows (rows % 128 == 0 unless batch == 1); W4 [N][K / 2]
+ * with its scale atoms regrouped per 192-row column tile, [ceil(N / 192)][K / 64][2][512] (rows 0-127 and 128-191 of the
+ * tile; flux.ops.fp4_weight prepares both from fx_quantize_rows_fp4's output).  K % 256 == 0.  Epilogue fields as fx_gemm_args. */
+typedef struct fx_gemm4_args {
+  const void* A; const void* sfa; const float* a_scale;
+  const void* W; const void* sfw; const float* w_scale;
+  const void* bias;
+  void* out; int64_t ldo; int64_t out_bs; int32_t out_f32; int32_t act;
+  const void* gate; int64_t gate_bs;
+  const void* resid; int64_t ldr; int64_t resid_bs;
+  int32_t batch, rows, N, K;
+} fx_gemm4_args;
+int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream);
+
 /* ---------------------------------------------------------------- attention
  * Non-causal softmax(q k^T * scale) v over head_dim 128 on tcgen05 (flash-style, online softmax);
  * replaces mx.fast.scaled_dot_product_attention + the transpose/reshape at flux/layers.py:41-43.

@@ -43,7 +43,7 @@ class Mode:
     """fp32: every op in float32.  fp64: float64.  bf16: float32 math, result of every reference
     op rounded to bfloat16 (how an unfused bf16 MLX graph behaves: flux/flux.py:24)."""
 
-    def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None):
+    def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None, bits: int = 8):
         assert name in ("fp32", "fp64", "bf16")
         self.name = name
         self.dtype = torch.float64 if name == "fp64" else torch.float32
@@ -51,6 +51,9 @@ class Mode:
         # QK-norm and RoPE) and v are cast to e4m3 without a scale, the softmax numerators are cast to e4m3 after a
         # 2^4 scale (fx_attention fp8 mode), the row sum and everything else stay fp32
         self.quantize_attention = quantize if quantize_attention is None else quantize_attention
+        # bits = 4: restates Flux.quantize(bits=4) -- the Linears matched by FP4_LINEARS see NVFP4 activations and weights
+        # (nvfp4_quant_rows), the other block Linears stay FP8
+        self.bits = bits
         # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
         # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
         # e4m3 activations and weights (fx_quantize_rows in include/flux_b200.h), everything else is unchanged.
@@ -71,6 +74,9 @@ FP32 = Mode("fp32")
 FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|attn\.proj|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
 
 
+FP4_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.proj|mlp\.2)|single_blocks\.\d+\.linear2)$")
+
+
 def fp8_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor]:
     """Row-wise e4m3 quantisation as fx_quantize_rows does it (all in fp32): inv = 448 / absmax, q = e4m3_rn_sat(x * inv),
     dequantisation scale = absmax * (1/448); a zero row gets inv = scale = 1.  Returns (q as float32 values, scale [..., 1])."""
@@ -83,9 +89,53 @@ def fp8_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor]:
     return q, scale
 
 
+E2M1_VALUES = (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0)
+
+
+def e2m1_round(v: Tensor) -> Tensor:
+    """Round to nearest e2m1 value (ties to the even mantissa), saturating at +-6: cvt.rn.satfinite.e2m1x2.f32."""
+    a = v.abs()
+    q = torch.zeros_like(a)
+    q = torch.where(a > 0.25, torch.full_like(a, 0.5), q)
+    q = torch.where(a >= 0.75, torch.full_like(a, 1.0), q)
+    q = torch.where(a > 1.25, torch.full_like(a, 1.5), q)
+    q = torch.where(a >= 1.75, torch.full_like(a, 2.0), q)
+    q = torch.where(a > 2.5, torch.full_like(a, 3.0), q)
+    q = torch.where(a >= 3.5, torch.full_like(a, 4.0), q)
+    q = torch.where(a > 5.0, torch.full_like(a, 6.0), q)
+    return torch.copysign(q, v)
+
+
+def nvfp4_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """THIS repo's NVFP4 quantiser (fx_quantize_rows_fp4), every step one IEEE fp32 operation:
+    g = absmax(row) * (1/2688) (1 for a zero row); per block of 16: sf = e4m3_rn(absmax(block) * (1/6) * rcp(g)), d = sf * g,
+    q = e2m1_rn_sat(x * rcp(d)) (0 where d == 0), rcp = correctly rounded reciprocal.  Returns (q values, sf values
+    [.., K/16], g [.., 1]); x ~= q * sf * g."""
+    x32 = x.to(torch.float32)
+    K = x32.shape[-1]
+    amax = x32.abs().amax(dim=-1, keepdim=True)
+    g = torch.where(amax > 0, amax * torch.tensor(1.0 / 2688.0, dtype=torch.float32), torch.ones_like(amax))
+    xb = x32.reshape(*x32.shape[:-1], K // 16, 16)
+    bmax = xb.abs().amax(dim=-1)
+    one = torch.ones((), dtype=torch.float32)
+    u = (bmax * torch.tensor(1.0 / 6.0, dtype=torch.float32)) * (one / g)
+    sf = u.clamp(max=448.0).to(torch.float8_e4m3fn).to(torch.float32)
+    d = (sf * g).unsqueeze(-1)
+    rd = torch.where(d > 0, one / torch.where(d > 0, d, torch.ones_like(d)), torch.zeros_like(d))
+    q = e2m1_round(xb * rd)
+    return q.reshape(x32.shape), sf, g
+
+
 def _linear(m: Mode, x: Tensor, sd: Dict[str, Tensor], key: str, bias: bool = True) -> Tensor:
     w = m.w(sd[key + ".weight"])
     b = m.w(sd[key + ".bias"]) if bias and (key + ".bias") in sd else None
+    if m.quantize and m.bits == 4 and FP4_LINEARS.match(key):
+        qx, sx, gx = nvfp4_quant_rows(x)
+        qw, sw, gw = nvfp4_quant_rows(w)
+        xd = qx * sx.repeat_interleave(16, dim=-1) * gx
+        wd = qw * sw.repeat_interleave(16, dim=-1) * gw
+        y = F.linear(xd, wd).to(m.dtype)
+        return m.r(y + b if b is not None else y)
     if m.quantize and FP8_LINEARS.match(key):
         xq, xs = fp8_quant_rows(x)
         wq, ws = fp8_quant_rows(w)

@@ -75,6 +75,14 @@ def main(which, sweep=None):
         w1q, w1s = ops.quantize_rows(w1)
         w2q, w2s = ops.quantize_rows(w2)
         wfq, wfs = ops.quantize_rows(wfc1)
+        catm8, cms = ops.quantize_rows(cat[:, S:, D:].contiguous())
+        wf2q, wf2s = ops.quantize_rows(wfc2)
+    f4 = any(n.endswith("_f4") for n in which)
+    if f4:  # --quantize 4 operands (NVFP4)
+        cat4, csf4, cs4 = ops.quantize_rows_fp4(cat)
+        w24, w2sf, w2s4 = ops.fp4_weight(w2)
+        catm4, cmsf4, cms4 = ops.quantize_rows_fp4(cat[:, S:, D:])
+        wf24, wf2sf, wf2s4 = ops.fp4_weight(wfc2)
     tests = {
         "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
         "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
@@ -97,6 +105,10 @@ def main(which, sweep=None):
         "linear2_f8": (lambda: ops.gemm(cat8, w2q, b2, gate=gate, resid=x, out=x, a_scale=cs, w_scale=w2s), 2.0 * B * N * D * (D + M)),
         "fc1_f8": (lambda: ops.gemm(xm8[:, S:], wfq, bfc1, act="gelu_tanh", out=cat[:, S:, D:], a_scale=xs[:, S:], w_scale=wfs),
                    2.0 * B * L * M * D),
+        "linear2_f4": (lambda: ops.gemm_fp4(cat4, csf4, cs4, w24, w2sf, w2s4, B, bias=b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
+        "fc2_f4": (lambda: ops.gemm_fp4(catm4, cmsf4, cms4, wf24, wf2sf, wf2s4, B, bias=b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * M),
+        "quant_cat_f4": (lambda: ops.quantize_rows_fp4(cat), 0.0),
+        "fc2_f8": (lambda: ops.gemm(catm8, wf2q, b2, gate=gate, resid=x[:, S:], out=x[:, S:], a_scale=cms, w_scale=wf2s), 2.0 * B * L * D * M),
         "quant_cat_f8": (lambda: ops.quantize_rows(cat, out=cat8, out_scale=cs), 0.0),
         "rownorm_f8": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm8, out_scale=xs), 0.0),
         "cublas_l1": (lambda: torch.matmul(xm.view(-1, D), w1.T), 2.0 * B * N * (3 * D + M) * D),
@@ -113,7 +125,8 @@ def main(which, sweep=None):
     for name in which or list(tests):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
-        nbytes = {"rownorm": 4 * x.numel(), "rownorm_f8": 3 * x.numel(), "quant_cat_f8": 3 * cat.numel()}.get(name)
+        nbytes = {"rownorm": 4 * x.numel(), "rownorm_f8": 3 * x.numel(), "quant_cat_f8": 3 * cat.numel(),
+                  "quant_cat_f4": 2.5625 * cat.numel()}.get(name)
         extra = f" = {nbytes / ms / 1e6:.0f} GB/s" if nbytes else f" = {tf:.0f} TFLOP/s"
         print(f"{name:10s} {ms:8.3f} ms{extra}{last_clock}", flush=True)
 
