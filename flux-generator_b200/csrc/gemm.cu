@@ -68,18 +68,20 @@ static void fill_tiling(GemmParams& p, int tiles_m_per_batch, int bn) {
   }
 }
 
-template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false>
+template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false, int CL = 1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, NCTA>;
-  auto kern = gemm_kernel<BN, EPI, CONV, NCTA, F8>;
+  auto kern = gemm_kernel<BN, EPI, CONV, NCTA, F8, CL>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
-  const int units = num_sms() / NCTA;  // persistent: one CTA (or CTA pair) per SM (pair)
-  const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA;
+  // persistent: one CTA (or CTA pair) per SM (pair); clusters of two pairs: only 33 clusters of 4 CTAs are co-resident on
+  // the 148 SMs (cudaOccupancyMaxActiveClusters; the GPCs hold 16 / 18 / 20 SMs)
+  const int units = CL == 2 ? 33 : num_sms() / NCTA;
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * NCTA * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -87,7 +89,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.x = NCTA * CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -123,10 +125,25 @@ static int launch_bn(int bn, int ncta, const CUtensorMap& ta, const CUtensorMap&
 
 static int pick_bn(int N) { return N > 128 ? 256 : (N > 64 ? 128 : 64); }
 
+// Clusters of two CTA pairs sharing (multicasting) their W tile (gemm.cuh, CL = 2): FX_GEMM_CL=2 enables them for the wide
+// CTA-pair GEMMs with at least `FX_GEMM_CL_MIN_TILES` row tiles.  Returns 2 and rewrites the raster to super row tiles.
+static int want_cluster(GemmParams& p, int bn, int ncta) {
+  static int cl = env_int("FX_GEMM_CL", 1), min_tiles = env_int("FX_GEMM_CL_MIN_TILES", 16);
+  if (cl != 2 || ncta != 2 || bn != 256 || p.tiles_m < min_tiles) return 1;
+  p.tiles_m_real = p.tiles_m;
+  p.tiles_m = (p.tiles_m + 1) / 2;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  p.group_m = (p.group_m + 1) / 2;
+  if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+  p.ls_group = 0;
+  return 2;
+}
+
 // FP8 (e4m3) operands: only the wide CTA-pair tiles are instantiated (the quantised path covers the big
 // Linear layers of the MMDiT blocks, all N >= 3072)
 template <int EPI>
-static int launch_f8(int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+static int launch_f8(int ncta, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st, int cl = 1) {
+  if (ncta == 2 && cl == 2) return launch<256, EPI, false, 2, true, 2>(ta, tw, p, st);
   if (ncta == 2) return launch<256, EPI, false, 2, true>(ta, tw, p, st);
   return launch<256, EPI, false, 1, true>(ta, tw, p, st);
 }
@@ -134,7 +151,7 @@ static int launch_f8(int ncta, const CUtensorMap& ta, const CUtensorMap& tw, con
 // A [batch][rows][K] and W [N][K] tensor maps; esz = bytes per element (2 bf16, 1 e4m3); the box is always
 // 128 bytes of K by (128 | bn / ncta) rows
 static int make_operand_maps(CUtensorMap* ta, CUtensorMap* tw, const void* A, int64_t lda, int64_t a_bs, const void* W,
-                             int64_t ldw, int batch, int rows, int N, int K, int bn, int ncta, int esz) {
+                             int64_t ldw, int batch, int rows, int N, int K, int bn, int ncta, int esz, int cl = 1) {
   const bool u8 = esz == 1;
   const uint32_t bk = 128 / esz;
   {
@@ -146,7 +163,7 @@ static int make_operand_maps(CUtensorMap* ta, CUtensorMap* tw, const void* A, in
   }
   const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
   const uint64_t strides[1] = {(uint64_t)ldw * esz};
-  const uint32_t box[2] = {bk, (uint32_t)(bn / ncta)};
+  const uint32_t box[2] = {bk, (uint32_t)(bn / ncta / cl)};  // cl = 2: each CTA fetches (and multicasts) a quarter of the tile
   return make_tmap_bf16(tw, W, 2, dims, strides, box, u8);
 }
 
@@ -175,10 +192,12 @@ extern "C" int fx_gemm(const fx_gemm_args* a, fx_stream stream) {
   const int ncta = want_ncta(bn);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), bn);
   fill_l2_policy(p, esz);
+  const int cl = want_cluster(p, bn, ncta);
   CUtensorMap ta, tw;
-  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, bn, ncta, esz);
+  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, bn, ncta, esz, cl);
   if (rc) return rc;
-  if (a->fp8) return launch_f8<EPI_GENERIC>(ncta, ta, tw, p, (cudaStream_t)stream);
+  if (a->fp8) return launch_f8<EPI_GENERIC>(ncta, ta, tw, p, (cudaStream_t)stream, cl);
+  if (cl == 2) return launch<256, EPI_GENERIC, false, 2, false, 2>(ta, tw, p, (cudaStream_t)stream);
   return launch_bn<EPI_GENERIC, false>(bn, ncta, ta, tw, p, (cudaStream_t)stream);
 }
 
@@ -211,10 +230,12 @@ extern "C" int fx_gemm_qkv(const fx_qkv_args* a, fx_stream stream) {
   const int ncta = want_ncta(256);
   fill_tiling(p, (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta), 256);
   fill_l2_policy(p, esz);
+  const int cl = want_cluster(p, 256, ncta);
   CUtensorMap ta, tw;
-  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, 256, ncta, esz);
+  int rc = make_operand_maps(&ta, &tw, a->A, a->lda, a->a_bs, a->W, a->ldw, a->batch, a->rows, a->N, a->K, 256, ncta, esz, cl);
   if (rc) return rc;
-  if (a->fp8) return launch_f8<EPI_QKV>(ncta, ta, tw, p, (cudaStream_t)stream);
+  if (a->fp8) return launch_f8<EPI_QKV>(ncta, ta, tw, p, (cudaStream_t)stream, cl);
+  if (cl == 2) return launch<256, EPI_QKV, false, 2, false, 2>(ta, tw, p, (cudaStream_t)stream);
   if (ncta == 2) return launch<256, EPI_QKV, false, 2>(ta, tw, p, (cudaStream_t)stream);
   return launch<256, EPI_QKV, false>(ta, tw, p, (cudaStream_t)stream);
 }

@@ -88,6 +88,9 @@ struct GemmParams {
   // ---- timing experiment only (FX_GEMM_DBG_SKIP_W=1, wrong results): the W tile load of every other k-block is skipped,
   //      i.e. 25 % less L2 -> SM traffic at the same MMA work: what sharing operand tiles across CTAs could buy at most
   int dbg_skip_w;
+  // ---- CL = 2 (two CTA pairs per cluster): tiles_m counts SUPER row tiles (two row tiles that share their W tile);
+  //      tiles_m_real = the row tiles that exist (the second tile of the last super tile may not)
+  int tiles_m_real;
 };
 
 // (sum, sum of squares) of one 32-column chunk of a warp's 32 output rows for the GS-channel GroupNorm groups it
@@ -296,13 +299,22 @@ __device__ __forceinline__ void stage_vec_f32(float* dst, const float* src, int 
   for (int i = lane; i < n; i += 32) dst[i] = (src != nullptr && n0 + i < limit) ? __ldg(src + n0 + i) : fill;
 }
 
-template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false>
+// CL = 2: a cluster of TWO CTA pairs works on two row tiles of the same column tile.  Their W tile is identical, so
+// each of the four CTAs fetches a quarter of it and TMA-multicasts the quarter to the CTA that holds the same half in the
+// other pair: 25 % fewer bytes leave the L2 per FLOP.  (Measured with FX_GEMM_DBG_SKIP_W: 25 % less L2 -> SM traffic is
+// worth 8-17 % on these GEMMs -- the chip is power-limited and moving operands costs as much as multiplying them;
+// profiles/r02_gemm_l2_traffic_sensitivity.txt.)  The price: a slot of the ring is free only when BOTH pairs have consumed
+// it (empty barriers count two commits), and only 33 clusters of 4 are co-resident on the 148 SMs (132 CTAs).
+template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false, int CL = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
             const GemmParams p) {
   using Cfg = GemmCfg<BN, NCTA>;
-  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
-  const int first_tile = blockIdx.x / NCTA, tile_stride = gridDim.x / NCTA;
+  static_assert(CL == 1 || (NCTA == 2 && !CONV), "pair clusters are for the CTA-pair GEMMs");
+  const uint32_t cl_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = cl_rank & 1u;   // rank inside the CTA pair
+  const int pair_idx = int(cl_rank >> 1);   // which pair of the cluster (CL = 2)
+  const int first_tile = blockIdx.x / (NCTA * CL), tile_stride = gridDim.x / (NCTA * CL);
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -313,7 +325,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   volatile uint32_t* ls_issued = reinterpret_cast<volatile uint32_t*>(smem + STAGES * Cfg::STAGE_BYTES + 192);   // producer -> sync warp
   volatile uint32_t* ls_allowed = ls_issued + 1;                                                               // sync warp -> producer
-  const bool lockstep = (NCTA == 2) && !CONV && p.ls_group > 0 && cta_rank == 0;
+  const bool lockstep = (NCTA == 2) && CL == 1 && !CONV && p.ls_group > 0 && cta_rank == 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,7 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // one tcgen05.commit per pair that reads (or writes into) this CTA's slot
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -362,6 +374,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
         int tm, tn;
         gemm_tile_coords(p, tile, tm, tn);
+        if (CL == 2) tm = 2 * tm + pair_idx;  // (a row tile past the end loads zeros: TMA out-of-bounds fill)
         const int b = tm / p.tiles_m_per_batch;
         const int tmb = tm - b * p.tiles_m_per_batch;
         int cy = 0, cx = 0;
@@ -397,14 +410,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           if (NCTA == 2) {
             // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
-            const bool skip_w = p.dbg_skip_w && (kb & 1);
+            const bool skip_w = CL == 1 && p.dbg_skip_w && (kb & 1);
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], skip_w ? 2 * Cfg::A_BYTES : 2 * Cfg::STAGE_BYTES);
             if (CONV) {
               tma2_load_4d(sa, &tmap_a, &full_bar[stage], c0, cx + dx, cy + dy, bimg);
             } else {
               tma2_load_3d_hint(sa, &tmap_a, &full_bar[stage], kb * KE, tmb * (2 * GEMM_BM) + int(cta_rank) * GEMM_BM, b, p.hint_a);
             }
-            if (!skip_w) tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
+            if (CL == 2) {
+              // this CTA's quarter of the W tile, multicast to the CTA of the other pair that holds the same half
+              tma2_load_2d_mcast(sb + pair_idx * (Cfg::B_BYTES / 2), &tmap_w, &full_bar[stage], kb * KE,
+                                 tn * BN + int(cta_rank) * (BN / 2) + pair_idx * (BN / 4), uint16_t(5u << cta_rank), p.hint_w);
+            } else if (!skip_w) {
+              tma2_load_2d_hint(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN + int(cta_rank) * (BN / 2), p.hint_w);
+            }
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (CONV) {
@@ -483,11 +502,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               else umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          if (NCTA == 2) tc_commit2(&empty_bar[stage]);
+          if (NCTA == 2 && CL == 2) tc_commit2_mask(&empty_bar[stage], 0xF);  // both pairs wait for both pairs
+          else if (NCTA == 2) tc_commit2(&empty_bar[stage]);
           else tc_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
+        if (NCTA == 2 && CL == 2) tc_commit2_mask(&tfull_bar[acc], uint16_t(3u << (2 * pair_idx)));
+        else if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
         else tc_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -509,6 +530,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
       int tm, tn;
       gemm_tile_coords(p, tile, tm, tn);
+      if (CL == 2) tm = 2 * tm + pair_idx;
       const int b = tm / p.tiles_m_per_batch;
       const int tmb = tm - b * p.tiles_m_per_batch;
       bool valid;
@@ -529,7 +551,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       } else {
         row = (long long)tmb * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
-        valid = row < p.rows;
+        valid = row < p.rows && (CL == 1 || tm < p.tiles_m_real);
       }
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);

@@ -276,6 +276,24 @@ __device__ __forceinline__ void umma2_ss_f8(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// W-tile quarter loaded once and written into the same shared-memory offset of every CTA in `mask` (the CTAs of a
+// cluster that hold the same half of the W tile); each destination pair's LEADER barrier is credited with the bytes
+__device__ __forceinline__ void tma2_load_2d_mcast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask,
+                                                   uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+// commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit2_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 // commit that arrives on the mbarrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tc_commit2(uint64_t* bar) {
   asm volatile(

@@ -25,6 +25,8 @@ model = Flux(p, device=dev)
 model.arena.buffer.normal_(0, 0.02)
 if os.environ.get("PROF_QUANT", "0") == "1":  # the --quantize (FP8) path
     model.quantize()
+if os.environ.get("PROF_QUANT", "0") == "4":  # --quantize --quantize-bits 4 (NVFP4 proj / mlp.2 / linear2)
+    model.quantize(bits=4)
 L, S = 4096, 256
 img = torch.randn(B, L, 64, device=dev, dtype=bf)
 txt = torch.randn(B, S, 4096, device=dev, dtype=bf)
@@ -34,7 +36,8 @@ ids[:, :, 1] = torch.arange(L, device=dev) // 64
 ids[:, :, 2] = torch.arange(L, device=dev) % 64
 tids = torch.zeros(B, S, 3, dtype=torch.int32, device=dev)
 ts = torch.full((B,), 0.75, dtype=bf, device=dev)
-model.forward(img, ids, txt, tids, ts, y)
+if os.environ.get("PROF_FLOW", "1") == "1":
+    model.forward(img, ids, txt, tids, ts, y)
 if os.environ.get("PROF_VAE", "1") == "1":
     ae = AutoEncoder(specs.AutoEncoderParams(), device=dev)
     ae.arena.buffer.normal_(0, 0.02)
