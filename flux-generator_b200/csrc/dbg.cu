@@ -277,6 +277,109 @@ __global__ void __launch_bounds__(128, 1) dbg_bs_kernel(const DbgBsParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same probe for a CTA PAIR (cta_group::2): M = 256 (128 rows per CTA), the W tile split over the two CTAs (N / 2 rows
+// each), NVFP4 (kind 2).  Question it answers: where do tcgen05.cp.cta_group::2 and the block-scaled MMA of a pair take
+// their scale factors from?  sfb_mode 0: every CTA stages the scale atoms of ALL N columns in its own shared memory and the
+// leader's tcgen05.cp.cta_group::2 copies, in each CTA, from that CTA's shared memory into that CTA's TMEM (hypothesis);
+// sfb_mode 1: every CTA stages only the atoms of its own half of the W rows.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_cp2_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma2_nvf4(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc, uint32_t sfa, uint32_t sfb) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d), "l"(ad),
+               "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+}
+struct DbgBs2Params {
+  const uint8_t *A, *B, *SFA, *SFB;  // A [256][kbytes]; B [N][kbytes]; SFA [256][nsf]; SFB [N][nsf]
+  float* D;                          // [256][N]
+  int N, kbytes, nsf, sfb_mode;
+};
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) dbg_bs2_kernel(const DbgBs2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t rank = cluster_ctarank();
+  const int atoms = p.kbytes / 128, NH = p.N / 2;
+  uint8_t* sa = smem;                                   // atoms x [128 rows x 128 B]: rows 128 * rank ...
+  uint8_t* sb = sa + atoms * 16384;                     // atoms x [NH rows x 128 B]: W rows NH * rank ...
+  uint8_t* ssfa = sb + atoms * NH * 128;
+  const int g4n = (p.nsf + 3) / 4, nrb = (p.N + 127) / 128;
+  uint8_t* ssfb = ssfa + g4n * 512;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int idx = tid; idx < 128 * (p.kbytes / 16); idx += 128) {
+    const int r = idx / (p.kbytes / 16), ch = idx % (p.kbytes / 16);
+    const int at = ch / 8, c = ch % 8;
+    *reinterpret_cast<uint4*>(sa + at * 16384 + r * 128 + ((c ^ (r & 7)) * 16)) =
+        *reinterpret_cast<const uint4*>(p.A + (long long)(rank * 128 + r) * p.kbytes + ch * 16);
+  }
+  for (int idx = tid; idx < NH * (p.kbytes / 16); idx += 128) {
+    const int n = idx / (p.kbytes / 16), ch = idx % (p.kbytes / 16);
+    const int at = ch / 8, c = ch % 8;
+    *reinterpret_cast<uint4*>(sb + at * (NH * 128) + n * 128 + ((c ^ (n & 7)) * 16)) =
+        *reinterpret_cast<const uint4*>(p.B + (long long)(rank * NH + n) * p.kbytes + ch * 16);
+  }
+  for (int idx = tid; idx < 128 * p.nsf; idx += 128) {
+    const int r = idx / p.nsf, s = idx % p.nsf;
+    ssfa[(s / 4) * 512 + (r % 32) * 16 + (r / 32) * 4 + (s % 4)] = p.SFA[(long long)(rank * 128 + r) * p.nsf + s];
+  }
+  for (int idx = tid; idx < nrb * 128 * p.nsf; idx += 128) {
+    const int n = idx / p.nsf, s = idx % p.nsf;   // n: slot row of the staged SFB set
+    const int rb = n / 128, r = n % 128;
+    int src = n;                                   // mode 0: all N columns, in order
+    if (p.sfb_mode == 1) src = (n < NH) ? int(rank) * NH + n : -1;  // mode 1: only this CTA's half, packed at the front
+    ssfb[((s / 4) * nrb + rb) * 512 + (r % 32) * 16 + (r / 32) * 4 + (s % 4)] = (src >= 0 && src < p.N) ? p.SFB[(long long)src * p.nsf + s] : 0;
+  }
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc2(&tmem_slot, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  constexpr uint32_t SFA_COL = 384, SFB_COL = 448;
+  if (rank == 0 && tid == 0) {
+    const uint32_t a_base = smem_u32(sa), b_base = smem_u32(sb);
+    for (int g = 0; g < g4n; ++g) {
+      tc_cp2_32x128b_warpx4(tmem + SFA_COL + g * 4, make_smem_desc_plain(smem_u32(ssfa + g * 512), 0, 128));
+      for (int rb = 0; rb < nrb; ++rb)
+        tc_cp2_32x128b_warpx4(tmem + SFB_COL + (g * nrb + rb) * 4, make_smem_desc_plain(smem_u32(ssfb + (g * nrb + rb) * 512), 0, 128));
+    }
+    for (int ks = 0; ks < p.kbytes / 32; ++ks) {
+      const uint64_t ad = make_smem_desc_sw128(a_base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+      const uint64_t bd = make_smem_desc_sw128(b_base + (ks >> 2) * (NH * 128) + (ks & 3) * 32, 16, 1024);
+      umma2_nvf4(tmem, ad, bd, make_idesc_bs(256, p.N, 1, 0, 0, 0, 0), ks != 0, tmem + SFA_COL + ks * 4, tmem + SFB_COL + ks * nrb * 4);
+    }
+    tc_commit2(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c = 0; c < p.N / 32; ++c) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(tmem + lane_base + c * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 32; ++e) p.D[(long long)(rank * 128 + tid) * p.N + c * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc2(tmem, 512);
+  }
+}
+
 }  // namespace fx
 
 extern "C" int fx_dbg_bs_tile(const void* A, const void* B, const void* SFA, const void* SFB, float* D, int32_t N, int32_t kbytes,
@@ -297,6 +400,22 @@ extern "C" int fx_dbg_bs_tile(const void* A, const void* B, const void* SFA, con
   }
   fx::dbg_bs_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
   return fx::launched("dbg_bs_kernel");
+}
+
+extern "C" int fx_dbg_bs2_tile(const void* A, const void* B, const void* SFA, const void* SFB, float* D, int32_t N, int32_t kbytes,
+                               int32_t nsf, int32_t sfb_mode, fx_stream stream) {
+  FX_REQUIRE(A && B && SFA && SFB && D && N % 64 == 0 && N >= 64 && N <= 256 && kbytes % 128 == 0 && kbytes >= 128 && kbytes <= 512 && nsf > 0,
+             "fx_dbg_bs2_tile: bad arguments");
+  fx::DbgBs2Params p{(const uint8_t*)A, (const uint8_t*)B, (const uint8_t*)SFA, (const uint8_t*)SFB, D, N, kbytes, nsf, sfb_mode};
+  const int atoms = kbytes / 128;
+  const int smem = atoms * 16384 + atoms * (N / 2) * 128 + ((nsf + 3) / 4) * 512 * (1 + (N + 127) / 128) + 2048;
+  static bool attr = false;
+  if (!attr) {
+    FX_CUDA(cudaFuncSetAttribute(fx::dbg_bs2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  fx::dbg_bs2_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(p);
+  return fx::launched("dbg_bs2_kernel");
 }
 
 namespace fx {

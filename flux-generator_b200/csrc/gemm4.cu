@@ -12,10 +12,12 @@
 //            where the MMA reads the four scales of its 64 elements of K for row r.
 //            A: atoms [row block of 128][K / 64]; W: atoms [192-row column tile][K / 64][2] (rows 0-127, 128-191 of the tile)
 //   a_scale  fp32 per row, w_scale fp32 per output channel: the second quantisation level (see fx_quantize_rows_fp4)
-// Kernel: one CTA per SM, 128 x 192 tiles (192 so that two accumulators AND two scale-factor slots fit the 512 TMEM
-// columns: 2 x 192 + 2 x 48), 4-stage TMA ring (A 16 KB + W 24 KB + scales 6 KB per stage), warp roles as gemm_kernel.
+// Kernel: persistent, 192-column tiles (192 so that two accumulators AND two scale-factor slots fit the 512 TMEM columns:
+// 2 x 192 + 2 x 48); CTA pairs (256 x 192 tiles, cta_group::2: the W tile is split over the pair, half the W bytes per FLOP)
+// when the row count allows, single CTAs (128 x 192) otherwise; TMA ring of A + W + scale atoms; warp roles as gemm_kernel.
 #include <cuda_fp4.h>
 #include <cuda_fp8.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -26,35 +28,46 @@
 namespace fx {
 
 constexpr int G4_BN = 192;
-constexpr int G4_STAGES = 4;
 constexpr int G4_A_BYTES = 128 * 128;           // 128 rows x 256 e2m1
-constexpr int G4_B_BYTES = G4_BN * 128;
 constexpr int G4_SFA_BYTES = 4 * 512;           // 4 K-groups (of 64 elements) x one 128-row atom
-constexpr int G4_SFB_BYTES = 4 * 2 * 512;       // 4 K-groups x two atoms (192 rows)
-constexpr int G4_STAGE_BYTES = G4_A_BYTES + G4_B_BYTES + G4_SFA_BYTES + G4_SFB_BYTES;
-constexpr int G4_EPI_OFF = G4_STAGES * G4_STAGE_BYTES + 256;
-constexpr int G4_STORE_OFF = G4_EPI_OFF + 8 * 384 * 4;
-constexpr int G4_SMEM = G4_STORE_OFF + 8 * 2048 + 1024;
+constexpr int G4_SFB_BYTES = 4 * 2 * 512;       // 4 K-groups x two atoms (192 rows): the WHOLE tile's columns, in every CTA
+template <int NCTA>
+struct G4Cfg {
+  // NCTA = 2: a CTA pair computes a 256 x 192 tile with cta_group::2 MMAs; each CTA stages its 128 A rows, HALF of the W
+  // tile (96 rows) and the scale atoms of its own A rows and of ALL 192 W rows (tcgen05.cp.cta_group::2 copies, in each CTA,
+  // from that CTA's shared memory into that CTA's TMEM: tests/gpu_bs_probe.py pair)
+  static constexpr int STAGES = NCTA == 2 ? 5 : 4;
+  static constexpr int B_BYTES = (G4_BN / NCTA) * 128;
+  static constexpr int STAGE_BYTES = G4_A_BYTES + B_BYTES + G4_SFA_BYTES + G4_SFB_BYTES;
+  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;
+  static constexpr int STORE_OFF = EPI_OFF + 8 * 384 * 4;
+  static constexpr int SMEM = STORE_OFF + 8 * 2048 + 1024;
+};
 constexpr int G4_TMEM_SF = 2 * G4_BN;           // scale-factor slots start behind the two accumulators
 constexpr int G4_SF_SLOT = 48;                  // 16 columns of A scales + 32 of W scales per stage
 
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ uint64_t make_smem_desc_sf(uint32_t smem_addr) {  // no swizzle, SBO = 128 B (8 rows x 16 B), version 1
   return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
 }
+template <int NCTA>
 __device__ __forceinline__ void tc_cp_sf(uint32_t taddr, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  if (NCTA == 2) asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+  else asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
 }
+template <int NCTA>
 __device__ __forceinline__ void umma_nvf4(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc, uint32_t sfa, uint32_t sfb) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
-      "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
-      : "memory");
+  if (NCTA == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
+        "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4nvf4.block_scale.block16 [%0], %1, %2, %3, [%5], [%6], p;\n\t}\n" ::"r"(d),
+        "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb)
+        : "memory");
 }
 // cute::UMMA::InstrDescriptorBlockScaled: a/b format E2M1 (1) at [7,10) / [10,13), N >> 3 at [17,23), scale format UE4M3 (0)
 // at [23], M >> 4 at [24,29), scale-factor ids 0
@@ -64,76 +77,100 @@ __host__ __device__ constexpr uint32_t make_idesc_nvf4(int M, int N) {
 
 struct Gemm4Params {
   GemmParams g;              // shapes, raster, generic epilogue (a_scale / w_scale = the second-level scales)
-  const uint8_t* sfa;        // A scale atoms [row blocks][K / 64][512]
-  const uint8_t* sfb;        // W scale atoms [column tiles][K / 64][2][512]
   int k_groups;              // K / 64
 };
 
+// tmap_sfa / tmap_sfb: the scale-atom buffers viewed as [bytes / 128][128] byte matrices (no swizzle): one stage's atoms of a
+// row block / column tile are 16 / 32 consecutive rows, fetched by TMA like the operands (and, for a pair, credited to the
+// leader's barrier like them)
+template <int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const Gemm4Params q) {
+gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb, const Gemm4Params q) {
   const GemmParams& p = q.g;
-  constexpr int BN = G4_BN, STAGES = G4_STAGES;
+  using Cfg = G4Cfg<NCTA>;
+  constexpr int BN = G4_BN, STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G4_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int first_tile = blockIdx.x, tile_stride = gridDim.x;
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int first_tile = blockIdx.x / NCTA, tile_stride = gridDim.x / NCTA;
 
   if (warp == GEMM_WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_sfa);
+    tma_prefetch_desc(&tmap_sfb);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 8 * NCTA);
     }
     fence_barrier_init();
   }
   if (warp == GEMM_WARP_MMA) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc2(tmem_slot, 512);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= GEMM_CTRL0 && warp < GEMM_CTRL0 + 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == GEMM_WARP_TMA) {
-      // ================= TMA producer: A tile, W tile, their scale atoms (plain bulk copies: already in atom order)
+      // ================= TMA producer: A rows, this CTA's share of the W tile, the scale atoms (already in atom order)
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
           int tm, tn;
           gemm_tile_coords(p, tile, tm, tn);
+          const int rb = tm * NCTA + int(cta_rank);  // 128-row block of the flattened activation rows
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * G4_STAGE_BYTES;
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + G4_A_BYTES;
-            uint8_t* ssfa = sb + G4_B_BYTES;
+            uint8_t* ssfa = sb + Cfg::B_BYTES;
             uint8_t* ssfb = ssfa + G4_SFA_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], G4_STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * 128, tm * GEMM_BM);
-            tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * 128, tn * BN);
-            bulk_load(ssfa, q.sfa + ((long long)tm * q.k_groups + kb * 4) * 512, G4_SFA_BYTES, &full_bar[stage]);
-            bulk_load(ssfb, q.sfb + ((long long)tn * q.k_groups + kb * 4) * 1024, G4_SFB_BYTES, &full_bar[stage]);
+            const int sfa_row = (rb * q.k_groups + kb * 4) * 4;          // 4 rows of 128 B per atom
+            const int sfb_row = (tn * q.k_groups + kb * 4) * 8;          // two atoms per K-group
+            if (NCTA == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              tma2_load_2d(sa, &tmap_a, &full_bar[stage], kb * 128, rb * GEMM_BM);
+              tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * 128, tn * BN + int(cta_rank) * (BN / 2));
+              tma2_load_2d(ssfa, &tmap_sfa, &full_bar[stage], 0, sfa_row);
+              tma2_load_2d(ssfb, &tmap_sfb, &full_bar[stage], 0, sfb_row);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * 128, rb * GEMM_BM);
+              tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * 128, tn * BN);
+              tma_load_2d(ssfa, &tmap_sfa, &full_bar[stage], 0, sfa_row);
+              tma_load_2d(ssfb, &tmap_sfb, &full_bar[stage], 0, sfb_row);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     } else if (warp == GEMM_WARP_MMA) {
       // ================= MMA issuer: per stage 12 scale-atom copies into the stage's TMEM slot, then 4 MMAs (K = 64 each)
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_nvf4(GEMM_BM, BN);
+      if (lane == 0 && cta_rank == 0) {
+        constexpr uint32_t idesc = make_idesc_nvf4(GEMM_BM * NCTA, BN);
         int stage = 0;
         uint32_t phase = 0, n = 0;
         int acc = 0;
@@ -145,25 +182,27 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * G4_STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
             const uint32_t sb = sa + G4_A_BYTES;
-            const uint32_t ssfa = sb + G4_B_BYTES, ssfb = ssfa + G4_SFA_BYTES;
+            const uint32_t ssfa = sb + Cfg::B_BYTES, ssfb = ssfa + G4_SFA_BYTES;
             // tcgen05.cp and tcgen05.mma execute in issue order: slot (n & 1) was last read by the MMAs of stage n - 2
             const uint32_t t_sfa = tmem_base + G4_TMEM_SF + (n & 1) * G4_SF_SLOT, t_sfb = t_sfa + 16;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              tc_cp_sf(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
-              tc_cp_sf(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
-              tc_cp_sf(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
+              tc_cp_sf<NCTA>(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
+              tc_cp_sf<NCTA>(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
+              tc_cp_sf<NCTA>(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_nvf4(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
-                        (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
-            tc_commit(&empty_bar[stage]);
+              umma_nvf4<NCTA>(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
+                              (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
+            if (NCTA == 2) tc_commit2(&empty_bar[stage]);
+            else tc_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(&tfull_bar[acc]);
+          if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
+          else tc_commit(&tfull_bar[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -174,10 +213,10 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int quarter = warp & 3;
     const int half = (warp - GEMM_EPI0) >> 2;
     const int r = quarter * 32 + lane;
-    float* sb = reinterpret_cast<float*>(smem + G4_EPI_OFF) + (warp - GEMM_EPI0) * 384;
+    float* sb = reinterpret_cast<float*>(smem + Cfg::EPI_OFF) + (warp - GEMM_EPI0) * 384;
     float* sg = sb + 128;
     float* sw = sb + 256;
-    uint8_t* wst = smem + G4_STORE_OFF + (warp - GEMM_EPI0) * 2048;
+    uint8_t* wst = smem + Cfg::STORE_OFF + (warp - GEMM_EPI0) * 2048;
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = BN / 64, WN = BN / 2;
@@ -186,7 +225,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       gemm_tile_coords(p, tile, tm, tn);
       const int b = tm / p.tiles_m_per_batch;
       const int tmb = tm - b * p.tiles_m_per_batch;
-      const long long row = (long long)tmb * GEMM_BM + r;
+      const long long row = (long long)tmb * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
       const bool valid = row < p.rows;
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
@@ -232,16 +271,21 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&tempty_bar[acc]);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync();
+  else __syncthreads();
   if (warp == GEMM_WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (NCTA == 2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -298,19 +342,22 @@ __global__ void __launch_bounds__(256) quantize_rows_fp4_kernel(const Quant4Para
 #pragma unroll
   for (int i = 0; i < ITERS; ++i) {
     const int c = i * 2048 + tid * 8;
-    if (c >= p.K) continue;
+    const bool in = c < p.K;  // (no early exit: the warp shuffles below need every lane)
     const float u = __fmul_rn(__fmul_rn(bmax[i], 1.0f / 6.0f), rg);
     const __nv_fp8_storage_t sf8 = __nv_cvt_float_to_fp8(u, __NV_SATFINITE, __NV_E4M3);
     const float d = __fmul_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(sf8, __NV_E4M3))), g);
-    const int j = c >> 4;  // scale index in the row
-    if ((tid & 1) == 0) sf_row[(j >> 2) * 512 + (j & 3)] = sf8;
+    const int j = c >> 4;  // scale index in the row; the four scales of a K-group sit in lanes 8m, 8m+2, 8m+4, 8m+6
+    uint32_t sfw = uint32_t(sf8);
+    sfw |= __shfl_down_sync(0xffffffffu, sfw, 2) << 8;
+    sfw |= __shfl_down_sync(0xffffffffu, sfw, 4) << 16;   // (lanes 8m and 8m+4 each hold two bytes by now)
+    if (in && (tid & 7) == 0) *reinterpret_cast<uint32_t*>(sf_row + (j >> 2) * 512) = sfw;
     const float rd = d > 0.f ? __frcp_rn(d) : 0.f;
     uint32_t w = 0;
 #pragma unroll
     for (int e = 0; e < 8; e += 2)
       w |= uint32_t(__nv_cvt_float2_to_fp4x2(make_float2(__fmul_rn(v[i][e], rd), __fmul_rn(v[i][e + 1], rd)), __NV_E2M1, cudaRoundNearest))
            << (4 * e);
-    *reinterpret_cast<uint32_t*>(qr + (c >> 1)) = w;
+    if (in) *reinterpret_cast<uint32_t*>(qr + (c >> 1)) = w;
   }
 }
 
@@ -336,33 +383,85 @@ extern "C" int fx_quantize_rows_fp4(const fx_quant4_args* a, fx_stream stream) {
   return launched("quantize_rows_fp4_kernel");
 }
 
+// scale-atom buffer as a [bytes / 128][128] byte matrix, no swizzle (the atoms are consumed by tcgen05.cp, not by the MMA)
+static int make_tmap_sf(CUtensorMap* out, const void* base, uint64_t bytes, uint32_t box_rows) {
+  tmap_encode_fn fn = get_tmap_encode();
+  if (!fn) return fail(FX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[2] = {128, bytes / 128};
+  cuuint64_t gs[1] = {128};
+  cuuint32_t bx[2] = {128, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FX_ERR_CUDA, "cuTensorMapEncodeTiled (scale atoms) failed (%d)", (int)r);
+  return FX_OK;
+}
+
+template <int NCTA>
+static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tsa, const CUtensorMap& tsb, const Gemm4Params& q,
+                      cudaStream_t st) {
+  using Cfg = G4Cfg<NCTA>;
+  auto kern = gemm_nvfp4_kernel<NCTA>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM); });
+  if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm_fp4 smem attribute: %s", cudaGetErrorString(attr_err));
+  const int units = num_sms() / NCTA;
+  const int grid = (q.g.num_tiles < units ? q.g.num_tiles : units) * NCTA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, tsa, tsb, q);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(FX_ERR_CUDA, "gemm_nvfp4_kernel launch: %s", cudaGetErrorString(e));
+  }
+  return launched("gemm_nvfp4_kernel");
+}
+
 extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && a->out, "fx_gemm_fp4: null pointer");
   FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm_fp4: empty problem");
   FX_REQUIRE(a->K % 256 == 0, "fx_gemm_fp4: K (%d) must be a multiple of 256", a->K);
   FX_REQUIRE(a->rows % 128 == 0 || a->batch == 1, "fx_gemm_fp4: rows per batch element (%d) must be a multiple of 128", a->rows);
   FX_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->sfa) && aligned16(a->sfw), "fx_gemm_fp4: operands must be 16-byte aligned");
+  // CTA pairs (256 x 192 tiles) when every batch element is a whole number of 256-row tiles; FX_GEMM4_NCTA=1 forces single CTAs
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FX_GEMM4_NCTA");
+    forced = e ? atoi(e) : 0;
+  }
+  const int ncta = (forced == 1 || a->rows % 256 != 0) ? 1 : 2;
   Gemm4Params q{};
   GemmParams& p = q.g;
   p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
   p.k_blocks = a->K / 256;
   q.k_groups = a->K / 64;
-  q.sfa = (const uint8_t*)a->sfa; q.sfb = (const uint8_t*)a->sfw;
   p.a_scale = a->a_scale; p.a_scale_bs = a->rows; p.w_scale = a->w_scale;
   p.bias = (const __nv_bfloat16*)a->bias;
   p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
-  p.tiles_m_per_batch = (a->rows + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_m_per_batch = (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta);
   p.tiles_m = p.tiles_m_per_batch * a->batch;
   p.tiles_n = (a->N + G4_BN - 1) / G4_BN;
   p.num_tiles = p.tiles_m * p.tiles_n;
   p.group_m = p.tiles_m < 8 ? p.tiles_m : 8;
   p.group_n = 0;
   p.stream_out = 1;
-  CUtensorMap ta, tw;
+  const uint64_t rows_total = (uint64_t)a->batch * a->rows;
+  CUtensorMap ta, tw, tsa, tsb;
   {  // A: flattened rows [batch * rows][K / 2] bytes (the quantiser writes a compact operand)
-    const uint64_t dims[2] = {(uint64_t)a->K / 2, (uint64_t)a->batch * a->rows};
+    const uint64_t dims[2] = {(uint64_t)a->K / 2, rows_total};
     const uint64_t strides[1] = {(uint64_t)a->K / 2};
     const uint32_t box[2] = {128, GEMM_BM};
     int rc = make_tmap_bf16(&ta, a->A, 2, dims, strides, box, true);
@@ -371,15 +470,14 @@ extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
   {
     const uint64_t dims[2] = {(uint64_t)a->K / 2, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->K / 2};
-    const uint32_t box[2] = {128, G4_BN};
+    const uint32_t box[2] = {128, (uint32_t)(G4_BN / ncta)};
     int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box, true);
     if (rc) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(gemm_nvfp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM); });
-  if (attr_err != cudaSuccess) return fail(FX_ERR_CUDA, "gemm_fp4 smem attribute: %s", cudaGetErrorString(attr_err));
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_nvfp4_kernel<<<grid, GEMM_THREADS, G4_SMEM, (cudaStream_t)stream>>>(ta, tw, q);
-  return launched("gemm_nvfp4_kernel");
+  int rc = make_tmap_sf(&tsa, a->sfa, ((rows_total + 127) / 128) * (uint64_t)q.k_groups * 512, 16);
+  if (rc) return rc;
+  rc = make_tmap_sf(&tsb, a->sfw, (uint64_t)p.tiles_n * q.k_groups * 1024, 32);
+  if (rc) return rc;
+  if (ncta == 2) return launch_fp4<2>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  return launch_fp4<1>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
 }

@@ -123,6 +123,7 @@ DBG_SYMBOLS = {
     "fx_dbg_umma_tile": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, C.c_uint32, C.c_uint32,
                                    C.c_uint32, c_vp]),
     "fx_dbg_mma_pattern": (C.c_int, [c_i32, c_i32, c_vp, c_vp]),
+    "fx_dbg_bs2_tile": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "fx_dbg_bs_tile": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, C.c_uint32, C.c_uint32,
                                  C.c_uint32, C.c_uint32, C.c_uint32, c_vp]),
 }

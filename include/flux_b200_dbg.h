@@ -37,6 +37,11 @@ int fx_dbg_bs_tile(const void* A, const void* B, const void* SFA, const void* SF
                    int32_t kind, int32_t a_tmem, int32_t b_mn_major, int32_t nsf, uint32_t b_lbo, uint32_t b_sbo,
                    uint32_t b_kstep, uint32_t cp_lbo, uint32_t cp_sbo, fx_stream stream);
 
+/* The NVFP4 probe for a CTA pair (cta_group::2, M = 256): A [256][kbytes], B [N][kbytes], SFA [256][nsf], SFB [N][nsf], D float
+ * [256][N].  sfb_mode 0: every CTA stages the scale atoms of all N columns; 1: only those of its own half of the W rows. */
+int fx_dbg_bs2_tile(const void* A, const void* B, const void* SFA, const void* SFB, float* D, int32_t N, int32_t kbytes,
+                    int32_t nsf, int32_t sfb_mode, fx_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,5 +97,30 @@ def main():
                       f"{rel(run(Ab, Bb, sa_b, sb_b, N, kb, kind, nsf=nsf), ref):.2e}", flush=True)
 
 
+def main_pair():
+    """CTA pair (cta_group::2) NVFP4: M = 256, which shared memory / TMEM do the scale factors of a pair come from?"""
+    g = torch.Generator().manual_seed(2)
+    for N, kb in ((256, 128), (192, 256), (128, 128)):
+        Ab, Af = fp4_bytes(256, kb, g)
+        Bb, Bf = fp4_bytes(N, kb, g)
+        nsf = 2 * kb // 16
+        for unit in (True, False):
+            sa_b, sa_f = ue4m3((256, nsf), g, unit)
+            sb_b, sb_f = ue4m3((N, nsf), g, unit)
+            ref = (Af * sa_f.repeat_interleave(16, 1)) @ (Bf * sb_f.repeat_interleave(16, 1)).T
+            for mode in (0, 1):
+                D = torch.full((256, N), float("nan"), device=dev, dtype=torch.float32)
+                t_ = [x.contiguous().to(dev) for x in (Ab, Bb, sa_b, sb_b)]
+                _native.check(lib.fx_dbg_bs2_tile(t_[0].data_ptr(), t_[1].data_ptr(), t_[2].data_ptr(), t_[3].data_ptr(), D.data_ptr(),
+                                                  N, kb, nsf, mode, _native.stream()))
+                torch.cuda.synchronize()
+                d = D.double().cpu()
+                print(f"pair nvfp4 unit_sf={int(unit)} N={N} K={2 * kb} sfb_mode={mode}: rel all {rel(d, ref):.2e}  "
+                      f"rows 0-127 {rel(d[:128], ref[:128]):.2e}  rows 128-255 {rel(d[128:], ref[128:]):.2e}", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pair":
+        main_pair()
+    else:
+        main()
