@@ -327,7 +327,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   volatile uint32_t* ls_allowed = ls_issued + 1;                                                               // sync warp -> producer
   const bool lockstep = (NCTA == 2) && CL == 1 && !CONV && p.ls_group > 0 && cta_rank == 0;
 
-  const int warp = threadIdx.x >> 5;
+  // the warp index goes through a shuffle so that ptxas knows it is warp-uniform: the producer / issuer loops below then run
+  // with every lane (uniform control flow) and their descriptors, coordinates and barrier addresses live in uniform registers
+  // -- an `if (lane == 0)` region instead costs a broadcast loop (ELECT / R2UR / BRA.U.ANY) around every TMA / tcgen05 op
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   constexpr int KE = F8 ? 2 * GEMM_BK : GEMM_BK;  // K elements per 128-byte stage row
 
@@ -367,7 +370,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == GEMM_WARP_TMA) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t lsg = 0;  // global K-group index of this pair (monotonic across its tiles)
@@ -384,10 +387,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (lockstep && kb % p.ls_group == 0) {  // entering K-group `lsg`: stay within ls_slack groups of the slowest pair
-            if (kb != 0 || lsg != 0) *ls_issued = lsg;  // groups < lsg are fully issued
+            if ((kb != 0 || lsg != 0) && lane == 0) *ls_issued = lsg;  // groups < lsg are fully issued
             while (*ls_allowed <= lsg) {
             }
             ++lsg;
+            __syncwarp();
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -408,6 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               dy = tap / 3 - 1;
             }
           }
+          if (elect_one()) {
           if (NCTA == 2) {
             // the leader's barrier collects both CTAs' bytes; only the leader arrives on it
             const bool skip_w = CL == 1 && p.dbg_skip_w && (kb & 1);
@@ -433,10 +438,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           }
           tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * KE, wrow + tn * BN);
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-      if (lockstep) *ls_issued = lsg;
+      if (lockstep && lane == 0) *ls_issued = lsg;
     }
   } else if (warp == GEMM_CTRL0 + 2) {
     // ================= wave-lockstep sync warp (leader CTA of the pair) =================
@@ -475,8 +482,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp == GEMM_WARP_MMA) {
     // ================= MMA issuer =================
-    if (lane == 0 && cta_rank == 0) {
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = F8 ? make_idesc_f8(GEMM_BM * NCTA, BN) : make_idesc_bf16(GEMM_BM * NCTA, BN, 0, 0);
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -484,12 +493,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tbase + acc * BN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sa = smem0 + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
@@ -505,11 +515,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
           if (NCTA == 2 && CL == 2) tc_commit2_mask(&empty_bar[stage], 0xF);  // both pairs wait for both pairs
           else if (NCTA == 2) tc_commit2(&empty_bar[stage]);
           else tc_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (NCTA == 2 && CL == 2) tc_commit2_mask(&tfull_bar[acc], uint16_t(3u << (2 * pair_idx)));
-        else if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
-        else tc_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if (NCTA == 2 && CL == 2) tc_commit2_mask(&tfull_bar[acc], uint16_t(3u << (2 * pair_idx)));
+          else if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
+          else tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

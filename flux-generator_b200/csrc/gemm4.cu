@@ -97,7 +97,8 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the issuer's descriptors in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int first_tile = blockIdx.x / NCTA, tile_stride = gridDim.x / NCTA;
 
@@ -135,7 +136,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == GEMM_WARP_TMA) {
       // ================= TMA producer: A rows, this CTA's share of the W tile, the scale atoms (already in atom order)
-      if (lane == 0) {
+      {
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
@@ -150,7 +151,8 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint8_t* ssfb = ssfa + G4_SFA_BYTES;
             const int sfa_row = (rb * q.k_groups + kb * 4) * 4;          // 4 rows of 128 B per atom
             const int sfb_row = (tn * q.k_groups + kb * 4) * 8;          // two atoms per K-group
-            if (NCTA == 2) {
+            if (!elect_one()) {
+            } else if (NCTA == 2) {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
               tma2_load_2d(sa, &tmap_a, &full_bar[stage], kb * 128, rb * GEMM_BM);
               tma2_load_2d(sb, &tmap_w, &full_bar[stage], kb * 128, tn * BN + int(cta_rank) * (BN / 2));
@@ -163,14 +165,18 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               tma_load_2d(ssfa, &tmap_sfa, &full_bar[stage], 0, sfa_row);
               tma_load_2d(ssfb, &tmap_sfb, &full_bar[stage], 0, sfb_row);
             }
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     } else if (warp == GEMM_WARP_MMA) {
       // ================= MMA issuer: per stage 12 scale-atom copies into the stage's TMEM slot, then 4 MMAs (K = 64 each)
-      if (lane == 0 && cta_rank == 0) {
+      if (cta_rank == 0) {
+        // the whole warp runs the loop (uniform control flow); one elected lane issues each tcgen05 instruction
         constexpr uint32_t idesc = make_idesc_nvf4(GEMM_BM * NCTA, BN);
+        const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t smem0 = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
         int stage = 0;
         uint32_t phase = 0, n = 0;
         int acc = 0;
@@ -178,31 +184,37 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
           mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BN;
+          const uint32_t d_tmem = tbase + acc * BN;
           for (int kb = 0; kb < p.k_blocks; ++kb, ++n) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sa = smem0 + stage * Cfg::STAGE_BYTES;
             const uint32_t sb = sa + G4_A_BYTES;
             const uint32_t ssfa = sb + Cfg::B_BYTES, ssfb = ssfa + G4_SFA_BYTES;
             // tcgen05.cp and tcgen05.mma execute in issue order: slot (n & 1) was last read by the MMAs of stage n - 2
-            const uint32_t t_sfa = tmem_base + G4_TMEM_SF + (n & 1) * G4_SF_SLOT, t_sfb = t_sfa + 16;
+            const uint32_t t_sfa = tbase + G4_TMEM_SF + (n & 1) * G4_SF_SLOT, t_sfb = t_sfa + 16;
+            if (elect_one()) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              tc_cp_sf<NCTA>(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
-              tc_cp_sf<NCTA>(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
-              tc_cp_sf<NCTA>(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
+              for (int g = 0; g < 4; ++g) {
+                tc_cp_sf<NCTA>(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
+                tc_cp_sf<NCTA>(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
+                tc_cp_sf<NCTA>(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_nvf4<NCTA>(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
+                                (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
+              if (NCTA == 2) tc_commit2(&empty_bar[stage]);
+              else tc_commit(&empty_bar[stage]);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_nvf4<NCTA>(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
-                              (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
-            if (NCTA == 2) tc_commit2(&empty_bar[stage]);
-            else tc_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
-          else tc_commit(&tfull_bar[acc]);
+          if (elect_one()) {
+            if (NCTA == 2) tc_commit2(&tfull_bar[acc]);
+            else tc_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
