@@ -132,7 +132,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   using Cfg = AttnCfg<P_TMEM>;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* q_full = bars;             // 1
   uint64_t* kv_full = bars + 1;        // NS
@@ -621,7 +621,7 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   constexpr int TILE = Cfg::TILE_BYTES;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* q_full = bars;             // 1: Q of the current item has landed
   uint64_t* q_empty = bars + 1;        // 1: every Q K^T of the current item has completed (tcgen05.commit)
@@ -996,7 +996,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   using Cfg = Attn3Cfg;
   constexpr int NS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
   uint64_t* q_full = bars;              // 1
   uint64_t* kv_full = bars + 1;         // NS

@@ -17,7 +17,7 @@ struct DbgUmmaParams {
 
 __global__ void __launch_bounds__(128, 1) dbg_umma_kernel(const DbgUmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sa = smem;                          // K/64 halves x [128 rows x 128 B]
   uint8_t* sb = smem + (p.K / 64) * 16384;     // see below
   __shared__ uint64_t bar;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void umma_ts_f8(uint32_t d, uint32_t a_tmem, uint64_t
 
 __global__ void __launch_bounds__(128, 1) dbg_bs_kernel(const DbgBsParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const int atoms = p.kbytes / 128;                 // 128-byte K atoms per row
   uint8_t* sa = smem;                               // atoms x [128 rows x 128 B]
   uint8_t* sb = sa + atoms * 16384;                 // K-major: atoms x [N rows x 128 B]; MN-major: [K rows x 128 B]
@@ -299,7 +299,7 @@ struct DbgBs2Params {
 };
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) dbg_bs2_kernel(const DbgBs2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   const uint32_t rank = cluster_ctarank();
   const int atoms = p.kbytes / 128, NH = p.N / 2;
   uint8_t* sa = smem;                                   // atoms x [128 rows x 128 B]: rows 128 * rank ...
@@ -501,7 +501,7 @@ __device__ __forceinline__ void pat_step(const PatCtx& c, int ks_, int vs, int r
 template <int PAT>
 __global__ void __launch_bounds__(128, 1) dbg_mma_pattern_kernel(int iters, long long* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * PAT_TILE);
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;

@@ -305,6 +305,171 @@ __device__ __forceinline__ void stage_vec_f32(float* dst, const float* src, int 
 // worth 8-17 % on these GEMMs -- the chip is power-limited and moving operands costs as much as multiplying them;
 // profiles/r02_gemm_l2_traffic_sensitivity.txt.)  The price: a slot of the ring is free only when BOTH pairs have consumed
 // it (empty barriers count two commits), and only 33 clusters of 4 are co-resident on the 148 SMs (132 CTAs).
+// QKV(+MLP) epilogue of one warp for one 128-column group (= one head of q, k or v, or 128 MLP columns) of one accumulator:
+// bias (and, DEQ, the row / column scales), per-head RMSNorm and RoPE for q and k, split stores (bf16 or e4m3); MLP columns take
+// the generic chunk (+bias, GELU).  `ta` = TMEM address of the group for this warp's lane quarter, `g0` its first output column.
+//
+// Latency structure (it matters once the main loop is short -- FP8 / NVFP4 at K = 3072 -- and the epilogue sets the pace):
+//  * epi_qkv_prefetch issues every tile-uniform global load of a group (bias, column scales, norm weights, row scale) back to
+//    back into registers (QkvPre); epi_qkv_group commits them to the warp's staging slots.  A caller with a tile queue
+//    prefetches the NEXT group between commit and processing (`nxt`), so the round trip hides behind this group's work;
+//  * both TMEM passes keep the tcgen05.ld of the following chunk in flight while a chunk is processed.
+struct QkvPre {
+  float b[4], w[4], g[4], rs;
+};
+struct QkvNext {   // the group a queue-driven caller will process next (has == false: none)
+  bool has;
+  int b;
+  long long row;
+  bool valid;
+  int g0;
+};
+template <bool DEQ>
+__device__ __forceinline__ void epi_qkv_prefetch(const GemmParams& p, int b, long long row, bool valid, int lane, int g0, QkvPre& pr) {
+  const int which = (g0 >= 3 * p.heads * 128) ? 3 : (g0 >> 7) / p.heads;  // 0 q, 1 k, 2 v, 3 mlp
+  const __nv_bfloat16* nw = which == 0 ? p.qnorm_w : p.knorm_w;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = i * 32 + lane;
+    const bool in = g0 + j < p.N;
+    pr.b[i] = (p.bias != nullptr && in) ? __bfloat162float(__ldg(p.bias + g0 + j)) : 0.f;
+    pr.w[i] = (DEQ && in) ? __ldg(p.w_scale + g0 + j) : 0.f;
+    pr.g[i] = which < 2 ? __bfloat162float(__ldg(nw + j)) : 1.f;
+  }
+  pr.rs = (DEQ && valid) ? __ldg(p.a_scale + (long long)b * p.a_scale_bs + row) : 1.f;
+}
+
+template <bool DEQ>
+__device__ __forceinline__ void epi_qkv_group(const GemmParams& p, int b, long long row, bool valid, uint32_t vmask, int lane, uint32_t ta,
+                                              int g0, float* sb, float* sg, float* sw, uint8_t* wst, uint64_t* tfull, uint32_t tfull_phase,
+                                              QkvPre& pr, const QkvNext& nxt) {
+  constexpr bool F8 = DEQ;
+  const int D3 = 3 * p.heads * 128;
+  const long long pos = (long long)p.seq_off + row;
+  const bool active = g0 < p.N;
+  const int hidx = g0 >> 7;
+  const int which = (g0 >= D3) ? 3 : hidx / p.heads;  // 0 q, 1 k, 2 v, 3 mlp
+  // piece k (4 (cos, sin) pairs) of this row: pe4[k * pe_st]
+  const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe) + (p.pe_blocked ? (pos >> 5) * 512 + (pos & 31) : pos * 16);
+  const int pe_st = p.pe_blocked ? 32 : 1;
+  uint4 pcur[4], pnxt[4];
+  __syncwarp();  // the previous group is done with the staging slots
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sb[i * 32 + lane] = pr.b[i];
+    sw[i * 32 + lane] = pr.w[i];
+    sg[i * 32 + lane] = pr.g[i];
+  }
+  const float rs = pr.rs;
+  if (active && which < 2 && valid) {  // first RoPE chunk to registers before the accumulator wait
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pe4 + i * pe_st);
+  }
+  if (nxt.has) epi_qkv_prefetch<DEQ>(p, nxt.b, nxt.row, nxt.valid, lane, nxt.g0, pr);
+  __syncwarp();
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (!active) return;
+  if (which == 3) {
+    // mlp region -> +bias, gelu -> `out` at column (g0 - 3D)
+    const long long out_off = (long long)b * p.out_bs + pos * p.ldo - D3;
+    uint32_t v[32];
+    tmem_ld_x32(ta, v);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float f[32];
+      tmem_ld_wait_x32(v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      if (c < 3) tmem_ld_x32(ta + (c + 1) * 32, v);
+      epi_generic_chunk<F8>(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true, sw + c * 32, rs, wst, lane, vmask,
+                            valid);
+    }
+    return;
+  }
+  const int head = hidx - which * p.heads;
+  __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) + (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
+  // dequantise (or just add the bias to) one chunk: x = acc * rs * w + bias
+  auto load_chunk = [&](const uint32_t* v, int c, float* x) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
+      if (F8) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
+        x[i] = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); x[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
+        x[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); x[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
+      } else {
+        x[i] = __uint_as_float(v[i]) + t.x; x[i + 1] = __uint_as_float(v[i + 1]) + t.y;
+        x[i + 2] = __uint_as_float(v[i + 2]) + t.z; x[i + 3] = __uint_as_float(v[i + 3]) + t.w;
+      }
+    }
+  };
+  uint32_t v[32];
+  tmem_ld_x32(ta, v);
+  float rr = 1.f;
+  if (which < 2) {  // pass 1: sum of squares of (acc + bias) over the head
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float x[32];
+      tmem_ld_wait_x32(v);
+      load_chunk(v, c, x);
+      tmem_ld_x32(ta + ((c + 1) & 3) * 32, v);  // next chunk of this pass; after the last one, chunk 0 again for pass 2
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) ss += x[i] * x[i] + x[i + 1] * x[i + 1] + x[i + 2] * x[i + 2] + x[i + 3] * x[i + 3];
+    }
+    rr = rsqrtf(ss * (1.0f / 128.0f) + p.rms_eps);
+  }
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {  // pass 2: normalise, rotate, store
+    if (which < 2 && valid && c < 3) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pe4 + ((c + 1) * 4 + i) * pe_st);
+    }
+    // every lane computes (rows past the end hold zeros / stale table values and are masked at the store)
+    float f[32];
+    tmem_ld_wait_x32(v);
+    load_chunk(v, c, f);
+    if (c < 3) tmem_ld_x32(ta + (c + 1) * 32, v);
+    if (which < 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sg + c * 32 + i * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(sg + c * 32 + i * 8 + 4);
+        const float wt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint32_t pw[4] = {pcur[i].x, pcur[i].y, pcur[i].z, pcur[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 cs = unpack_bf16(pw[j]);  // (cos, sin)
+          const float x0 = f[i * 8 + 2 * j] * rr * wt[2 * j];
+          const float x1 = f[i * 8 + 2 * j + 1] * rr * wt[2 * j + 1];
+          f[i * 8 + 2 * j] = x0 * cs.x - x1 * cs.y;
+          f[i * 8 + 2 * j + 1] = x0 * cs.y + x1 * cs.x;
+        }
+      }
+    }
+    if (p.qkv_f8) {  // 32 e4m3 bytes of this row: two full 16-byte vectors (rows are 128 bytes apart)
+      if (valid) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i], f[4 * i + 1]), __NV_SATFINITE, __NV_E4M3);
+          const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2], f[4 * i + 3]), __NV_SATFINITE, __NV_E4M3);
+          w8[i] = uint32_t(lo) | (uint32_t(hi) << 16);
+        }
+        uint8_t* d8 = reinterpret_cast<uint8_t*>(which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
+                      (((long long)b * p.heads + head) * p.seq_total + pos) * 128 + c * 32;
+        *reinterpret_cast<uint4*>(d8) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+        *reinterpret_cast<uint4*>(d8 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+      }
+    } else {
+      store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask, p.stream_out != 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];
+  }
+}
+
 template <int BN, int EPI, bool CONV, int NCTA = 1, bool F8 = false, int CL = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -317,7 +482,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int first_tile = blockIdx.x / (NCTA * CL), tile_stride = gridDim.x / (NCTA * CL);
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -630,149 +795,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       } else {
         // ---- QKV(+MLP) epilogue: this warp owns one 128-column group (= one head of q, k or v, or 128 MLP columns)
-        const int D3 = 3 * p.heads * 128;
-        const long long pos = (long long)p.seq_off + row;
-        const int g0 = tn * BN + half * 128;
-        const bool active = g0 < p.N;
-        const int hidx = g0 >> 7;
-        const int which = (g0 >= D3) ? 3 : hidx / p.heads;  // 0 q, 1 k, 2 v, 3 mlp
-        // piece k (4 (cos, sin) pairs) of this row: pe4[k * pe_st]
-        const uint4* pe4 = reinterpret_cast<const uint4*>(p.pe) + (p.pe_blocked ? (pos >> 5) * 512 + (pos & 31) : pos * 16);
-        const int pe_st = p.pe_blocked ? 32 : 1;
-        // ---- before the accumulator wait: bias / norm weight to smem, first RoPE chunk to registers
-        uint4 pcur[4], pnxt[4];
-        __syncwarp();
-        float rs = 1.f;
-        if (active) {
-          stage_vec(sb, p.bias, g0, 128, p.N, 0.f, lane);
-          if (F8) {
-            stage_vec_f32(sw, p.w_scale, g0, 128, p.N, 0.f, lane);
-            if (valid) rs = __ldg(p.a_scale + (long long)b * p.a_scale_bs + row);
-          }
-          if (which < 2) {
-            stage_vec(sg, which == 0 ? p.qnorm_w : p.knorm_w, 0, 128, 128, 1.f, lane);
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pcur[i] = __ldg(pe4 + i * pe_st);
-            }
-          }
-        }
-        __syncwarp();
-        mbar_wait(&tfull_bar[acc], acc_phase);
-        tc_fence_after();
-        if (active) {
-          const uint32_t ta = taddr + half * 128;
-          if (which == 3) {
-            // mlp region -> +bias, gelu -> `out` at column (g0 - 3D)
-            const long long out_off = (long long)b * p.out_bs + pos * p.ldo - D3;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              __syncwarp();
-              tmem_ld_x32(ta + c * 32, v);
-              tmem_ld_wait();
-              {
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                epi_generic_chunk<F8>(p, f, sb + c * 32, sg, nullptr, false, out_off, 0, g0 + c * 32, true, sw + c * 32, rs,
-                                      wst, lane, vmask, valid);
-              }
-            }
-          } else {
-            const int head = hidx - which * p.heads;
-            __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
-                                 (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
-            float rr = 1.f;
-            if (which < 2) {  // pass 1: sum of squares of (acc + bias) over the head
-              float ss = 0.f;
-#pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld_x32(ta + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
-                  float x0, x1, x2, x3;
-                  if (F8) {
-                    const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
-                    x0 = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); x1 = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
-                    x2 = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); x3 = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
-                  } else {
-                    x0 = __uint_as_float(v[i]) + t.x; x1 = __uint_as_float(v[i + 1]) + t.y;
-                    x2 = __uint_as_float(v[i + 2]) + t.z; x3 = __uint_as_float(v[i + 3]) + t.w;
-                  }
-                  ss += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
-                }
-              }
-              rr = rsqrtf(ss * (1.0f / 128.0f) + p.rms_eps);
-            }
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {  // pass 2: normalise, rotate, store
-              if (which < 2 && valid && c < 3) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) pnxt[i] = __ldg(pe4 + ((c + 1) * 4 + i) * pe_st);
-              }
-              uint32_t v[32];
-              __syncwarp();
-              tmem_ld_x32(ta + c * 32, v);
-              tmem_ld_wait();
-              {  // every lane computes (rows past the end hold zeros / stale table values and are masked at the store)
-                float f[32];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
-                  if (F8) {
-                    const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
-                    f[i] = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); f[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
-                    f[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); f[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
-                  } else {
-                  f[i] = __uint_as_float(v[i]) + t.x; f[i + 1] = __uint_as_float(v[i + 1]) + t.y;
-                  f[i + 2] = __uint_as_float(v[i + 2]) + t.z; f[i + 3] = __uint_as_float(v[i + 3]) + t.w;
-                  }
-                }
-                if (which < 2) {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(sg + c * 32 + i * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sg + c * 32 + i * 8 + 4);
-                    const float wt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                    const uint32_t pw[4] = {pcur[i].x, pcur[i].y, pcur[i].z, pcur[i].w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 cs = unpack_bf16(pw[j]);  // (cos, sin)
-                      const float x0 = f[i * 8 + 2 * j] * rr * wt[2 * j];
-                      const float x1 = f[i * 8 + 2 * j + 1] * rr * wt[2 * j + 1];
-                      f[i * 8 + 2 * j] = x0 * cs.x - x1 * cs.y;
-                      f[i * 8 + 2 * j + 1] = x0 * cs.y + x1 * cs.x;
-                    }
-                  }
-                }
-                if (p.qkv_f8) {  // 32 e4m3 bytes of this row: two full 16-byte vectors (rows are 128 bytes apart)
-                  if (valid) {
-                    uint32_t w8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                      const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i], f[4 * i + 1]), __NV_SATFINITE, __NV_E4M3);
-                      const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2], f[4 * i + 3]), __NV_SATFINITE, __NV_E4M3);
-                      w8[i] = uint32_t(lo) | (uint32_t(hi) << 16);
-                    }
-                    uint8_t* d8 = reinterpret_cast<uint8_t*>(which == 0 ? p.q : (which == 1 ? p.k : p.v)) +
-                                  (((long long)b * p.heads + head) * p.seq_total + pos) * 128 + c * 32;
-                    *reinterpret_cast<uint4*>(d8) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
-                    *reinterpret_cast<uint4*>(d8 + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
-                  }
-                } else {
-                  store_chunk32_coalesced(wst, lane, f, dst - (long long)lane * 128 + c * 32, 128, vmask, p.stream_out != 0);
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 4; ++i) pcur[i] = pnxt[i];
-            }
-          }
-        }
+        QkvPre pre;
+        epi_qkv_prefetch<F8>(p, b, row, valid, lane, tn * BN + half * 128, pre);
+        epi_qkv_group<F8>(p, b, row, valid, vmask, lane, taddr + half * 128, tn * BN + half * 128, sb, sg, sw, wst, &tfull_bar[acc],
+                          acc_phase, pre, QkvNext{false, 0, 0, false, 0});
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above)
       tc_fence_before();

@@ -27,24 +27,27 @@
 
 namespace fx {
 
-constexpr int G4_BN = 192;
+constexpr int G4_BN = 192;                      // generic epilogue tiles; the QKV epilogue uses 128-column tiles (= one head)
 constexpr int G4_A_BYTES = 128 * 128;           // 128 rows x 256 e2m1
 constexpr int G4_SFA_BYTES = 4 * 512;           // 4 K-groups (of 64 elements) x one 128-row atom
-constexpr int G4_SFB_BYTES = 4 * 2 * 512;       // 4 K-groups x two atoms (192 rows): the WHOLE tile's columns, in every CTA
-template <int NCTA>
+template <int NCTA, int BN>
 struct G4Cfg {
-  // NCTA = 2: a CTA pair computes a 256 x 192 tile with cta_group::2 MMAs; each CTA stages its 128 A rows, HALF of the W
-  // tile (96 rows) and the scale atoms of its own A rows and of ALL 192 W rows (tcgen05.cp.cta_group::2 copies, in each CTA,
-  // from that CTA's shared memory into that CTA's TMEM: tests/gpu_bs_probe.py pair)
-  static constexpr int STAGES = NCTA == 2 ? 5 : 4;
-  static constexpr int B_BYTES = (G4_BN / NCTA) * 128;
-  static constexpr int STAGE_BYTES = G4_A_BYTES + B_BYTES + G4_SFA_BYTES + G4_SFB_BYTES;
+  // NCTA = 2: a CTA pair computes a 256 x BN tile with cta_group::2 MMAs; each CTA stages its 128 A rows, HALF of the W
+  // tile and the scale atoms of its own A rows and of ALL BN W rows (tcgen05.cp.cta_group::2 copies, in each CTA, from
+  // that CTA's shared memory into that CTA's TMEM: tests/gpu_bs_probe.py pair)
+  static constexpr int NSFB = (BN + 127) / 128;             // W scale atoms per K-group: the WHOLE tile's columns, in every CTA
+  static constexpr int SFB_BYTES = 4 * NSFB * 512;
+  static constexpr int B_BYTES = (BN / NCTA) * 128;
+  static constexpr int STAGE_BYTES = G4_A_BYTES + B_BYTES + G4_SFA_BYTES + SFB_BYTES;
+  static constexpr int TAIL = 256 + 8 * 384 * 4 + 8 * 2048 + 1024;   // barriers, epilogue vectors, store staging, alignment
+  static constexpr int STAGES = (232448 - TAIL) / STAGE_BYTES;        // 5 / 4 (BN 192: pair / single), 7 / 5 (BN 128)
   static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;
   static constexpr int STORE_OFF = EPI_OFF + 8 * 384 * 4;
   static constexpr int SMEM = STORE_OFF + 8 * 2048 + 1024;
+  static constexpr int TMEM_SF = 2 * BN;                    // scale-factor slots start behind the two accumulators
+  static constexpr int SF_SLOT = 16 + 16 * NSFB;            // 16 columns of A scales + 16 per W atom row, per stage
+  static_assert(TMEM_SF + 2 * SF_SLOT <= 512 && STAGES >= 3, "TMEM / shared memory budget");
 };
-constexpr int G4_TMEM_SF = 2 * G4_BN;           // scale-factor slots start behind the two accumulators
-constexpr int G4_SF_SLOT = 48;                  // 16 columns of A scales + 32 of W scales per stage
 
 __device__ __forceinline__ uint64_t make_smem_desc_sf(uint32_t smem_addr) {  // no swizzle, SBO = 128 B (8 rows x 16 B), version 1
   return uint64_t((smem_addr & 0x3FFFF) >> 4) | (uint64_t(128 >> 4) << 32) | (uint64_t(1) << 46);
@@ -83,15 +86,16 @@ struct Gemm4Params {
 // tmap_sfa / tmap_sfb: the scale-atom buffers viewed as [bytes / 128][128] byte matrices (no swizzle): one stage's atoms of a
 // row block / column tile are 16 / 32 consecutive rows, fetched by TMA like the operands (and, for a pair, credited to the
 // leader's barrier like them)
-template <int NCTA>
+template <int NCTA, int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb, const Gemm4Params q) {
   const GemmParams& p = q.g;
-  using Cfg = G4Cfg<NCTA>;
-  constexpr int BN = G4_BN, STAGES = Cfg::STAGES;
+  using Cfg = G4Cfg<NCTA, BN>;
+  constexpr int STAGES = Cfg::STAGES, NSFB = Cfg::NSFB;
+  static_assert(EPI == EPI_GENERIC || BN == 128, "the QKV epilogue works on one head (128 columns) per tile");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -113,7 +117,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8 * NCTA);
+      mbar_init(&tempty_bar[s], (EPI == EPI_QKV ? 4 : 8) * NCTA);
     }
     fence_barrier_init();
   }
@@ -150,7 +154,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             uint8_t* ssfa = sb + Cfg::B_BYTES;
             uint8_t* ssfb = ssfa + G4_SFA_BYTES;
             const int sfa_row = (rb * q.k_groups + kb * 4) * 4;          // 4 rows of 128 B per atom
-            const int sfb_row = (tn * q.k_groups + kb * 4) * 8;          // two atoms per K-group
+            const int sfb_row = (tn * q.k_groups + kb * 4) * 4 * NSFB;   // NSFB atoms per K-group
             if (!elect_one()) {
             } else if (NCTA == 2) {
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
@@ -192,18 +196,18 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t sb = sa + G4_A_BYTES;
             const uint32_t ssfa = sb + Cfg::B_BYTES, ssfb = ssfa + G4_SFA_BYTES;
             // tcgen05.cp and tcgen05.mma execute in issue order: slot (n & 1) was last read by the MMAs of stage n - 2
-            const uint32_t t_sfa = tbase + G4_TMEM_SF + (n & 1) * G4_SF_SLOT, t_sfb = t_sfa + 16;
+            const uint32_t t_sfa = tbase + Cfg::TMEM_SF + (n & 1) * Cfg::SF_SLOT, t_sfb = t_sfa + 16;
             if (elect_one()) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 tc_cp_sf<NCTA>(t_sfa + g * 4, make_smem_desc_sf(ssfa + g * 512));
-                tc_cp_sf<NCTA>(t_sfb + g * 8, make_smem_desc_sf(ssfb + g * 1024));
-                tc_cp_sf<NCTA>(t_sfb + g * 8 + 4, make_smem_desc_sf(ssfb + g * 1024 + 512));
+#pragma unroll
+                for (int h = 0; h < NSFB; ++h) tc_cp_sf<NCTA>(t_sfb + (g * NSFB + h) * 4, make_smem_desc_sf(ssfb + (g * NSFB + h) * 512));
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_nvf4<NCTA>(d_tmem, make_smem_desc_sw128(sa + k * 32, 16, 1024), make_smem_desc_sw128(sb + k * 32, 16, 1024), idesc,
-                                (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 8);
+                                (kb | k) != 0 ? 1u : 0u, t_sfa + k * 4, t_sfb + k * 4 * NSFB);
               if (NCTA == 2) tc_commit2(&empty_bar[stage]);
               else tc_commit(&empty_bar[stage]);
             }
@@ -232,7 +236,48 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     constexpr int CH = BN / 64, WN = BN / 2;
+    // The tile's main loop is short at 4-bit MAC rates (K = 3072: ~4600 clocks), so the epilogue must not expose latencies:
+    //  * the tile-uniform vectors (bias, column scales, gate) and the row scale of the NEXT tile are fetched into registers
+    //    before this tile's chunk loop and written to the staging slots after it (pre_*: one global round trip per tile, hidden);
+    //  * inside the chunk loop the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed.
+    float pre_b[CH], pre_w[CH], pre_g[CH], pre_rs = 1.f;
+    auto prefetch = [&](int tile) {
+      int tm, tn;
+      gemm_tile_coords(p, tile, tm, tn);
+      const int b = tm / p.tiles_m_per_batch;
+      const long long row = (long long)(tm - b * p.tiles_m_per_batch) * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
+      const int nw0 = tn * BN + half * WN;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int n = nw0 + i * 32 + lane;
+        const bool in = n < p.N;
+        pre_b[i] = (p.bias != nullptr && in) ? __bfloat162float(__ldg(p.bias + n)) : 0.f;
+        pre_w[i] = in ? __ldg(p.w_scale + n) : 0.f;
+        pre_g[i] = (p.gate != nullptr && in) ? __bfloat162float(__ldg(p.gate + (long long)b * p.gate_bs + n)) : 1.f;
+      }
+      pre_rs = row < p.rows ? __ldg(p.a_scale + (long long)b * p.a_scale_bs + row) : 1.f;
+    };
+    // QKV: a tile is one head; the two warp groups take alternate accumulators, i.e. every other tile of the CTA's queue
+    QkvPre qpre;
+    auto qkv_coords = [&](int tile, QkvNext& n) {
+      int tm, tn;
+      gemm_tile_coords(p, tile, tm, tn);
+      n.b = tm / p.tiles_m_per_batch;
+      n.row = (long long)(tm - n.b * p.tiles_m_per_batch) * (GEMM_BM * NCTA) + cta_rank * GEMM_BM + r;
+      n.valid = n.row < p.rows;
+      n.g0 = tn * BN;
+    };
+    if (EPI == EPI_GENERIC && first_tile < p.num_tiles) prefetch(first_tile);
+    if (EPI == EPI_QKV && first_tile + half * tile_stride < p.num_tiles) {
+      QkvNext n;
+      qkv_coords(first_tile + half * tile_stride, n);
+      epi_qkv_prefetch<true>(p, n.b, n.row, n.valid, lane, n.g0, qpre);
+    }
     for (int tile = first_tile; tile < p.num_tiles; tile += tile_stride) {
+      if (EPI == EPI_QKV && half != acc) {
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       int tm, tn;
       gemm_tile_coords(p, tile, tm, tn);
       const int b = tm / p.tiles_m_per_batch;
@@ -241,45 +286,60 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const bool valid = row < p.rows;
       const uint32_t taddr = tmem_base + acc * BN + (uint32_t(quarter * 32) << 16);
       const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-      const int nw0 = tn * BN + half * WN;
-      const long long out_off = (long long)b * p.out_bs + row * p.ldo;
-      const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
-      const bool vec_ok = ((p.ldo | p.ldr) & 7) == 0;
-      __syncwarp();
-      stage_vec(sb, p.bias, nw0, WN, p.N, 0.f, lane);
-      if (p.gate) stage_vec(sg, p.gate + (long long)b * p.gate_bs, nw0, WN, p.N, 1.f, lane);
-      stage_vec_f32(sw, p.w_scale, nw0, WN, p.N, 0.f, lane);
-      const float rs = valid ? __ldg(p.a_scale + (long long)b * p.a_scale_bs + row) : 1.f;
-      const bool rr_ok = p.resid != nullptr && valid && vec_ok && (nw0 + WN <= p.N);
-      uint4 rcur[4], rnxt[4];
-      if (rr_ok) {
+      if (p.dbg_skip_w) {  // FX_GEMM4_DBG_NOEPI=1 (measurement only): the main loop without the epilogue's work
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      } else if (EPI == EPI_QKV) {
+        QkvNext n;
+        n.has = tile + 2 * tile_stride < p.num_tiles;
+        if (n.has) qkv_coords(tile + 2 * tile_stride, n);
+        epi_qkv_group<true>(p, b, row, valid, vmask, lane, taddr, tn * BN, sb, sg, sw, wst, &tfull_bar[acc], acc_phase, qpre, n);
+      } else {
+        const int nw0 = tn * BN + half * WN;
+        const long long out_off = (long long)b * p.out_bs + row * p.ldo;
+        const long long res_off = (long long)b * p.resid_bs + row * p.ldr;
+        const bool vec_ok = ((p.ldo | p.ldr) & 7) == 0;
+        __syncwarp();   // the previous tile's chunk loop is done with the staging slots
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rcur[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + nw0 + i * 8);
-      }
-      __syncwarp();
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < CH; ++c) {
-        const int n0 = nw0 + c * 32;
-        if (n0 >= p.N) break;
-        if (rr_ok && c + 1 < CH) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rnxt[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + n0 + 32 + i * 8);
+        for (int i = 0; i < CH; ++i) {
+          sb[i * 32 + lane] = pre_b[i];
+          sw[i * 32 + lane] = pre_w[i];
+          sg[i * 32 + lane] = pre_g[i];
         }
-        uint32_t v[32];
+        const float rs = pre_rs;
+        const bool rr_ok = p.resid != nullptr && valid && vec_ok && (nw0 + WN <= p.N);
+        uint4 rcur[4], rnxt[4];
+        if (rr_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rcur[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + nw0 + i * 8);
+        }
+        if (tile + tile_stride < p.num_tiles) prefetch(tile + tile_stride);
         __syncwarp();
-        tmem_ld_x32(taddr + half * WN + c * 32, v);
-        tmem_ld_wait();
-        {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld_x32(taddr + half * WN, v);
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+          const int n0 = nw0 + c * 32;
+          if (n0 >= p.N) {
+            tmem_ld_wait_x32(v);
+            break;
+          }
+          if (rr_ok && c + 1 < CH) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rnxt[i] = *reinterpret_cast<const uint4*>(p.resid + res_off + n0 + 32 + i * 8);
+          }
           float f[32];
+          tmem_ld_wait_x32(v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (c + 1 < CH) tmem_ld_x32(taddr + half * WN + (c + 1) * 32, v);   // in flight while this chunk is processed
           epi_generic_chunk<true>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0, vec_ok && (n0 + 32 <= p.N),
                                   sw + c * 32, rs, wst, lane, vmask, valid);
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
+          for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -409,11 +469,11 @@ static int make_tmap_sf(CUtensorMap* out, const void* base, uint64_t bytes, uint
   return FX_OK;
 }
 
-template <int NCTA>
+template <int NCTA, int BN, int EPI>
 static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tsa, const CUtensorMap& tsb, const Gemm4Params& q,
                       cudaStream_t st) {
-  using Cfg = G4Cfg<NCTA>;
-  auto kern = gemm_nvfp4_kernel<NCTA>;
+  using Cfg = G4Cfg<NCTA, BN>;
+  auto kern = gemm_nvfp4_kernel<NCTA, BN, EPI>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM); });
@@ -440,56 +500,102 @@ static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
   return launched("gemm_nvfp4_kernel");
 }
 
+// CTA pairs (256-row tiles) when every batch element is a whole number of 256-row tiles; FX_GEMM4_NCTA=1 forces single CTAs
+static int fp4_ncta(int rows) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("FX_GEMM4_NCTA");
+    forced = e ? atoi(e) : 0;
+  }
+  return (forced == 1 || rows % 256 != 0) ? 1 : 2;
+}
+
+// shapes, tiling and the four tensor maps shared by the two entry points (bn = column tile: 192 generic, 128 QKV)
+static int fp4_setup(Gemm4Params& q, const void* A, const void* sfa, const void* W, const void* sfw, int batch, int rows, int N, int K,
+                     int bn, int ncta, CUtensorMap* ta, CUtensorMap* tw, CUtensorMap* tsa, CUtensorMap* tsb) {
+  GemmParams& p = q.g;
+  p.batch = batch; p.rows = rows; p.N = N; p.K = K;
+  p.k_blocks = K / 256;
+  q.k_groups = K / 64;
+  p.a_scale_bs = rows;
+  p.tiles_m_per_batch = (rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta);
+  p.tiles_m = p.tiles_m_per_batch * batch;
+  p.tiles_n = (N + bn - 1) / bn;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  p.group_m = p.tiles_m < 8 ? p.tiles_m : 8;
+  p.group_n = 0;
+  p.stream_out = 1;
+  {
+    const char* e = getenv("FX_GEMM4_DBG_NOEPI");
+    p.dbg_skip_w = (e && atoi(e)) ? 1 : 0;
+  }
+  const uint64_t rows_total = (uint64_t)batch * rows;
+  {  // A: flattened rows [batch * rows][K / 2] bytes (the quantiser writes a compact operand)
+    const uint64_t dims[2] = {(uint64_t)K / 2, rows_total};
+    const uint64_t strides[1] = {(uint64_t)K / 2};
+    const uint32_t box[2] = {128, GEMM_BM};
+    int rc = make_tmap_bf16(ta, A, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)K / 2, (uint64_t)N};
+    const uint64_t strides[1] = {(uint64_t)K / 2};
+    const uint32_t box[2] = {128, (uint32_t)(bn / ncta)};
+    int rc = make_tmap_bf16(tw, W, 2, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  const int nsfb = (bn + 127) / 128;
+  int rc = make_tmap_sf(tsa, sfa, ((rows_total + 127) / 128) * (uint64_t)q.k_groups * 512, 16);
+  if (rc) return rc;
+  return make_tmap_sf(tsb, sfw, (uint64_t)p.tiles_n * q.k_groups * nsfb * 512, 16 * nsfb);
+}
+
 extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
   FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && a->out, "fx_gemm_fp4: null pointer");
   FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm_fp4: empty problem");
   FX_REQUIRE(a->K % 256 == 0, "fx_gemm_fp4: K (%d) must be a multiple of 256", a->K);
   FX_REQUIRE(a->rows % 128 == 0 || a->batch == 1, "fx_gemm_fp4: rows per batch element (%d) must be a multiple of 128", a->rows);
   FX_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->sfa) && aligned16(a->sfw), "fx_gemm_fp4: operands must be 16-byte aligned");
-  // CTA pairs (256 x 192 tiles) when every batch element is a whole number of 256-row tiles; FX_GEMM4_NCTA=1 forces single CTAs
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("FX_GEMM4_NCTA");
-    forced = e ? atoi(e) : 0;
-  }
-  const int ncta = (forced == 1 || a->rows % 256 != 0) ? 1 : 2;
+  const int ncta = fp4_ncta(a->rows);
   Gemm4Params q{};
   GemmParams& p = q.g;
-  p.batch = a->batch; p.rows = a->rows; p.N = a->N; p.K = a->K;
-  p.k_blocks = a->K / 256;
-  q.k_groups = a->K / 64;
-  p.a_scale = a->a_scale; p.a_scale_bs = a->rows; p.w_scale = a->w_scale;
+  CUtensorMap ta, tw, tsa, tsb;
+  int rc = fp4_setup(q, a->A, a->sfa, a->W, a->sfw, a->batch, a->rows, a->N, a->K, G4_BN, ncta, &ta, &tw, &tsa, &tsb);
+  if (rc) return rc;
+  p.a_scale = a->a_scale; p.w_scale = a->w_scale;
   p.bias = (const __nv_bfloat16*)a->bias;
   p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
-  p.tiles_m_per_batch = (a->rows + GEMM_BM * ncta - 1) / (GEMM_BM * ncta);
-  p.tiles_m = p.tiles_m_per_batch * a->batch;
-  p.tiles_n = (a->N + G4_BN - 1) / G4_BN;
-  p.num_tiles = p.tiles_m * p.tiles_n;
-  p.group_m = p.tiles_m < 8 ? p.tiles_m : 8;
-  p.group_n = 0;
-  p.stream_out = 1;
-  const uint64_t rows_total = (uint64_t)a->batch * a->rows;
+  if (ncta == 2) return launch_fp4<2, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  return launch_fp4<1, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+}
+
+extern "C" int fx_gemm_fp4_qkv(const fx_gemm4_qkv_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && a->q && a->k && a->v && a->pe && a->q_scale && a->k_scale,
+             "fx_gemm_fp4_qkv: null pointer");
+  FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->K > 0 && a->heads > 0, "fx_gemm_fp4_qkv: empty problem");
+  FX_REQUIRE(a->K % 256 == 0, "fx_gemm_fp4_qkv: K (%d) must be a multiple of 256", a->K);
+  FX_REQUIRE(a->rows % 128 == 0 || a->batch == 1, "fx_gemm_fp4_qkv: rows per batch element (%d) must be a multiple of 128", a->rows);
+  FX_REQUIRE(a->seq_off >= 0 && a->seq_off + a->rows <= a->seq_total, "fx_gemm_fp4_qkv: rows exceed seq_total");
+  FX_REQUIRE(!a->pe_blocked || (a->seq_off % 32 == 0), "fx_gemm_fp4_qkv: the blocked pe layout needs seq_off %% 32 == 0");
+  FX_REQUIRE(aligned16(a->A) && aligned16(a->W) && aligned16(a->sfa) && aligned16(a->sfw) && aligned16(a->pe),
+             "fx_gemm_fp4_qkv: operands must be 16-byte aligned");
+  FX_REQUIRE(!a->qkv_fp8 || (aligned16(a->q) && aligned16(a->k) && aligned16(a->v)), "fx_gemm_fp4_qkv: q/k/v must be 16-byte aligned");
+  const int ncta = fp4_ncta(a->rows);
+  Gemm4Params q{};
+  GemmParams& p = q.g;
   CUtensorMap ta, tw, tsa, tsb;
-  {  // A: flattened rows [batch * rows][K / 2] bytes (the quantiser writes a compact operand)
-    const uint64_t dims[2] = {(uint64_t)a->K / 2, rows_total};
-    const uint64_t strides[1] = {(uint64_t)a->K / 2};
-    const uint32_t box[2] = {128, GEMM_BM};
-    int rc = make_tmap_bf16(&ta, a->A, 2, dims, strides, box, true);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[2] = {(uint64_t)a->K / 2, (uint64_t)a->N};
-    const uint64_t strides[1] = {(uint64_t)a->K / 2};
-    const uint32_t box[2] = {128, (uint32_t)(G4_BN / ncta)};
-    int rc = make_tmap_bf16(&tw, a->W, 2, dims, strides, box, true);
-    if (rc) return rc;
-  }
-  int rc = make_tmap_sf(&tsa, a->sfa, ((rows_total + 127) / 128) * (uint64_t)q.k_groups * 512, 16);
+  int rc = fp4_setup(q, a->A, a->sfa, a->W, a->sfw, a->batch, a->rows, 3 * a->heads * 128, a->K, 128, ncta, &ta, &tw, &tsa, &tsb);
   if (rc) return rc;
-  rc = make_tmap_sf(&tsb, a->sfw, (uint64_t)p.tiles_n * q.k_groups * 1024, 32);
-  if (rc) return rc;
-  if (ncta == 2) return launch_fp4<2>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
-  return launch_fp4<1>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  p.a_scale = a->a_scale; p.w_scale = a->w_scale;
+  p.bias = (const __nv_bfloat16*)a->bias;
+  p.heads = a->heads; p.seq_total = a->seq_total; p.seq_off = a->seq_off; p.rms_eps = a->rms_eps;
+  p.qnorm_w = (const __nv_bfloat16*)a->q_scale; p.knorm_w = (const __nv_bfloat16*)a->k_scale;
+  p.pe = (const uint32_t*)a->pe;
+  p.pe_blocked = a->pe_blocked;
+  p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
+  p.qkv_f8 = a->qkv_fp8 ? 1 : 0;
+  if (ncta == 2) return launch_fp4<2, 128, EPI_QKV>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  return launch_fp4<1, 128, EPI_QKV>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
 }

@@ -176,6 +176,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo, uint32_t hi) {
   return d;
 }
 // one lane of a converged warp (the lowest): the thread that issues tcgen05.mma / commit / TMA
+// 1024-byte aligned start inside the dynamic shared memory window (SWIZZLE_128B tiles need it).  Written as base + integer
+// offset -- NOT as a round trip through uintptr_t -- so that the compiler keeps the shared address space of everything derived
+// from it: LDS / STS instead of generic LD.E / ST.E (which are tracked on the long scoreboard) in the epilogues.
+__device__ __forceinline__ uint8_t* smem_align1024(uint8_t* smem_raw) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_raw));
+  return smem_raw + ((1024u - (a & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -319,6 +327,17 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The wait as a read-modify-write of the 32 destination registers: when a tcgen05.ld stays in flight across other work
+// (software-pipelined epilogues), the compiler must not read -- or copy -- the registers before this point.
+__device__ __forceinline__ void tmem_ld_wait_x32(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "

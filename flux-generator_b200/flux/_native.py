@@ -75,6 +75,13 @@ class Gemm4Args(C.Structure):
                 ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32)]
 
 
+class Gemm4QkvArgs(C.Structure):
+    _fields_ = [("A", c_vp), ("sfa", c_vp), ("a_scale", c_vp), ("W", c_vp), ("sfw", c_vp), ("w_scale", c_vp), ("bias", c_vp),
+                ("q_scale", c_vp), ("k_scale", c_vp), ("pe", c_vp), ("pe_blocked", c_i32),
+                ("q", c_vp), ("k", c_vp), ("v", c_vp), ("qkv_fp8", c_i32), ("rms_eps", C.c_float),
+                ("batch", c_i32), ("rows", c_i32), ("K", c_i32), ("heads", c_i32), ("seq_total", c_i32), ("seq_off", c_i32)]
+
+
 class GemvArgs(C.Structure):
     _fields_ = [("in_", c_vp), ("ld_in", c_i64), ("W", c_vp), ("ldw", c_i64), ("bias", c_vp), ("add", c_vp),
                 ("ld_add", c_i64), ("out", c_vp), ("ld_out", c_i64), ("batch", c_i32), ("N", c_i32), ("K", c_i32),
@@ -91,6 +98,7 @@ SYMBOLS = {
     "fx_gemm_qkv": (C.c_int, [C.POINTER(QkvArgs), c_vp]),
     "fx_quantize_rows_fp4": (C.c_int, [C.POINTER(Quant4Args), c_vp]),
     "fx_gemm_fp4": (C.c_int, [C.POINTER(Gemm4Args), c_vp]),
+    "fx_gemm_fp4_qkv": (C.c_int, [C.POINTER(Gemm4QkvArgs), c_vp]),
     "fx_conv3x3": (C.c_int, [C.POINTER(ConvArgs), c_vp]),
     "fx_conv3x3_gn_blocks": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "fx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

@@ -113,7 +113,8 @@ class Flux:
         self._txt_cache: Optional[tuple] = None
         self._q8: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}  # --quantize: key -> (e4m3 weight, fp32 row scales)
         self._q8_attention = False                                  # --quantize: Q K^T and P V in FP8 as well
-        self._q4: Dict[str, tuple] = {}   # --quantize 4: key -> (e2m1 weight, scale atoms, fp32 row scales) of the K-long Linears
+        self._q4: Dict[str, tuple] = {}   # --quantize 4: key -> (e2m1 weight, scale atoms, fp32 row scales)
+        self._q4_all = False              # ... of every block Linear (fp4_scope "all") or only of fp4_keys() ("cat")
         self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
         self._lora_pending: Dict[str, torch.Tensor] = {}       # adapter tensors loaded but not yet fused
 
@@ -164,7 +165,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:  # weights changed under a quantised model: requantise
             self._q8 = {}
-            self.quantize(self._q8_attention, 4 if self._q4 else 8)
+            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat")
         return self
 
     # ------------------------------------------------------------------ LoRA adapters (txt2image.py:32-39)
@@ -192,7 +193,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:
             self._q8 = {}
-            self.quantize(self._q8_attention, 4 if self._q4 else 8)
+            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat")
         return len(deltas)
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
@@ -222,19 +223,36 @@ class Flux:
         keys += [f"single_blocks.{i}.linear2" for i in range(p.depth_single_blocks)]
         return keys
 
-    def quantize(self, attention: bool = True, bits: int = 8) -> "Flux":
+    def quantize(self, attention: bool = True, bits: int = 8, fp4_scope: str = "all") -> "Flux":
         """Quantise the block Linears to FP8 e4m3 with one scale per output channel (fx_quantize_rows) and switch
         forward() to the FP8 tcgen05 path: activations are row-quantised by the producing norm kernel (or one
         extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16.
         attention=True: the QKV epilogue writes q, k, v as e4m3 and the attention kernel runs Q K^T and P V on
         kind::f8f6f4 too (P converted to e4m3 with a 2^4 scale; softmax statistics stay fp32).
-        bits=4: additionally the Linears of fp4_keys() run as NVFP4 W4A4 (e2m1 + UE4M3 block scales + fp32 row scales,
+        bits=4: the block Linears run as NVFP4 W4A4 (e2m1 + UE4M3 block scales + fp32 row scales,
         tcgen05.mma.kind::mxf4nvf4.block_scale; csrc/gemm4.cu) -- the analogue of the reference's 4-bit
-        nn.quantize(group_size=64) (txt2image.py:28-29,79-82); everything else stays FP8."""
+        nn.quantize(group_size=64) (txt2image.py:28-29,79-82).  fp4_scope "all": every block Linear (qkv, proj, mlp.0,
+        mlp.2, linear1, linear2); "cat": only fp4_keys(), the rest stays FP8.  Shapes the NVFP4 kernel does not tile
+        (token counts that are not multiples of 128) fall back to the FP8 Linears, which are always prepared."""
         if bits not in (4, 8):
             raise ValueError("quantize(bits=...) must be 8 or 4")
+        if fp4_scope not in ("all", "cat"):
+            raise ValueError("quantize(fp4_scope=...) must be 'all' or 'cat'")
         self._q8_attention = bool(attention)
         self._q4 = {k: ops.fp4_weight(self._w(k)) for k in self.fp4_keys()} if bits == 4 else {}
+        self._q4_all = bits == 4 and fp4_scope == "all"
+        if self._q4_all:
+            p, D3 = self.params, 3 * self.hidden_size
+            for i in range(p.depth):
+                for s in ("img", "txt"):
+                    k = f"double_blocks.{i}.{s}_attn.qkv"
+                    self._q4[k] = ops.fp4_weight(self._w(k), ops.FP4_TILE_N_QKV)   # one head per column tile
+                    k = f"double_blocks.{i}.{s}_mlp.0"
+                    self._q4[k] = ops.fp4_weight(self._w(k))
+            for i in range(p.depth_single_blocks):   # linear1 = qkv rows (QKV epilogue) | mlp rows (GELU into the cat buffer)
+                k = f"single_blocks.{i}.linear1"
+                self._q4[k + ".qkv"] = ops.fp4_weight(self._w(k)[:D3], ops.FP4_TILE_N_QKV)
+                self._q4[k + ".mlp"] = ops.fp4_weight(self._w(k)[D3:])
         keys = self.quantized_keys()
         total = sum(self._shape(k + ".weight")[0] * self._shape(k + ".weight")[1] for k in keys)
         rows = sum(self._shape(k + ".weight")[0] for k in keys)
@@ -256,6 +274,7 @@ class Flux:
         """Back to the bf16 Linears (drops the FP8 copies; the bf16 arena was never modified)."""
         self._q8 = {}
         self._q4 = {}
+        self._q4_all = False
         self._q8_attention = False
         self._graphs.clear()
         self._ws.clear()
@@ -489,16 +508,25 @@ class Flux:
         if self._q8_attention:
             q, k, v = ws["q8"], ws["k8"], ws["v8"]
         xm, xm8, cat8, xs, cs = ws["xm"], ws["xm8"], ws["cat8"], ws["xs"], ws["cs"]
+        B = x.shape[0]
+        f4 = self._q4_all and "a4" in ws   # NVFP4 for the norm-fed Linears too: bf16 row norm, then the NVFP4 row quantiser
         for i in range(p.depth):
             pre = f"double_blocks.{i}."
             streams = (("img", slice(S, None), S), ("txt", slice(0, S), 0))
             for name, rows, off in streams:
                 mk = pre + name + "_mod.lin"
                 ak = pre + name + "_attn."
+                qn, kn = self.arena[ak + "norm.query_norm.scale"], self.arena[ak + "norm.key_norm.scale"]
+                if f4:
+                    ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, rows])
+                    a4, sfa, sa = ops.quantize_rows_fp4(xm[:, rows], out=ws["a4"])
+                    w4, sfw, sw = self._q4[ak + "qkv"]
+                    ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, self._b(ak + "qkv"), qn, kn, pe, q, k, v, off, rms_eps=QK_RMS_EPS,
+                                     pe_blocked=pe_blocked)
+                    continue
                 ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
                 w8, wsc = self._q8[ak + "qkv"]
-                ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), self.arena[ak + "norm.query_norm.scale"],
-                             self.arena[ak + "norm.key_norm.scale"], pe, q, k, v, off, rms_eps=QK_RMS_EPS,
+                ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), qn, kn, pe, q, k, v, off, rms_eps=QK_RMS_EPS,
                              a_scale=xs[:, rows], w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, rows, off in streams:
@@ -507,18 +535,34 @@ class Flux:
                 mlp = pre + name + "_mlp."
                 xr = x[:, rows]
                 self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
-                ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
-                w8, wsc = self._q8[mlp + "0"]
-                ops.gemm(xm8[:, rows], w8, self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:], a_scale=xs[:, rows], w_scale=wsc)
+                if f4:
+                    ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm[:, rows])
+                    a4, sfa, sa = ops.quantize_rows_fp4(xm[:, rows], out=ws["a4"])
+                    w4, sfw, sw = self._q4[mlp + "0"]
+                    ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:])
+                else:
+                    ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
+                    w8, wsc = self._q8[mlp + "0"]
+                    ops.gemm(xm8[:, rows], w8, self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:], a_scale=xs[:, rows], w_scale=wsc)
                 self._cat_gemm(ws, mlp + "2", cat[:, rows, D:], cat8[:, rows, D:], cs[:, rows], self._mod(ws, mk, 5), xr)
         for i in range(p.depth_single_blocks):
             pre = f"single_blocks.{i}."
             mk = pre + "modulation.lin"
-            ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8, out_scale=xs)
-            w8, wsc = self._q8[pre + "linear1"]
-            ops.gemm_qkv(xm8, w8, self._b(pre + "linear1"), self.arena[pre + "norm.query_norm.scale"],
-                         self.arena[pre + "norm.key_norm.scale"], pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
-                         a_scale=xs, w_scale=wsc, pe_blocked=pe_blocked)
+            qn, kn = self.arena[pre + "norm.query_norm.scale"], self.arena[pre + "norm.key_norm.scale"]
+            if f4:
+                ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
+                a4, sfa, sa = ops.quantize_rows_fp4(xm, out=ws["a4"])
+                bias = self._b(pre + "linear1")
+                w4, sfw, sw = self._q4[pre + "linear1.qkv"]
+                ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, None if bias is None else bias[:3 * D], qn, kn, pe, q, k, v, 0,
+                                 rms_eps=QK_RMS_EPS, pe_blocked=pe_blocked)
+                w4, sfw, sw = self._q4[pre + "linear1.mlp"]
+                ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=None if bias is None else bias[3 * D:], act="gelu_tanh", out=cat[:, :, D:])
+            else:
+                ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8, out_scale=xs)
+                w8, wsc = self._q8[pre + "linear1"]
+                ops.gemm_qkv(xm8, w8, self._b(pre + "linear1"), qn, kn, pe, q, k, v, 0, mlp_out=cat[:, :, D:], rms_eps=QK_RMS_EPS,
+                             a_scale=xs, w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             self._cat_gemm(ws, pre + "linear2", cat, cat8, cs, self._mod(ws, mk, 2), x)
 
@@ -554,7 +598,7 @@ class Flux:
         S = txt.shape[1]
         pe, _ = self._pe(txt_ids, img_ids)
         temb = self._txt_in(txt.to(bf16) if txt.dtype != bf16 else txt)
-        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8), bool(self._q4))
+        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8), bool(self._q4), self._q4_all)
         g = self._graphs.get(key)
         if g is None:
             D = self.hidden_size

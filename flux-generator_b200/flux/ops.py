@@ -314,23 +314,55 @@ def quantize_rows_fp4(x: torch.Tensor, out=None):
     return q, sf, scale
 
 
-FP4_TILE_N = 192  # column tile of the NVFP4 GEMM (csrc/gemm4.cu)
+FP4_TILE_N = 192      # column tile of the NVFP4 GEMM with the generic epilogue (csrc/gemm4.cu)
+FP4_TILE_N_QKV = 128  # ... with the QKV epilogue: one head per tile
 
 
-def fp4_weight(w: torch.Tensor):
-    """Linear weight bf16 [N, K] -> (w4 uint8 [N, K/2], scale atoms regrouped per 192-row column tile
-    [ceil(N/192), K/64, 2, 512], w_scale fp32 [N]) for gemm_fp4 (done once, at Flux.quantize)."""
+def fp4_weight(w: torch.Tensor, tile_n: int = FP4_TILE_N):
+    """Linear weight bf16 [N, K] -> (w4 uint8 [N, K/2], scale atoms regrouped per `tile_n`-row column tile
+    [ceil(N/tile_n), K/64, ceil(tile_n/128), 512], w_scale fp32 [N]) for gemm_fp4 (tile_n = 192) / gemm_fp4_qkv (128);
+    done once, at Flux.quantize."""
     Nn, K = w.shape
     q, sf, scale = quantize_rows_fp4(w)
     m = sf_atoms_to_matrix(sf, K)[:Nn]                                   # [N, K/16]
-    tiles = (Nn + FP4_TILE_N - 1) // FP4_TILE_N
-    pad = torch.zeros((tiles, 256, K // 16), device=w.device, dtype=torch.uint8)
-    full = torch.zeros((tiles * FP4_TILE_N, K // 16), device=w.device, dtype=torch.uint8)
+    tiles = (Nn + tile_n - 1) // tile_n
+    na = (tile_n + 127) // 128                                           # atoms per tile and K-group
+    pad = torch.zeros((tiles, na * 128, K // 16), device=w.device, dtype=torch.uint8)
+    full = torch.zeros((tiles * tile_n, K // 16), device=w.device, dtype=torch.uint8)
     full[:Nn] = m
-    pad[:, :FP4_TILE_N] = full.view(tiles, FP4_TILE_N, K // 16)
-    atoms = sf_matrix_to_atoms(pad.view(tiles * 256, K // 16))          # [tiles * 2, K/64, 512]
-    atoms = atoms.view(tiles, 2, K // 64, 512).permute(0, 2, 1, 3).contiguous()
+    pad[:, :tile_n] = full.view(tiles, tile_n, K // 16)
+    atoms = sf_matrix_to_atoms(pad.view(tiles * na * 128, K // 16))     # [tiles * na, K/64, 512]
+    atoms = atoms.view(tiles, na, K // 64, 512).permute(0, 2, 1, 3).contiguous()
     return q, atoms, scale
+
+
+def gemm_fp4_qkv(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4: torch.Tensor, sfw: torch.Tensor,
+                 w_scale: torch.Tensor, batch: int, bias: Optional[torch.Tensor], q_scale: torch.Tensor, k_scale: torch.Tensor,
+                 pe: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, seq_off: int, rms_eps: float = 1e-6,
+                 pe_blocked: bool = False) -> None:
+    """gemm_qkv on NVFP4 operands: qkv = (a4 @ w4.T) * a_scale * w_scale + bias; q, k = rope(rmsnorm(.)) per head;
+    q/k/v [B, H, seq_total, 128] (bf16 or e4m3) filled at rows seq_off + r.  w4 / sfw from fp4_weight(w, FP4_TILE_N_QKV)."""
+    _chk(a4, torch.uint8), _chk(w4, torch.uint8), _chk(sfa, torch.uint8), _chk(sfw, torch.uint8)
+    _chk(a_scale, torch.float32), _chk(w_scale, torch.float32)
+    rows_total, kb = a4.shape
+    Nn = w4.shape[0]
+    B, H, St, hd = q.shape
+    if w4.shape[1] != kb or rows_total % batch or batch != B or hd != 128 or Nn != 3 * H * 128:
+        raise ValueError("fp4 qkv operands do not match")
+    f8 = q.dtype == fp8
+    for t in (q, k, v):
+        _chk(t, fp8 if f8 else bf16)
+        if not t.is_contiguous() or t.shape != q.shape:
+            raise ValueError("q/k/v must be contiguous [B,H,S,128]")
+    args = N.Gemm4QkvArgs()
+    args.A, args.sfa, args.a_scale = a4.data_ptr(), sfa.data_ptr(), a_scale.data_ptr()
+    args.W, args.sfw, args.w_scale = w4.data_ptr(), sfw.data_ptr(), w_scale.data_ptr()
+    args.bias = N.ptr(bias)
+    args.q_scale, args.k_scale, args.pe, args.pe_blocked = q_scale.data_ptr(), k_scale.data_ptr(), pe.data_ptr(), int(pe_blocked)
+    args.q, args.k, args.v, args.qkv_fp8 = q.data_ptr(), k.data_ptr(), v.data_ptr(), int(f8)
+    args.rms_eps = rms_eps
+    args.batch, args.rows, args.K, args.heads, args.seq_total, args.seq_off = B, rows_total // batch, 2 * kb, H, St, seq_off
+    N.check(N.lib().fx_gemm_fp4_qkv(C.byref(args), N.stream()))
 
 
 def gemm_fp4(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4: torch.Tensor, sfw: torch.Tensor,

@@ -150,6 +150,21 @@ typedef struct fx_gemm4_args {
 } fx_gemm4_args;
 int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream);
 
+/* fx_gemm_fp4_qkv: the NVFP4 form of fx_gemm_qkv (flux/layers.py:195-214: qkv Linear -> per-head QK-RMSNorm -> RoPE -> q, k, v
+ * [batch][heads][seq_total][128] at rows seq_off + r, bf16 or e4m3).  N = 3 * heads * 128; tiles are one head (128 columns) wide,
+ * so W's scale atoms are [N / 128][K / 64] (ops.fp4_weight(w, tile_n=128)).  Rows % 128 == 0 unless batch == 1; K % 256 == 0. */
+typedef struct fx_gemm4_qkv_args {
+  const void* A; const void* sfa; const float* a_scale;
+  const void* W; const void* sfw; const float* w_scale;
+  const void* bias;
+  const void* q_scale; const void* k_scale; /* [128] RMSNorm weights */
+  const void* pe; int32_t pe_blocked;       /* as fx_qkv_args */
+  void* q; void* k; void* v; int32_t qkv_fp8;
+  float rms_eps;
+  int32_t batch, rows, K, heads, seq_total, seq_off;
+} fx_gemm4_qkv_args;
+int fx_gemm_fp4_qkv(const fx_gemm4_qkv_args* a, fx_stream stream);
+
 /* ---------------------------------------------------------------- attention
  * Non-causal softmax(q k^T * scale) v over head_dim 128 on tcgen05 (flash-style, online softmax);
  * replaces mx.fast.scaled_dot_product_attention + the transpose/reshape at flux/layers.py:41-43.

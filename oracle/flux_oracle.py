@@ -43,7 +43,8 @@ class Mode:
     """fp32: every op in float32.  fp64: float64.  bf16: float32 math, result of every reference
     op rounded to bfloat16 (how an unfused bf16 MLX graph behaves: flux/flux.py:24)."""
 
-    def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None, bits: int = 8):
+    def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None, bits: int = 8,
+                 fp4_scope: str = "all"):
         assert name in ("fp32", "fp64", "bf16")
         self.name = name
         self.dtype = torch.float64 if name == "fp64" else torch.float32
@@ -51,9 +52,12 @@ class Mode:
         # QK-norm and RoPE) and v are cast to e4m3 without a scale, the softmax numerators are cast to e4m3 after a
         # 2^4 scale (fx_attention fp8 mode), the row sum and everything else stay fp32
         self.quantize_attention = quantize if quantize_attention is None else quantize_attention
-        # bits = 4: restates Flux.quantize(bits=4) -- the Linears matched by FP4_LINEARS see NVFP4 activations and weights
-        # (nvfp4_quant_rows), the other block Linears stay FP8
+        # bits = 4: restates Flux.quantize(bits=4) -- NVFP4 activations and weights (nvfp4_quant_rows) for every block Linear
+        # (fp4_scope "all": FP8_LINEARS) or only for the K-long ones that read the attention | GELU(mlp) buffer (fp4_scope
+        # "cat": FP4_LINEARS, the other block Linears then stay FP8)
         self.bits = bits
+        assert fp4_scope in ("all", "cat")
+        self.fp4_scope = fp4_scope
         # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
         # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
         # e4m3 activations and weights (fx_quantize_rows in include/flux_b200.h), everything else is unchanged.
@@ -129,7 +133,7 @@ def nvfp4_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
 def _linear(m: Mode, x: Tensor, sd: Dict[str, Tensor], key: str, bias: bool = True) -> Tensor:
     w = m.w(sd[key + ".weight"])
     b = m.w(sd[key + ".bias"]) if bias and (key + ".bias") in sd else None
-    if m.quantize and m.bits == 4 and FP4_LINEARS.match(key):
+    if m.quantize and m.bits == 4 and (FP8_LINEARS if m.fp4_scope == "all" else FP4_LINEARS).match(key):
         qx, sx, gx = nvfp4_quant_rows(x)
         qw, sw, gw = nvfp4_quant_rows(w)
         xd = qx * sx.repeat_interleave(16, dim=-1) * gx

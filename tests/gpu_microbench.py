@@ -83,6 +83,13 @@ def main(which, sweep=None):
         w24, w2sf, w2s4 = ops.fp4_weight(w2)
         catm4, cmsf4, cms4 = ops.quantize_rows_fp4(cat[:, S:, D:])
         wf24, wf2sf, wf2s4 = ops.fp4_weight(wfc2)
+        xm4, xmsf4, xms4 = ops.quantize_rows_fp4(xm)
+        xi4, xisf4, xis4 = ops.quantize_rows_fp4(xm[:, S:])
+        wq4, wqsf, wqs4 = ops.fp4_weight(w1[:3 * D], ops.FP4_TILE_N_QKV)
+        wm4, wmsf, wms4 = ops.fp4_weight(w1[3 * D:])
+        wp4, wpsf, wps4 = ops.fp4_weight(wproj)
+        ca4, casf4, cas4 = ops.quantize_rows_fp4(cat[:, S:, :D])
+        q8o, k8o, v8o = (torch.empty(B, H, N, 128, device=dev, dtype=ops.fp8) for _ in range(3))
     tests = {
         "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
         "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
@@ -108,6 +115,13 @@ def main(which, sweep=None):
         "linear2_f4": (lambda: ops.gemm_fp4(cat4, csf4, cs4, w24, w2sf, w2s4, B, bias=b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
         "fc2_f4": (lambda: ops.gemm_fp4(catm4, cmsf4, cms4, wf24, wf2sf, wf2s4, B, bias=b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * M),
         "quant_cat_f4": (lambda: ops.quantize_rows_fp4(cat), 0.0),
+        "quant_x_f4": (lambda: ops.quantize_rows_fp4(xm), 0.0),
+        "qkv1_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q8o, k8o, v8o, 0), 2.0 * B * N * 3 * D * D),
+        "qkv1_bf16out_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q, k, v, 0), 2.0 * B * N * 3 * D * D),
+        "mlp1_f4": (lambda: ops.gemm_fp4(xm4, xmsf4, xms4, wm4, wmsf, wms4, B, bias=b1[3 * D:], act="gelu_tanh", out=cat[:, :, D:]), 2.0 * B * N * M * D),
+        "qkv_img_f4": (lambda: ops.gemm_fp4_qkv(xi4, xisf4, xis4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q8o, k8o, v8o, S), 2.0 * B * L * 3 * D * D),
+        "fc1_f4": (lambda: ops.gemm_fp4(xi4, xisf4, xis4, wm4, wmsf, wms4, B, bias=b1[3 * D:], act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
+        "proj_f4": (lambda: ops.gemm_fp4(ca4, casf4, cas4, wp4, wpsf, wps4, B, bias=b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * D),
         "fc2_f8": (lambda: ops.gemm(catm8, wf2q, b2, gate=gate, resid=x[:, S:], out=x[:, S:], a_scale=cms, w_scale=wf2s), 2.0 * B * L * D * M),
         "quant_cat_f8": (lambda: ops.quantize_rows(cat, out=cat8, out_scale=cs), 0.0),
         "rownorm_f8": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out=xm8, out_scale=xs), 0.0),
@@ -126,7 +140,7 @@ def main(which, sweep=None):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
         nbytes = {"rownorm": 4 * x.numel(), "rownorm_f8": 3 * x.numel(), "quant_cat_f8": 3 * cat.numel(),
-                  "quant_cat_f4": 2.5625 * cat.numel()}.get(name)
+                  "quant_cat_f4": 2.5625 * cat.numel(), "quant_x_f4": 2.5625 * xm.numel()}.get(name)
         extra = f" = {nbytes / ms / 1e6:.0f} GB/s" if nbytes else f" = {tf:.0f} TFLOP/s"
         print(f"{name:10s} {ms:8.3f} ms{extra}{last_clock}", flush=True)
 

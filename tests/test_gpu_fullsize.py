@@ -205,7 +205,9 @@ def test_fp8_full_depth_four_steps(schnell, vae):
         l8lin = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
         model.quantize()                                # + FP8 attention (the default --quantize)
         l8 = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
-        model.quantize(bits=4)                          # + NVFP4 proj / mlp.2 / linear2 (--quantize --quantize-bits 4)
+        model.quantize(bits=4, fp4_scope="cat")         # + NVFP4 proj / mlp.2 / linear2, FP8 elsewhere
+        l4c = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
+        model.quantize(bits=4)                          # NVFP4 for every block Linear (--quantize --quantize-bits 4)
         l4 = run(lambda x, ts: model.forward(x, ids, txt, tids, ts, y))
     finally:
         model.dequantize()
@@ -217,6 +219,7 @@ def test_fp8_full_depth_four_steps(schnell, vae):
                fp8_vs_bf16_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l8, l16)],
                fp8_linears_only_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l8lin, lo)],
                nvfp4_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l4, lo)],
+               nvfp4_cat_only_vs_fp32_latent_rel_l2=[rel_l2(a, b) for a, b in zip(l4c, lo)],
                nvfp4_image_mean_abs_255=(im4 - oim).abs().mean().item() * 255,
                bf16_image_mean_abs_255=(im16 - oim).abs().mean().item() * 255,
                fp8_image_mean_abs_255=(im8 - oim).abs().mean().item() * 255,
@@ -225,7 +228,7 @@ def test_fp8_full_depth_four_steps(schnell, vae):
     assert max(rep["bf16_vs_fp32_latent_rel_l2"]) <= 2e-2, rep
     assert max(rep["fp8_vs_fp32_latent_rel_l2"]) <= 8e-2, rep
     assert rep["bf16_image_mean_abs_255"] <= 2 and rep["fp8_image_mean_abs_255"] <= 4, rep
-    # NVFP4 (W4A4 on a third of the linear FLOPs): reported; the stated bound of the 4-bit mode is latents rel-L2 <= 2.5e-1
+    # NVFP4 (W4A4 on every block Linear): reported; the stated bound of the 4-bit mode is latents rel-L2 <= 2.5e-1
     assert max(rep["nvfp4_vs_fp32_latent_rel_l2"]) <= 2.5e-1, rep
 
 
