@@ -2,6 +2,7 @@
 // embedding, Euler step, latent packing, GroupNorm(+SiLU), nearest upsample, row softmax, transpose,
 // image finish, embedding gather, gated activation.  All vectorised to 16-byte accesses, bf16 in HBM,
 // fp32 in registers.
+#include <cuda_fp4.h>
 #include <cuda_fp8.h>
 #include <stdlib.h>
 
@@ -51,6 +52,7 @@ struct RowNormParams {
   const __nv_bfloat16 *p0, *p1; long long p_bs;
   float eps; int mode, batch, rows, D;
   float* scale_out; long long scale_bs;  // F8OUT: out holds e4m3 bytes, scale_out[b][r] the row's dequantisation scale
+  uint8_t* sf_out;                       // NVFP4 output (block kernel, OUT == 2): UE4M3 block-scale atoms; out = compact e2m1 rows
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -170,8 +172,11 @@ __device__ __forceinline__ float block_sum4(float v, float* red, int lane, int w
 __device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {  // packed bf16 pair -> packed fp32 pair (2 ALU ops)
   return pack2f(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
-template <int VPT, bool F8OUT, int MINB>  // VPT = ceil(D / 1024) 16-byte vectors per thread; MINB resident blocks per SM
+// OUT: 0 bf16, 1 e4m3 + row scale (= fx_quantize_rows of the bf16 result), 2 NVFP4 (= fx_quantize_rows_fp4 of the bf16 result:
+// compact e2m1 rows, UE4M3 scale atoms, fp32 row scale; bit-identical to the two-kernel sequence, csrc/gemm4.cu)
+template <int VPT, int OUT, int MINB>  // VPT = ceil(D / 1024) 16-byte vectors per thread; MINB resident blocks per SM
 __global__ void __launch_bounds__(128, MINB) rownorm_block_kernel(const RowNormParams p) {
+  constexpr bool F8OUT = OUT == 1;
   // Persistent blocks walk the rows with a grid stride; the next row's loads are issued before the current row is
   // reduced.  The kernel was INSTRUCTION-bound, not HBM-bound (~350 instructions per thread and row: the packed row was
   // unpacked three times and the modulation vectors once per row; 3.9 TB/s whatever the launch geometry).  Now the row
@@ -268,7 +273,50 @@ __global__ void __launch_bounds__(128, MINB) rownorm_block_kernel(const RowNormP
         if (F8OUT) amax2 = __hmax2(amax2, __habs2(*reinterpret_cast<const __nv_bfloat162*>(&w[j])));
       }
       keep[i] = make_uint4(w[0], w[1], w[2], w[3]);
-      if (!F8OUT && in[i]) *reinterpret_cast<uint4*>(orow + (i * 128 + tid) * 8) = keep[i];
+      if (OUT == 0 && in[i]) *reinterpret_cast<uint4*>(orow + (i * 128 + tid) * 8) = keep[i];
+    }
+    if (OUT == 2) {  // exactly quantize_rows_fp4(rownorm(x)): two-level NVFP4 of the ROUNDED values (see csrc/gemm4.cu)
+      float bmax[VPT], amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        float o[8];
+        unpack8(keep[i], o);
+        float mx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, fabsf(o[j]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));  // a block of 16 = two neighbouring threads
+        bmax[i] = mx;
+        amax = fmaxf(amax, mx);
+      }
+      amax = warp_max(amax);
+      if (lane == 0) rd[2][warp] = amax;
+      __syncthreads();
+      amax = fmaxf(fmaxf(rd[2][0], rd[2][1]), fmaxf(rd[2][2], rd[2][3]));
+      const float g = amax > 0.f ? __fmul_rn(amax, 1.0f / 2688.0f) : 1.0f;
+      const float rg = __frcp_rn(g);
+      if (tid == 0) p.scale_out[gr] = g;
+      uint8_t* sf_row = p.sf_out + (gr >> 7) * (long long)(p.D / 64) * 512 + (int(gr) & 31) * 16 + ((int(gr) & 127) >> 5) * 4;
+      uint8_t* q4 = reinterpret_cast<uint8_t*>(p.out) + gr * (long long)(p.D / 2);
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int c = (i * 128 + tid) * 8;
+        const float u = __fmul_rn(__fmul_rn(bmax[i], 1.0f / 6.0f), rg);
+        const __nv_fp8_storage_t sf8 = __nv_cvt_float_to_fp8(u, __NV_SATFINITE, __NV_E4M3);
+        const float d = __fmul_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(sf8, __NV_E4M3))), g);
+        uint32_t sfw = uint32_t(sf8);  // the four scales of a K-group sit in lanes 8m, 8m+2, 8m+4, 8m+6
+        sfw |= __shfl_down_sync(0xffffffffu, sfw, 2) << 8;
+        sfw |= __shfl_down_sync(0xffffffffu, sfw, 4) << 16;
+        if (in[i] && (tid & 7) == 0) *reinterpret_cast<uint32_t*>(sf_row + (c >> 6) * 512) = sfw;
+        const float rdv = d > 0.f ? __frcp_rn(d) : 0.f;
+        float o[8];
+        unpack8(keep[i], o);
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e += 2)
+          w |= uint32_t(__nv_cvt_float2_to_fp4x2(make_float2(__fmul_rn(o[e], rdv), __fmul_rn(o[e + 1], rdv)), __NV_E2M1, cudaRoundNearest))
+               << (4 * e);
+        if (in[i]) *reinterpret_cast<uint32_t*>(q4 + (c >> 1)) = w;
+      }
     }
     if (F8OUT) {  // exactly quantize_rows(rownorm(x)): absmax of the ROUNDED values, then e4m3 + the row's scale
       float amax = warp_max(fmaxf(__low2float(amax2), __high2float(amax2)));
@@ -791,12 +839,15 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
   FX_REQUIRE(a->ldx % 8 == 0 && a->ldo % 8 == 0 && a->x_bs % 8 == 0 && a->out_bs % 8 == 0 && a->p_bs % 8 == 0,
              "fx_rownorm: strides must be multiples of 8 elements");
   if (a->batch <= 0 || a->rows <= 0) return FX_OK;
-  FX_REQUIRE(!a->out_fp8 || (a->scale_out && a->ldo % 16 == 0 && a->out_bs % 16 == 0),
+  FX_REQUIRE(a->out_fp8 != 1 || (a->scale_out && a->ldo % 16 == 0 && a->out_bs % 16 == 0),
              "fx_rownorm: out_fp8 needs scale_out and 16-byte aligned output rows");
   RowNormParams p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, (__nv_bfloat16*)a->out, a->ldo, a->out_bs,
                   (const __nv_bfloat16*)a->p0, (const __nv_bfloat16*)a->p1, a->p_bs, a->eps, a->mode, a->batch, a->rows, a->D,
-                  a->scale_out, a->scale_bs};
+                  a->scale_out, a->scale_bs, (uint8_t*)a->sf_out};
   const long long rows = (long long)a->batch * a->rows;
+  if (a->out_fp8 == 2)
+    FX_REQUIRE(a->sf_out && a->scale_out && a->D % 64 == 0 && a->D >= 1024 && rows < (1ll << 31),
+               "fx_rownorm: NVFP4 output needs sf_out, scale_out and D %% 64 == 0, D >= 1024");
   int blocks = int((rows + 7) / 8);
   {  // FX_ROWNORM_PERSIST = blocks per SM of a persistent grid-stride grid (0 = one row per warp).  Default 2 = the
      // kernel's occupancy: +5 % (3.69 -> 3.88 TB/s); more blocks than are resident is slower (3.0 TB/s)
@@ -813,7 +864,7 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
     const char* e = getenv("FX_ROWNORM_BLOCK");
     block_rows = e ? atoi(e) : 1;
   }
-  if (block_rows && a->D >= 1024 && rows < (1ll << 31)) {  // wide rows: one block per row
+  if ((block_rows || a->out_fp8 == 2) && a->D >= 1024 && rows < (1ll << 31)) {  // wide rows: one block per row
     static int per_sm = -1;  // FX_ROWNORM_BLOCKS_PER_SM: resident 128-thread blocks per SM of the persistent grid
     if (per_sm < 0) {
       const char* e = getenv("FX_ROWNORM_BLOCKS_PER_SM");
@@ -825,8 +876,9 @@ extern "C" int fx_rownorm(const fx_rownorm_args* a, fx_stream stream) {
     const int vpt = (a->D + 1023) / 1024;
 #define FX_RB(V, M)                                                                  \
   case V:                                                                            \
-    if (a->out_fp8) rownorm_block_kernel<V, true, M><<<g, 128, 0, st>>>(p);          \
-    else rownorm_block_kernel<V, false, M><<<g, 128, 0, st>>>(p);                    \
+    if (a->out_fp8 == 2) rownorm_block_kernel<V, 2, M><<<g, 128, 0, st>>>(p);        \
+    else if (a->out_fp8) rownorm_block_kernel<V, 1, M><<<g, 128, 0, st>>>(p);        \
+    else rownorm_block_kernel<V, 0, M><<<g, 128, 0, st>>>(p);                        \
     break;
     if (per_sm == 4) { switch (vpt) { FX_RB(1, 4) FX_RB(2, 4) FX_RB(3, 4) FX_RB(4, 4) } }
     else if (per_sm == 5) { switch (vpt) { FX_RB(1, 5) FX_RB(2, 5) FX_RB(3, 5) FX_RB(4, 5) } }

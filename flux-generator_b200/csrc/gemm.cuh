@@ -200,13 +200,15 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
                                                   int n0, bool fast, const float* sw = nullptr, float rs = 1.f,
                                                   uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true,
                                                   long long lane_off = -1, long long ld_hi = -1) {
-  if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias
+  if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias -- on packed fp32 pairs (FMUL2 / FFMA2: same roundings)
+    const uint64_t rs2 = pack2f(rs, rs);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 t = *reinterpret_cast<const float4*>(sb + i);
       const float4 w = *reinterpret_cast<const float4*>(sw + i);
-      f[i] = fmaf(f[i], rs * w.x, t.x); f[i + 1] = fmaf(f[i + 1], rs * w.y, t.y);
-      f[i + 2] = fmaf(f[i + 2], rs * w.z, t.z); f[i + 3] = fmaf(f[i + 3], rs * w.w, t.w);
+      const float2 lo = unpack2f(ffma2(pack2f(f[i], f[i + 1]), fmul2(rs2, pack2f(w.x, w.y)), pack2f(t.x, t.y)));
+      const float2 hi = unpack2f(ffma2(pack2f(f[i + 2], f[i + 3]), fmul2(rs2, pack2f(w.z, w.w)), pack2f(t.z, t.w)));
+      f[i] = lo.x; f[i + 1] = lo.y; f[i + 2] = hi.x; f[i + 3] = hi.y;
     }
   } else {
 #pragma unroll
@@ -245,7 +247,9 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 t = *reinterpret_cast<const float4*>(sg + i);
-      f[i] *= t.x; f[i + 1] *= t.y; f[i + 2] *= t.z; f[i + 3] *= t.w;
+      const float2 lo = unpack2f(fmul2(pack2f(f[i], f[i + 1]), pack2f(t.x, t.y)));
+      const float2 hi = unpack2f(fmul2(pack2f(f[i + 2], f[i + 3]), pack2f(t.z, t.w)));
+      f[i] = lo.x; f[i + 1] = lo.y; f[i + 2] = hi.x; f[i + 3] = hi.y;
     }
   }
   if (fast) {

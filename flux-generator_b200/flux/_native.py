@@ -55,7 +55,7 @@ class AttnSmallArgs(C.Structure):
 class RowNormArgs(C.Structure):
     _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_bs", c_i64), ("out", c_vp), ("ldo", c_i64), ("out_bs", c_i64),
                 ("p0", c_vp), ("p1", c_vp), ("p_bs", c_i64), ("eps", c_f32), ("mode", c_i32), ("batch", c_i32),
-                ("rows", c_i32), ("D", c_i32), ("out_fp8", c_i32), ("scale_out", c_vp), ("scale_bs", c_i64)]
+                ("rows", c_i32), ("D", c_i32), ("out_fp8", c_i32), ("scale_out", c_vp), ("scale_bs", c_i64), ("sf_out", c_vp)]
 
 
 class QuantArgs(C.Structure):

@@ -509,7 +509,7 @@ class Flux:
             q, k, v = ws["q8"], ws["k8"], ws["v8"]
         xm, xm8, cat8, xs, cs = ws["xm"], ws["xm8"], ws["cat8"], ws["xs"], ws["cs"]
         B = x.shape[0]
-        f4 = self._q4_all and "a4" in ws   # NVFP4 for the norm-fed Linears too: bf16 row norm, then the NVFP4 row quantiser
+        f4 = self._q4_all and "a4" in ws   # NVFP4 for the norm-fed Linears too: the AdaLN row norm writes the NVFP4 operand
         for i in range(p.depth):
             pre = f"double_blocks.{i}."
             streams = (("img", slice(S, None), S), ("txt", slice(0, S), 0))
@@ -518,8 +518,7 @@ class Flux:
                 ak = pre + name + "_attn."
                 qn, kn = self.arena[ak + "norm.query_norm.scale"], self.arena[ak + "norm.key_norm.scale"]
                 if f4:
-                    ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm[:, rows])
-                    a4, sfa, sa = ops.quantize_rows_fp4(xm[:, rows], out=ws["a4"])
+                    a4, sfa, sa = ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out_fp4=ws["a4"])
                     w4, sfw, sw = self._q4[ak + "qkv"]
                     ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, self._b(ak + "qkv"), qn, kn, pe, q, k, v, off, rms_eps=QK_RMS_EPS,
                                      pe_blocked=pe_blocked)
@@ -536,8 +535,7 @@ class Flux:
                 xr = x[:, rows]
                 self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
                 if f4:
-                    ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm[:, rows])
-                    a4, sfa, sa = ops.quantize_rows_fp4(xm[:, rows], out=ws["a4"])
+                    a4, sfa, sa = ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out_fp4=ws["a4"])
                     w4, sfw, sw = self._q4[mlp + "0"]
                     ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:])
                 else:
@@ -550,8 +548,7 @@ class Flux:
             mk = pre + "modulation.lin"
             qn, kn = self.arena[pre + "norm.query_norm.scale"], self.arena[pre + "norm.key_norm.scale"]
             if f4:
-                ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm)
-                a4, sfa, sa = ops.quantize_rows_fp4(xm, out=ws["a4"])
+                a4, sfa, sa = ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out_fp4=ws["a4"])
                 bias = self._b(pre + "linear1")
                 w4, sfw, sw = self._q4[pre + "linear1.qkv"]
                 ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, None if bias is None else bias[:3 * D], qn, kn, pe, q, k, v, 0,

@@ -224,11 +224,29 @@ def attention_small(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: in
 
 
 def rownorm(x: torch.Tensor, mode: int, p0: torch.Tensor, p1: Optional[torch.Tensor], eps: float,
-            out: Optional[torch.Tensor] = None, out_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, out_scale: Optional[torch.Tensor] = None, out_fp4=None):
     """mode 0: (1+p1[b])*LN(x)+p0[b]; mode 1: LN(x)*p0+p1; mode 2: RMSNorm(x)*p0.
-    A float8_e4m3fn `out` (with out_scale fp32 [B,R]) gets the row-quantised result (--quantize)."""
+    A float8_e4m3fn `out` (with out_scale fp32 [B,R]) gets the row-quantised result (--quantize).
+    out_fp4 = (q, sf, scale) flat uint8 / uint8 / fp32 buffers (as quantize_rows_fp4(out=...)): the NVFP4 operand of the
+    result, bit-identical to quantize_rows_fp4(rownorm(x)); returns (q [rows, D/2], sf atoms, scale [rows])."""
     _chk(x)
     B, R, D, ldx, xbs = _as3(x)
+    if out_fp4 is not None:
+        rows = B * R
+        if rows % 128 or D % 64 or D < 1024:
+            raise ValueError("rownorm(out_fp4=...) needs a multiple of 128 rows and D % 64 == 0, D >= 1024")
+        q = out_fp4[0][:rows * (D // 2)].view(rows, D // 2)
+        sf = out_fp4[1][:(rows // 128) * (D // 64) * 512].view(rows // 128, D // 64, 512)
+        scale = out_fp4[2][:rows]
+        args = N.RowNormArgs()
+        args.x, args.ldx, args.x_bs = x.data_ptr(), ldx, xbs
+        args.out, args.ldo, args.out_bs = q.data_ptr(), 0, 0
+        args.p0, args.p1 = p0.data_ptr(), N.ptr(p1)
+        args.p_bs = p0.stride(0) if (mode == 0 and p0.dim() == 2) else 0
+        args.eps, args.mode, args.batch, args.rows, args.D = eps, mode, B, R, D
+        args.out_fp8, args.scale_out, args.scale_bs, args.sf_out = 2, scale.data_ptr(), R, sf.data_ptr()
+        N.check(N.lib().fx_rownorm(C.byref(args), N.stream()))
+        return q, sf, scale
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=bf16)
     _chk(out, out.dtype)

@@ -210,6 +210,10 @@ typedef struct fx_rownorm_args {
    * fp8 fx_gemm / fx_gemm_qkv */
   int32_t out_fp8;
   float* scale_out; int64_t scale_bs;
+  /* --quantize 4: out_fp8 == 2 writes the NVFP4 operand of fx_gemm_fp4 / fx_gemm_fp4_qkv instead: `out` = compact e2m1 rows
+   * [batch * rows][D / 2] (ldo / out_bs ignored), sf_out = UE4M3 scale atoms, scale_out = fp32 [batch * rows]; bit-identical
+   * to fx_quantize_rows_fp4 applied to the bf16 result.  D % 64 == 0, D >= 1024. */
+  void* sf_out;
 } fx_rownorm_args;
 int fx_rownorm(const fx_rownorm_args* a, fx_stream stream);
 

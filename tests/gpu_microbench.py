@@ -119,6 +119,7 @@ def main(which, sweep=None):
         "qkv1_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q8o, k8o, v8o, 0), 2.0 * B * N * 3 * D * D),
         "qkv1_bf16out_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q, k, v, 0), 2.0 * B * N * 3 * D * D),
         "mlp1_f4": (lambda: ops.gemm_fp4(xm4, xmsf4, xms4, wm4, wmsf, wms4, B, bias=b1[3 * D:], act="gelu_tanh", out=cat[:, :, D:]), 2.0 * B * N * M * D),
+        "mlp1_noact_f4": (lambda: ops.gemm_fp4(xm4, xmsf4, xms4, wm4, wmsf, wms4, B, bias=b1[3 * D:], out=cat[:, :, D:]), 2.0 * B * N * M * D),
         "qkv_img_f4": (lambda: ops.gemm_fp4_qkv(xi4, xisf4, xis4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q8o, k8o, v8o, S), 2.0 * B * L * 3 * D * D),
         "fc1_f4": (lambda: ops.gemm_fp4(xi4, xisf4, xis4, wm4, wmsf, wms4, B, bias=b1[3 * D:], act="gelu_tanh", out=cat[:, S:, D:]), 2.0 * B * L * M * D),
         "proj_f4": (lambda: ops.gemm_fp4(ca4, casf4, cas4, wp4, wpsf, wps4, B, bias=b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * D),

@@ -117,6 +117,27 @@ def test_gemm_fp4_qkv_epilogue(B, R, H, K, off, f8out):
         assert all(torch.equal(x_, y_) for x_, y_ in zip(got, got2))
 
 
+@pytest.mark.parametrize("B,R,D,mode", [(2, 256, 3072, 0), (1, 128, 4096, 2), (3, 128, 1024, 1)])
+def test_rownorm_nvfp4_output_bit_identical_to_two_kernels(B, R, D, mode):
+    """fx_rownorm with out_fp8 == 2 (the AdaLN / LayerNorm / RMSNorm row kernel writing the NVFP4 operand directly) produces
+    the bytes, scale atoms and row scales of fx_quantize_rows_fp4 applied to its bf16 output -- integer work: bit-exact."""
+    x = rnd(B, R + 8, D, seed=41)[:, 8:]                       # a strided view: rows start inside the buffer
+    if mode == 0:
+        p0, p1 = rnd(B, D, seed=42, scale=0.1), rnd(B, D, seed=43, scale=0.1)
+    else:
+        p0, p1 = (1 + rnd(D, seed=42, scale=0.1).float()).to(bf), (rnd(D, seed=43, scale=0.1) if mode == 1 else None)
+    want = ops.quantize_rows_fp4(ops.rownorm(x, mode, p0, p1, 1e-6))
+    rows = B * R
+    bufs = (torch.full((rows * D // 2 + 64,), 0xAA, device=dev, dtype=torch.uint8),
+            torch.zeros((rows // 128) * (D // 64) * 512, device=dev, dtype=torch.uint8), torch.zeros(rows, device=dev))
+    got = ops.rownorm(x, mode, p0, p1, 1e-6, out_fp4=bufs)
+    for g_, w_ in zip(got, want):
+        assert g_.shape == w_.shape and torch.equal(g_, w_)
+    assert (bufs[0][rows * D // 2:] == 0xAA).all()              # nothing written past the operand
+    with pytest.raises(ValueError):
+        ops.rownorm(rnd(1, 100, D, seed=1), mode, p0, p1, 1e-6, out_fp4=bufs)   # rows must fill whole 128-row scale atoms
+
+
 @pytest.mark.parametrize("scope", ["all", "cat"])
 def test_flow_nvfp4_full_width_vs_quantised_oracle(scope):
     """hidden 3072 / 24 heads, depth 1+1, batch 2, N = 128 + 384: Flux.quantize(bits=4) -- NVFP4 for every block Linear
