@@ -199,7 +199,8 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
                                                   const uint4* rr, bool rr_ok, long long out_off, long long res_off,
                                                   int n0, bool fast, const float* sw = nullptr, float rs = 1.f,
                                                   uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true,
-                                                  long long lane_off = -1, long long ld_hi = -1) {
+                                                  long long lane_off = -1, long long ld_hi = -1, const void* tmap_out = nullptr,
+                                                  int t_row0 = 0, int t_b = 0) {
   if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias -- on packed fp32 pairs (FMUL2 / FFMA2: same roundings)
     const uint64_t rs2 = pack2f(rs, rs);
 #pragma unroll
@@ -270,6 +271,8 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
       }
+    } else if (tmap_out != nullptr) {  // warp-collective: staged, then one TMA store (rows / columns clipped by the tensor map)
+      store_chunk32_tma(wst, lane, f, tmap_out, n0, t_row0, t_b);
     } else if (wst != nullptr) {  // warp-collective: every lane takes part, rows are masked
       // lane_off: distance (elements) from the warp's row 0 to this lane's row (lane * ldo unless the rows are image patches)
       store_chunk32_coalesced(wst, lane, f,

@@ -44,11 +44,12 @@ struct G4Cfg {
   static constexpr int SFB_BYTES = 4 * NSFB * 512;
   static constexpr int B_BYTES = (BN / NCTA) * 128;
   static constexpr int STAGE_BYTES = G4_A_BYTES + B_BYTES + G4_SFA_BYTES + SFB_BYTES;
-  static constexpr int TAIL = 256 + G4_EPI_WARPS * (384 * 4 + 2048) + 1024;   // barriers, epilogue vectors, store staging, alignment
+  // behind the ring: barriers (1 KB slot), store staging (12 x 2 KB, 512-byte aligned: TMA SWIZZLE_64B), epilogue vectors
+  static constexpr int TAIL = 1024 + G4_EPI_WARPS * (2048 + 384 * 4) + 1024;
   static constexpr int STAGES = (232448 - TAIL) / STAGE_BYTES;        // 5 / 3 (BN 192: pair / single), 6 / 5 (BN 128)
-  static constexpr int EPI_OFF = STAGES * STAGE_BYTES + 256;
-  static constexpr int STORE_OFF = EPI_OFF + G4_EPI_WARPS * 384 * 4;
-  static constexpr int SMEM = STORE_OFF + G4_EPI_WARPS * 2048 + 1024;
+  static constexpr int STORE_OFF = STAGES * STAGE_BYTES + 1024;
+  static constexpr int EPI_OFF = STORE_OFF + G4_EPI_WARPS * 2048;
+  static constexpr int SMEM = EPI_OFF + G4_EPI_WARPS * 384 * 4 + 1024;
   static constexpr int NACC = BN == 128 ? 3 : 2;            // accumulators in TMEM: 3 x 128 (QKV) or 2 x 192 columns
   static constexpr int TMEM_SF = NACC * BN;                 // scale-factor slots start behind the accumulators
   static constexpr int SF_SLOT = 16 + 16 * NSFB;            // 16 columns of A scales + 16 per W atom row, per stage
@@ -87,6 +88,7 @@ __host__ __device__ constexpr uint32_t make_idesc_nvf4(int M, int N) {
 struct Gemm4Params {
   GemmParams g;              // shapes, raster, generic epilogue (a_scale / w_scale = the second-level scales)
   int k_groups;              // K / 64
+  int tma_out;               // generic epilogue, bf16 output: chunks leave through TMA stores (tmap_out)
 };
 
 // tmap_sfa / tmap_sfb: the scale-atom buffers viewed as [bytes / 128][128] byte matrices (no swizzle): one stage's atoms of a
@@ -95,7 +97,8 @@ struct Gemm4Params {
 template <int NCTA, int BN, int EPI>
 __global__ void __launch_bounds__(G4_THREADS, 1)
 gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb, const Gemm4Params q) {
+                  const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb,
+                  const __grid_constant__ CUtensorMap tmap_out, const Gemm4Params q) {
   const GemmParams& p = q.g;
   using Cfg = G4Cfg<NCTA, BN>;
   constexpr int STAGES = Cfg::STAGES, NSFB = Cfg::NSFB, NACC = Cfg::NACC;
@@ -117,6 +120,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_sfa);
     tma_prefetch_desc(&tmap_sfb);
+    if (q.tma_out) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -350,7 +354,8 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           if (c + 1 < CH) tmem_ld_x32(taddr + group * WN + (c + 1) * 32, v);   // in flight while this chunk is processed
           epi_generic_chunk<true>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0, vec_ok && (n0 + 32 <= p.N),
-                                  sw + c * 32, rs, wst, lane, vmask, valid);
+                                  sw + c * 32, rs, wst, lane, vmask, valid, -1, -1, (q.tma_out && vmask != 0u) ? &tmap_out : nullptr,
+                                  int(row) - lane, b);
 #pragma unroll
           for (int i = 0; i < 4; ++i) rcur[i] = rnxt[i];
         }
@@ -363,6 +368,7 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
+    if (q.tma_out && lane == 0) tma_store_wait_all();   // the staging buffer must outlive the bulk stores that read it
   }
 
   tc_fence_before();
@@ -492,8 +498,8 @@ static int make_tmap_sf(CUtensorMap* out, const void* base, uint64_t bytes, uint
 }
 
 template <int NCTA, int BN, int EPI>
-static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tsa, const CUtensorMap& tsb, const Gemm4Params& q,
-                      cudaStream_t st) {
+static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tsa, const CUtensorMap& tsb, const CUtensorMap& to,
+                      const Gemm4Params& q, cudaStream_t st) {
   using Cfg = G4Cfg<NCTA, BN>;
   auto kern = gemm_nvfp4_kernel<NCTA, BN, EPI>;
   static std::once_flag once;
@@ -514,7 +520,7 @@ static int launch_fp4(const CUtensorMap& ta, const CUtensorMap& tw, const CUtens
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, tsa, tsb, q);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, tsa, tsb, to, q);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return fail(FX_ERR_CUDA, "gemm_nvfp4_kernel launch: %s", cudaGetErrorString(e));
@@ -589,8 +595,24 @@ extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
   p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
-  if (ncta == 2) return launch_fp4<2, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
-  return launch_fp4<1, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  // bf16 outputs leave through TMA stores when the output view is TMA-addressable (16-byte aligned base and strides)
+  CUtensorMap to = tsa;
+  static int tma_out = -1;
+  if (tma_out < 0) {
+    const char* e = getenv("FX_GEMM4_TMA_OUT");
+    tma_out = e ? atoi(e) : 1;
+  }
+  q.tma_out = 0;
+  if (tma_out && !a->out_f32 && aligned16(a->out) && a->ldo % 8 == 0 && a->out_bs % 8 == 0 && a->N % 8 == 0) {
+    const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->rows, (uint64_t)a->batch};
+    const uint64_t strides[2] = {(uint64_t)a->ldo * 2, (uint64_t)(a->batch > 1 ? a->out_bs : (long long)a->rows * a->ldo) * 2};
+    const uint32_t box[3] = {32, 32, 1};
+    rc = make_tmap_bf16(&to, a->out, 3, dims, strides, box, false, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    q.tma_out = 1;
+  }
+  if (ncta == 2) return launch_fp4<2, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, to, q, (cudaStream_t)stream);
+  return launch_fp4<1, G4_BN, EPI_GENERIC>(ta, tw, tsa, tsb, to, q, (cudaStream_t)stream);
 }
 
 extern "C" int fx_gemm_fp4_qkv(const fx_gemm4_qkv_args* a, fx_stream stream) {
@@ -618,6 +640,6 @@ extern "C" int fx_gemm_fp4_qkv(const fx_gemm4_qkv_args* a, fx_stream stream) {
   p.pe_blocked = a->pe_blocked;
   p.q = (__nv_bfloat16*)a->q; p.k = (__nv_bfloat16*)a->k; p.v = (__nv_bfloat16*)a->v;
   p.qkv_f8 = a->qkv_fp8 ? 1 : 0;
-  if (ncta == 2) return launch_fp4<2, 128, EPI_QKV>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
-  return launch_fp4<1, 128, EPI_QKV>(ta, tw, tsa, tsb, q, (cudaStream_t)stream);
+  if (ncta == 2) return launch_fp4<2, 128, EPI_QKV>(ta, tw, tsa, tsb, tsa, q, (cudaStream_t)stream);
+  return launch_fp4<1, 128, EPI_QKV>(ta, tw, tsa, tsb, tsa, q, (cudaStream_t)stream);
 }

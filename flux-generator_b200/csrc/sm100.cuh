@@ -450,4 +450,36 @@ __device__ __forceinline__ void store_chunk32_coalesced(uint8_t* wst, int lane, 
   __syncwarp();
 }
 
+// ------------------------------------------------------------------ TMA stores (shared -> global, bulk async group)
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// store_chunk32_coalesced with the global half done by the TMA engine: the warp stages its 32 rows x 32 bf16 columns in the same
+// XOR-swizzled 2 KB buffer (= CU_TENSOR_MAP_SWIZZLE_64B of a [32 rows][64 bytes] box; wst 512-byte aligned) and one lane issues a
+// single bulk tensor store -- no LDS / address arithmetic / four STG per lane, rows and columns past the tensor are clipped by
+// the tensor map.  The buffer is reused only after the previous store of this warp has read it (wait_group.read).
+__device__ __forceinline__ void store_chunk32_tma(uint8_t* wst, int lane, const float* f, const void* tmap, int col, int row0, int b) {
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(f[8 * j], f[8 * j + 1]); u.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]); u.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(wst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = u;
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tmap, wst, col, row0, b);
+    tma_store_commit();
+  }
+}
+
 }  // namespace fx

@@ -26,7 +26,7 @@ inline tmap_encode_fn get_tmap_encode() {
 // bf16 (or, u8 = true, byte / FP8) tensor, 128-byte swizzle, zero OOB fill.  dims/box innermost first;
 // strides (bytes) for dims 1..rank-1.
 inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                          const uint32_t* box, bool u8 = false) {
+                          const uint32_t* box, bool u8 = false, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   tmap_encode_fn fn = get_tmap_encode();
   if (!fn) return fail(FX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gd[5];
@@ -40,7 +40,7 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
     if (i > 0) gs[i - 1] = strides[i - 1];
   }
   CUresult r = fn(out, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(FX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",

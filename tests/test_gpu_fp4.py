@@ -63,7 +63,8 @@ def test_quantize_rows_fp4_bit_exact_vs_oracle(B, R, K):
         ops.quantize_rows_fp4(rnd(4, 100))        # K must be a multiple of 64
 
 
-@pytest.mark.parametrize("B,R,N,K", [(1, 128, 192, 256), (2, 256, 3072, 3072), (1, 200, 500, 1024), (8, 128, 384, 15360)])
+@pytest.mark.parametrize("B,R,N,K", [(1, 128, 192, 256), (2, 256, 3072, 3072), (1, 200, 500, 1024), (8, 128, 384, 15360),
+                                     (1, 200, 384, 512), (3, 384, 200, 256)])
 def test_gemm_fp4_vs_dequantised_matmul(B, R, N, K):
     a, w = rnd(B, R, K, seed=2), rnd(N, K, seed=3, scale=K ** -0.5)
     a4, sfa, sa = ops.quantize_rows_fp4(a)
@@ -85,6 +86,11 @@ def test_gemm_fp4_vs_dequantised_matmul(B, R, N, K):
     assert rel_l2(buf[:, :, :N], want) <= 5e-3 and torch.equal(buf[:, :, N:], res[:, :, N:])
     act = ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=bias, act="gelu_tanh")
     assert rel_l2(act, torch.nn.functional.gelu(ref.view(B, R, N) + bias.float(), approximate="tanh")) <= 5e-3
+    # bf16 output into a column window of a wider, row-padded buffer (the GELU -> `cat` case; TMA stores clip rows / columns)
+    wide = torch.full((B, R + 3, N + 64), 7.0, device=dev, dtype=bf)
+    ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=bias, out=wide[:, :R, 32:32 + N])
+    assert rel_l2(wide[:, :R, 32:32 + N], ref.view(B, R, N) + bias.float()) <= 5e-3
+    assert (wide[:, R:] == 7.0).all() and (wide[:, :, :32] == 7.0).all() and (wide[:, :, 32 + N:] == 7.0).all()
 
 
 @pytest.mark.parametrize("B,R,H,K,off,f8out", [(1, 128, 1, 256, 0, False), (2, 256, 3, 3072, 32, False), (1, 200, 2, 1024, 40, False),
