@@ -379,8 +379,9 @@ def main_arm(args) -> None:
     torch.cuda.synchronize()
     text_ms = te[0].elapsed_time(te[1])
 
-    # ---- --quantize leg (reported beside the bf16 headline, never in its place): the block Linears as FP8 e4m3
-    # tcgen05 GEMMs (W8A8, per-row scales, fp32 accumulate); same workload, device-resident inputs
+    # ---- --quantize legs (reported beside the bf16 headline, never in its place); same workload, device-resident inputs.
+    # `quantized` = the CLI's --quantize (4-bit like the reference's: NVFP4 W4A4 block Linears + e4m3 attention);
+    # `quantized.fp8` = --quantize --quantize-bits 8 (FP8 e4m3 W8A8 block Linears + e4m3 attention)
     quant = None
     if not args.no_quantized:
         pipe.flow.quantize()
@@ -398,15 +399,18 @@ def main_arm(args) -> None:
         pipe.flow.quantize(bits=4)
         split_events.clear()
         q4_ms, _, q4_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
-        quant["nvfp4"] = {
+        quant4 = {
             "dtype": "nvfp4 (block Linears W4A4: e2m1 + UE4M3 scale per 16 + fp32 row / channel scales, fp32 accumulate; attention e4m3; "
                      "embedders / final layer / VAE bf16)",
             "value": B * world * args.steps / (q4_ms * 1e-3), "unit": UNIT, "ms_per_step": q4_ms / args.steps,
             "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
-            "clocks": q4_clocks, "flag": "txt2image.py --quantize --quantize-bits 4 / Flux.quantize(bits=4)",
+            "clocks": q4_clocks, "flag": "txt2image.py --quantize / Flux.quantize(bits=4)",
             "parity": "tests/test_gpu_fp4.py (quantiser bit-exact vs the oracle, GEMM / QKV epilogue vs dequantised fp32 matmul), "
                       "tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (latents rel-L2 vs the fp32 oracle 1.1e-2 .. 2.3e-2 per "
                       "step, image mean |diff| 1.48/255; the reference's own --quantize is 4-bit weights, txt2image.py:79-82)"}
+        quant["flag"] = "txt2image.py --quantize --quantize-bits 8 / Flux.quantize()"
+        quant4["fp8"] = quant
+        quant = quant4
 
     if rank == 0:
         pk = peaks()

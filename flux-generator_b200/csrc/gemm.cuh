@@ -397,14 +397,16 @@ __device__ __forceinline__ void epi_qkv_group(const GemmParams& p, int b, long l
   const int head = hidx - which * p.heads;
   __nv_bfloat16* dst = (which == 0 ? p.q : (which == 1 ? p.k : p.v)) + (((long long)b * p.heads + head) * p.seq_total + pos) * 128;
   // dequantise (or just add the bias to) one chunk: x = acc * rs * w + bias
+  const uint64_t rs2 = pack2f(rs, rs);
   auto load_chunk = [&](const uint32_t* v, int c, float* x) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 t = *reinterpret_cast<const float4*>(sb + c * 32 + i);
-      if (F8) {
+      if (F8) {  // packed fp32 pairs (FMUL2 / FFMA2): the same roundings as fmaf(v, rs * w, t), half the issue slots
         const float4 w = *reinterpret_cast<const float4*>(sw + c * 32 + i);
-        x[i] = fmaf(__uint_as_float(v[i]), rs * w.x, t.x); x[i + 1] = fmaf(__uint_as_float(v[i + 1]), rs * w.y, t.y);
-        x[i + 2] = fmaf(__uint_as_float(v[i + 2]), rs * w.z, t.z); x[i + 3] = fmaf(__uint_as_float(v[i + 3]), rs * w.w, t.w);
+        const float2 lo = unpack2f(ffma2(pack2f(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), fmul2(rs2, pack2f(w.x, w.y)), pack2f(t.x, t.y)));
+        const float2 hi = unpack2f(ffma2(pack2f(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), fmul2(rs2, pack2f(w.z, w.w)), pack2f(t.z, t.w)));
+        x[i] = lo.x; x[i + 1] = lo.y; x[i + 2] = hi.x; x[i + 3] = hi.y;
       } else {
         x[i] = __uint_as_float(v[i]) + t.x; x[i + 1] = __uint_as_float(v[i + 1]) + t.y;
         x[i + 2] = __uint_as_float(v[i + 2]) + t.z; x[i + 3] = __uint_as_float(v[i + 3]) + t.w;

@@ -395,7 +395,7 @@ struct Quant4Params {
   int batch, rows, K;
 };
 template <int ITERS>  // ITERS = ceil(K / 2048)
-__global__ void __launch_bounds__(256, ITERS > 6 ? 3 : 4) quantize_rows_fp4_kernel(const Quant4Params p) {
+__global__ void __launch_bounds__(256, 4) quantize_rows_fp4_kernel(const Quant4Params p) {
   // The row stays in registers as PACKED bf16 (4 registers per 8 elements; unpacked fp32 copies cost 90 registers at
   // K = 15360 -> two resident blocks per SM and 2.3 TB/s, against 5.7 TB/s for the K = 12288 instance); the block maxima are
   // taken on packed pairs (|x| and max are exact in bf16).

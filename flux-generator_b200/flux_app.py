@@ -130,7 +130,7 @@ class FluxAPI:
                 kw["device"] = self.device
             self.pipeline = flux.FluxPipeline(flux_model, **kw)
             if self.quantize:
-                self.pipeline.flow.quantize()
+                self.pipeline.flow.quantize(bits=4)   # like txt2image.py --quantize (the reference quantises to 4 bits)
             self.current_model = flux_model
         return self.pipeline
 
@@ -320,7 +320,7 @@ def main(argv=None):
     listen_group = parser.add_mutually_exclusive_group()
     listen_group.add_argument("--listen-all", action="store_true", help="Listen on all network interfaces (0.0.0.0)")
     parser.add_argument("--synthetic", action="store_true", help="seeded random weights / tokenizers (no checkpoints offline)")
-    parser.add_argument("--quantize", "-q", action="store_true", help="FP8 block Linears (Flux.quantize)")
+    parser.add_argument("--quantize", "-q", action="store_true", help="NVFP4 (W4A4) block Linears + e4m3 attention (Flux.quantize(bits=4))")
     parser.add_argument("--gpus", type=int, default=1, help="worker processes, one per GPU; coalesced batches are spread over them")
     args = parser.parse_args(argv)
     host = "0.0.0.0" if args.listen_all else "127.0.0.1"

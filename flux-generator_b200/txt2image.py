@@ -43,8 +43,9 @@ def build_parser():
     parser.add_argument("--n-rows", type=int, default=1)
     parser.add_argument("--decoding-batch-size", type=int, default=1)
     parser.add_argument("--quantize", "-q", action="store_true")
-    parser.add_argument("--quantize-bits", type=int, choices=[8, 4], default=8,
-                        help="with --quantize: 8 = FP8 e4m3 Linears + attention (default), 4 = additionally NVFP4 (W4A4) for the K-long Linears")
+    parser.add_argument("--quantize-bits", type=int, choices=[8, 4], default=4,
+                        help="with --quantize: 4 = NVFP4 (W4A4) block Linears + e4m3 attention (default: the reference's --quantize is "
+                             "4-bit too), 8 = FP8 e4m3 Linears + attention")
     parser.add_argument("--preload-models", action="store_true")
     parser.add_argument("--output", default="out.png")
     parser.add_argument("--save-raw", action="store_true")
@@ -95,7 +96,7 @@ def main(argv=None):
     if args.adapter:  # txt2image.py:76-77
         from flux.lora import load_adapter
         load_adapter(flux, args.adapter, fuse=args.fuse_adapter)
-    if args.quantize:  # txt2image.py:79-82 quantises flow / t5 / clip; here: the flow model's block Linears -> FP8
+    if args.quantize:  # txt2image.py:79-82 quantises flow / t5 / clip to 4 bits; here: the flow model's block Linears -> NVFP4 / FP8
         flux.flow.quantize(bits=args.quantize_bits)
     if args.preload_models:
         flux.ensure_models_are_loaded()

@@ -90,6 +90,8 @@ def main(which, sweep=None):
         wp4, wpsf, wps4 = ops.fp4_weight(wproj)
         ca4, casf4, cas4 = ops.quantize_rows_fp4(cat[:, S:, :D])
         q8o, k8o, v8o = (torch.empty(B, H, N, 128, device=dev, dtype=ops.fp8) for _ in range(3))
+        f4bufs = (torch.empty(B * N * D // 2, device=dev, dtype=torch.uint8), torch.empty(B * N * D // 16, device=dev, dtype=torch.uint8),
+                  torch.empty(B * N, device=dev))
     tests = {
         "linear1": (lambda: ops.gemm_qkv(xm, w1, b1, qs, ks, pe, q, k, v, 0, mlp_out=cat[:, :, D:]), 2.0 * B * N * (3 * D + M) * D),
         "linear2": (lambda: ops.gemm(cat, w2, b2, gate=gate, resid=x, out=x), 2.0 * B * N * D * (D + M)),
@@ -116,6 +118,8 @@ def main(which, sweep=None):
         "fc2_f4": (lambda: ops.gemm_fp4(catm4, cmsf4, cms4, wf24, wf2sf, wf2s4, B, bias=b2, gate=gate, resid=x[:, S:], out=x[:, S:]), 2.0 * B * L * D * M),
         "quant_cat_f4": (lambda: ops.quantize_rows_fp4(cat), 0.0),
         "quant_x_f4": (lambda: ops.quantize_rows_fp4(xm), 0.0),
+        "quant_mlp_f4": (lambda: ops.quantize_rows_fp4(cat[:, S:, D:]), 0.0),
+        "rownorm_f4": (lambda: ops.rownorm(x, 0, shift, scale, 1e-6, out_fp4=f4bufs), 0.0),
         "qkv1_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q8o, k8o, v8o, 0), 2.0 * B * N * 3 * D * D),
         "qkv1_bf16out_f4": (lambda: ops.gemm_fp4_qkv(xm4, xmsf4, xms4, wq4, wqsf, wqs4, B, b1[:3 * D], qs, ks, pe, q, k, v, 0), 2.0 * B * N * 3 * D * D),
         "mlp1_f4": (lambda: ops.gemm_fp4(xm4, xmsf4, xms4, wm4, wmsf, wms4, B, bias=b1[3 * D:], act="gelu_tanh", out=cat[:, :, D:]), 2.0 * B * N * M * D),
@@ -141,7 +145,8 @@ def main(which, sweep=None):
         fn, fl = tests[name]
         ms, tf = sustained(fn, fl)
         nbytes = {"rownorm": 4 * x.numel(), "rownorm_f8": 3 * x.numel(), "quant_cat_f8": 3 * cat.numel(),
-                  "quant_cat_f4": 2.5625 * cat.numel(), "quant_x_f4": 2.5625 * xm.numel()}.get(name)
+                  "quant_cat_f4": 2.5625 * cat.numel(), "quant_x_f4": 2.5625 * xm.numel(),
+                  "quant_mlp_f4": 2.5625 * B * L * M, "rownorm_f4": 2.5625 * x.numel()}.get(name)
         extra = f" = {nbytes / ms / 1e6:.0f} GB/s" if nbytes else f" = {tf:.0f} TFLOP/s"
         print(f"{name:10s} {ms:8.3f} ms{extra}{last_clock}", flush=True)
 
