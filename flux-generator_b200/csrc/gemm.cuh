@@ -200,7 +200,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
                                                   int n0, bool fast, const float* sw = nullptr, float rs = 1.f,
                                                   uint8_t* wst = nullptr, int lane = 0, uint32_t vmask = 0, bool valid = true,
                                                   long long lane_off = -1, long long ld_hi = -1, const void* tmap_out = nullptr,
-                                                  int t_row0 = 0, int t_b = 0) {
+                                                  int t_row0 = 0, int t_b = 0, bool math_only = false) {
   if (F8) {  // dequantise: acc * a_scale[row] * w_scale[n], then + bias -- on packed fp32 pairs (FMUL2 / FFMA2: same roundings)
     const uint64_t rs2 = pack2f(rs, rs);
 #pragma unroll
@@ -253,6 +253,7 @@ __device__ __forceinline__ void epi_generic_chunk(const GemmParams& p, float* f,
       f[i] = lo.x; f[i + 1] = lo.y; f[i + 2] = hi.x; f[i + 3] = hi.y;
     }
   }
+  if (math_only) return;  // f[] = act(acc * scales + bias) (* gate): the caller consumes it (NVFP4 operand producer)
   if (fast) {
     if (p.resid && valid) {
       const __nv_bfloat16* r = p.resid + res_off + n0;

@@ -85,11 +85,67 @@ __host__ __device__ constexpr uint32_t make_idesc_nvf4(int M, int N) {
   return (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// Destination of a producer that emits an NVFP4 operand chunk by chunk (32 columns of a row at a time): e2m1 rows, UE4M3
+// scale atoms and one power-of-two exponent per chunk; fx_fp4_finalize then lifts the block scales to the row's scale
+// (oracle: nvfp4_quant_rows_chunked).  kc = total columns (K) of the consumer's operand.  The exponents mirror the scale atoms:
+// 256 bytes per (128-row block, K-group of 64): byte (r % 32) * 8 + (r / 32) * 2 + (chunk & 1) -- so the finalise pass reads the
+// exponents of the four rows whose scales share a 16-byte atom piece with one 8-byte load.
+struct ChunkQ {
+  uint8_t* q;
+  uint8_t* sf;
+  int8_t* e;
+  int kc;
+  int col0;   // column of the operand at which this producer's column 0 lands
+};
 struct Gemm4Params {
   GemmParams g;              // shapes, raster, generic epilogue (a_scale / w_scale = the second-level scales)
   int k_groups;              // K / 64
   int tma_out;               // generic epilogue, bf16 output: chunks leave through TMA stores (tmap_out)
+  ChunkQ out4;               // q != nullptr: the generic epilogue writes the NEXT GEMM's NVFP4 operand instead of `out`
 };
+
+// one chunk (32 values of flattened row m, operand columns [col, col + 32)) -> 16 bytes of e2m1, two UE4M3 block scales, the
+// chunk's exponent.  Every step a single IEEE fp32 operation (bit-exact against the oracle for identical inputs).
+__device__ __forceinline__ void fp4_chunk_quantise(const float* f, long long m, int col, const ChunkQ& o, bool valid) {
+  float bm[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bm[0] = fmaxf(bm[0], fabsf(f[i]));
+    bm[1] = fmaxf(bm[1], fabsf(f[16 + i]));
+  }
+  const float t = __fmul_rn(fmaxf(bm[0], bm[1]), 1.0f / 2688.0f);
+  const uint32_t tb = __float_as_uint(t);
+  int e = int((tb >> 23) & 255u) - 127 + ((tb & 0x7fffffu) != 0u ? 1 : 0);   // smallest e with 2^e >= t
+  e = e < -100 ? -100 : e;
+  const float g = __uint_as_float(uint32_t(127 + e) << 23), inv_g = __uint_as_float(uint32_t(127 - e) << 23);
+  uint32_t w[4];
+  uint32_t sfw = 0;
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const float u = __fmul_rn(__fmul_rn(bm[b], 1.0f / 6.0f), inv_g);
+    const __nv_fp8_storage_t sf8 = __nv_cvt_float_to_fp8(u, __NV_SATFINITE, __NV_E4M3);
+    const float d = __fmul_rn(__half2float(__half(__nv_cvt_fp8_to_halfraw(sf8, __NV_E4M3))), g);
+    const float rd = d > 0.f ? __frcp_rn(d) : 0.f;
+    sfw |= uint32_t(sf8) << (8 * b);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t x = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        x |= uint32_t(__nv_cvt_float2_to_fp4x2(make_float2(__fmul_rn(f[16 * b + 8 * h + i], rd), __fmul_rn(f[16 * b + 8 * h + i + 1], rd)),
+                                               __NV_E2M1, cudaRoundNearest))
+             << (4 * i);
+      w[2 * b + h] = x;
+    }
+  }
+  if (valid) {
+    *reinterpret_cast<uint4*>(o.q + m * (long long)(o.kc / 2) + (col >> 1)) = make_uint4(w[0], w[1], w[2], w[3]);
+    const int rr = int(m & 127);
+    *reinterpret_cast<uint16_t*>(o.sf + ((m >> 7) * (long long)(o.kc / 64) + (col >> 6)) * 512 + (rr & 31) * 16 + (rr >> 5) * 4 +
+                                 ((col >> 4) & 3)) = uint16_t(sfw);
+    o.e[((m >> 7) * (long long)(o.kc / 64) + (col >> 6)) * 256 + (rr & 31) * 8 + (rr >> 5) * 2 + ((col >> 5) & 1)] = int8_t(e);
+  }
+}
 
 // tmap_sfa / tmap_sfb: the scale-atom buffers viewed as [bytes / 128][128] byte matrices (no swizzle): one stage's atoms of a
 // row block / column tile are 16 / 32 consecutive rows, fetched by TMA like the operands (and, for a pair, credited to the
@@ -353,6 +409,11 @@ gemm_nvfp4_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           if (c + 1 < CH) tmem_ld_x32(taddr + group * WN + (c + 1) * 32, v);   // in flight while this chunk is processed
+          if (q.out4.q != nullptr) {  // bias + activation, then straight to the next GEMM's NVFP4 operand (no bf16 round trip)
+            epi_generic_chunk<true>(p, f, sb + c * 32, sg + c * 32, rcur, false, 0, 0, n0, true, sw + c * 32, rs, nullptr, lane, vmask,
+                                    valid, -1, -1, nullptr, 0, 0, true);
+            fp4_chunk_quantise(f, (long long)b * p.rows + row, q.out4.col0 + n0, q.out4, valid && vmask != 0u);
+          } else
           epi_generic_chunk<true>(p, f, sb + c * 32, sg + c * 32, rcur, rr_ok, out_off, res_off, n0, vec_ok && (n0 + 32 <= p.N),
                                   sw + c * 32, rs, wst, lane, vmask, valid, -1, -1, (q.tma_out && vmask != 0u) ? &tmap_out : nullptr,
                                   int(row) - lane, b);
@@ -458,6 +519,94 @@ __global__ void __launch_bounds__(256, 4) quantize_rows_fp4_kernel(const Quant4P
       w |= uint32_t(__nv_cvt_float2_to_fp4x2(make_float2(__fmul_rn(v.x, rd), __fmul_rn(v.y, rd)), __NV_E2M1, cudaRoundNearest)) << (8 * e);
     }
     if (in) *reinterpret_cast<uint32_t*>(qr + (c >> 1)) = w;
+  }
+}
+
+// ------------------------------------------------------------------ chunked NVFP4 producer for a bf16 tensor + finalise
+// x bf16 [batch][rows][C] (C % 32 == 0) -> columns [col0, col0 + C) of the operand described by ChunkQ: one thread per chunk.
+struct QuantChunksParams {
+  const __nv_bfloat16* x; long long ldx, x_bs;
+  int batch, rows, C;
+  ChunkQ o;
+};
+__global__ void __launch_bounds__(256) quantize_chunks_fp4_kernel(const QuantChunksParams p) {
+  const int cpr = p.C / 32;  // chunks per row
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long m = idx / cpr;
+  if (m >= (long long)p.batch * p.rows) return;
+  const int c = int(idx - m * cpr);
+  const int b = int(m / p.rows);
+  const long long r = m - (long long)b * p.rows;
+  const uint4* src = reinterpret_cast<const uint4*>(p.x + b * p.x_bs + r * p.ldx + c * 32);
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(src + i);
+    const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
+    f[8 * i] = a0.x; f[8 * i + 1] = a0.y; f[8 * i + 2] = a1.x; f[8 * i + 3] = a1.y;
+    f[8 * i + 4] = a2.x; f[8 * i + 5] = a2.y; f[8 * i + 6] = a3.x; f[8 * i + 7] = a3.y;
+  }
+  fp4_chunk_quantise(f, m, p.o.col0 + c * 32, p.o, true);
+}
+
+// Finalise: row exponent = max over the row's chunk exponents, scale[row] = 2^that, every block scale shifted from its chunk's
+// exponent to the row's (e4m3_rn of an exact product: an exponent shift unless the result is subnormal).  One 256-thread block
+// per 128-row block; lane l of every warp owns rows l, l + 32, l + 64, l + 96 (one 16-byte piece of every scale atom, one
+// 8-byte piece of every exponent group); the eight warps split the K-groups.
+__global__ void __launch_bounds__(256) fp4_finalize_kernel(uint8_t* sf, const int8_t* e, float* scale, int kc) {
+  __shared__ int s_max[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long rb = blockIdx.x;
+  const int kg = kc / 64;
+  const uint2* eg = reinterpret_cast<const uint2*>(e + rb * (long long)kg * 256) + lane;
+  int mx[4] = {-128, -128, -128, -128};
+#pragma unroll 4
+  for (int k = warp; k < kg; k += 8) {
+    const uint2 w = eg[k * 32];
+    const uint32_t ws[2] = {w.x, w.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t h = ws[q >> 1] >> (16 * (q & 1));
+      mx[q] = max(mx[q], max(int(int8_t(h)), int(int8_t(h >> 8))));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s_max[warp][q * 32 + lane] = mx[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    int m = s_max[0][q * 32 + lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = max(m, s_max[w][q * 32 + lane]);
+    mx[q] = m;
+    if (warp == 0) scale[rb * 128 + q * 32 + lane] = __uint_as_float(uint32_t(127 + m) << 23);
+  }
+  uint4* atoms = reinterpret_cast<uint4*>(sf + rb * (long long)kg * 512) + lane;
+#pragma unroll 2
+  for (int k = warp; k < kg; k += 8) {
+    const uint2 ew = eg[k * 32];
+    const uint32_t es[2] = {ew.x, ew.y};
+    const uint4 w = atoms[k * 32];
+    uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t ee = es[q >> 1] >> (16 * (q & 1));
+      uint32_t out = 0;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {   // the two chunks (= two blocks of 16 each) of this K-group
+        int sh = mx[q] - int(int8_t(ee >> (8 * c)));
+        sh = sh > 60 ? 60 : sh;
+        const float f2 = __uint_as_float(uint32_t(127 - sh) << 23);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int s4 = 2 * c + t;
+          const float v = __half2float(__half(__nv_cvt_fp8_to_halfraw(__nv_fp8_storage_t((ws[q] >> (8 * s4)) & 255u), __NV_E4M3)));
+          out |= uint32_t(__nv_cvt_float_to_fp8(__fmul_rn(v, f2), __NV_SATFINITE, __NV_E4M3)) << (8 * s4);
+        }
+      }
+      ws[q] = out;
+    }
+    atoms[k * 32] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
   }
 }
 
@@ -579,7 +728,7 @@ static int fp4_setup(Gemm4Params& q, const void* A, const void* sfa, const void*
 }
 
 extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
-  FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && a->out, "fx_gemm_fp4: null pointer");
+  FX_REQUIRE(a && a->A && a->W && a->sfa && a->sfw && a->a_scale && a->w_scale && (a->out || a->q_out), "fx_gemm_fp4: null pointer");
   FX_REQUIRE(a->batch > 0 && a->rows > 0 && a->N > 0 && a->K > 0, "fx_gemm_fp4: empty problem");
   FX_REQUIRE(a->K % 256 == 0, "fx_gemm_fp4: K (%d) must be a multiple of 256", a->K);
   FX_REQUIRE(a->rows % 128 == 0 || a->batch == 1, "fx_gemm_fp4: rows per batch element (%d) must be a multiple of 128", a->rows);
@@ -595,6 +744,13 @@ extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
   p.out = a->out; p.ldo = a->ldo; p.out_bs = a->out_bs; p.out_f32 = a->out_f32; p.act = a->act;
   p.gate = (const __nv_bfloat16*)a->gate; p.gate_bs = a->gate_bs;
   p.resid = (const __nv_bfloat16*)a->resid; p.ldr = a->ldr; p.resid_bs = a->resid_bs;
+  if (a->q_out) {  // emit the next GEMM's NVFP4 operand instead of `out`
+    FX_REQUIRE(a->sf_out && a->e_out && !a->gate && !a->resid, "fx_gemm_fp4: q_out needs sf_out and e_out and takes no gate / residual");
+    FX_REQUIRE(a->N % 64 == 0 && a->out_kc % 128 == 0 && a->out_col0 % 64 == 0 && a->out_col0 + a->N <= a->out_kc &&
+                   (a->rows % 128 == 0) && aligned16(a->q_out) && aligned16(a->sf_out),
+               "fx_gemm_fp4: q_out needs N %% 64 == 0, rows %% 128 == 0, out_kc %% 128 == 0, out_col0 %% 64 == 0 inside out_kc");
+    q.out4 = ChunkQ{(uint8_t*)a->q_out, (uint8_t*)a->sf_out, (int8_t*)a->e_out, a->out_kc, a->out_col0};
+  }
   // bf16 outputs leave through TMA stores when the output view is TMA-addressable (16-byte aligned base and strides)
   CUtensorMap to = tsa;
   static int tma_out = -1;
@@ -603,7 +759,7 @@ extern "C" int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream) {
     tma_out = e ? atoi(e) : 1;
   }
   q.tma_out = 0;
-  if (tma_out && !a->out_f32 && aligned16(a->out) && a->ldo % 8 == 0 && a->out_bs % 8 == 0 && a->N % 8 == 0) {
+  if (tma_out && !a->q_out && !a->out_f32 && aligned16(a->out) && a->ldo % 8 == 0 && a->out_bs % 8 == 0 && a->N % 8 == 0) {
     const uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)a->rows, (uint64_t)a->batch};
     const uint64_t strides[2] = {(uint64_t)a->ldo * 2, (uint64_t)(a->batch > 1 ? a->out_bs : (long long)a->rows * a->ldo) * 2};
     const uint32_t box[3] = {32, 32, 1};
@@ -642,4 +798,25 @@ extern "C" int fx_gemm_fp4_qkv(const fx_gemm4_qkv_args* a, fx_stream stream) {
   p.qkv_f8 = a->qkv_fp8 ? 1 : 0;
   if (ncta == 2) return launch_fp4<2, 128, EPI_QKV>(ta, tw, tsa, tsb, tsa, q, (cudaStream_t)stream);
   return launch_fp4<1, 128, EPI_QKV>(ta, tw, tsa, tsb, tsa, q, (cudaStream_t)stream);
+}
+
+extern "C" int fx_quantize_chunks_fp4(const fx_quant4c_args* a, fx_stream stream) {
+  FX_REQUIRE(a && a->x && a->q && a->sf && a->e, "fx_quantize_chunks_fp4: null pointer");
+  FX_REQUIRE(a->C > 0 && a->C % 64 == 0 && a->kc % 128 == 0 && a->col0 % 64 == 0 && a->col0 + a->C <= a->kc && a->ldx % 8 == 0 &&
+                 a->x_bs % 8 == 0 && aligned16(a->x) && aligned16(a->q) && aligned16(a->sf),
+             "fx_quantize_chunks_fp4: C %% 64, kc %% 128, col0 %% 64, 16-byte aligned rows required");
+  if (a->batch <= 0 || a->rows <= 0) return FX_OK;
+  QuantChunksParams p{(const __nv_bfloat16*)a->x, a->ldx, a->x_bs, a->batch, a->rows, a->C,
+                      ChunkQ{(uint8_t*)a->q, (uint8_t*)a->sf, (int8_t*)a->e, a->kc, a->col0}};
+  const long long chunks = (long long)a->batch * a->rows * (a->C / 32);
+  quantize_chunks_fp4_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  return launched("quantize_chunks_fp4_kernel");
+}
+
+extern "C" int fx_fp4_finalize(void* sf, const void* e, float* scale, int64_t rows, int32_t kc, fx_stream stream) {
+  FX_REQUIRE(sf && e && scale && rows > 0 && rows % 128 == 0 && kc > 0 && kc % 128 == 0 && aligned16(sf) &&
+                 (reinterpret_cast<uintptr_t>(e) & 7) == 0,
+             "fx_fp4_finalize: rows and kc must be multiples of 128, buffers aligned");
+  fp4_finalize_kernel<<<(unsigned)(rows / 128), 256, 0, (cudaStream_t)stream>>>((uint8_t*)sf, (const int8_t*)e, scale, kc);
+  return launched("fp4_finalize_kernel");
 }

@@ -72,7 +72,13 @@ class Gemm4Args(C.Structure):
     _fields_ = [("A", c_vp), ("sfa", c_vp), ("a_scale", c_vp), ("W", c_vp), ("sfw", c_vp), ("w_scale", c_vp), ("bias", c_vp),
                 ("out", c_vp), ("ldo", c_i64), ("out_bs", c_i64), ("out_f32", c_i32), ("act", c_i32),
                 ("gate", c_vp), ("gate_bs", c_i64), ("resid", c_vp), ("ldr", c_i64), ("resid_bs", c_i64),
-                ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32)]
+                ("batch", c_i32), ("rows", c_i32), ("N", c_i32), ("K", c_i32),
+                ("q_out", c_vp), ("sf_out", c_vp), ("e_out", c_vp), ("out_kc", c_i32), ("out_col0", c_i32)]
+
+
+class Quant4cArgs(C.Structure):
+    _fields_ = [("x", c_vp), ("ldx", c_i64), ("x_bs", c_i64), ("batch", c_i32), ("rows", c_i32), ("C", c_i32),
+                ("q", c_vp), ("sf", c_vp), ("e", c_vp), ("kc", c_i32), ("col0", c_i32)]
 
 
 class Gemm4QkvArgs(C.Structure):
@@ -99,6 +105,8 @@ SYMBOLS = {
     "fx_quantize_rows_fp4": (C.c_int, [C.POINTER(Quant4Args), c_vp]),
     "fx_gemm_fp4": (C.c_int, [C.POINTER(Gemm4Args), c_vp]),
     "fx_gemm_fp4_qkv": (C.c_int, [C.POINTER(Gemm4QkvArgs), c_vp]),
+    "fx_quantize_chunks_fp4": (C.c_int, [C.POINTER(Quant4cArgs), c_vp]),
+    "fx_fp4_finalize": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "fx_conv3x3": (C.c_int, [C.POINTER(ConvArgs), c_vp]),
     "fx_conv3x3_gn_blocks": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "fx_attention": (C.c_int, [C.POINTER(AttnArgs), c_vp]),

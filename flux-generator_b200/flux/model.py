@@ -115,6 +115,7 @@ class Flux:
         self._q8_attention = False                                  # --quantize: Q K^T and P V in FP8 as well
         self._q4: Dict[str, tuple] = {}   # --quantize 4: key -> (e2m1 weight, scale atoms, fp32 row scales)
         self._q4_all = False              # ... of every block Linear (fp4_scope "all") or only of fp4_keys() ("cat")
+        self._q4_fused = True             # scope "all": the GELU epilogue / attention-output quantiser emit mlp.2's / linear2's operand
         self._lora_cfg: Optional[Tuple[int, int]] = None       # (rank, num_blocks) after linear_to_lora_layers
         self._lora_pending: Dict[str, torch.Tensor] = {}       # adapter tensors loaded but not yet fused
 
@@ -165,7 +166,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:  # weights changed under a quantised model: requantise
             self._q8 = {}
-            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat")
+            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat", self._q4_fused)
         return self
 
     # ------------------------------------------------------------------ LoRA adapters (txt2image.py:32-39)
@@ -193,7 +194,7 @@ class Flux:
         self._graphs.clear()
         if self._q8:
             self._q8 = {}
-            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat")
+            self.quantize(self._q8_attention, 4 if self._q4 else 8, "all" if self._q4_all else "cat", self._q4_fused)
         return len(deltas)
 
     # ------------------------------------------------------------------ --quantize (txt2image.py:56,79-82)
@@ -223,7 +224,7 @@ class Flux:
         keys += [f"single_blocks.{i}.linear2" for i in range(p.depth_single_blocks)]
         return keys
 
-    def quantize(self, attention: bool = True, bits: int = 8, fp4_scope: str = "all") -> "Flux":
+    def quantize(self, attention: bool = True, bits: int = 8, fp4_scope: str = "all", fp4_fused: bool = True) -> "Flux":
         """Quantise the block Linears to FP8 e4m3 with one scale per output channel (fx_quantize_rows) and switch
         forward() to the FP8 tcgen05 path: activations are row-quantised by the producing norm kernel (or one
         extra pass for the attention | GELU(mlp) operand), accumulation stays fp32, outputs bf16.
@@ -232,7 +233,10 @@ class Flux:
         bits=4: the block Linears run as NVFP4 W4A4 (e2m1 + UE4M3 block scales + fp32 row scales,
         tcgen05.mma.kind::mxf4nvf4.block_scale; csrc/gemm4.cu) -- the analogue of the reference's 4-bit
         nn.quantize(group_size=64) (txt2image.py:28-29,79-82).  fp4_scope "all": every block Linear (qkv, proj, mlp.0,
-        mlp.2, linear1, linear2); "cat": only fp4_keys(), the rest stays FP8.  Shapes the NVFP4 kernel does not tile
+        mlp.2, linear1, linear2); "cat": only fp4_keys(), the rest stays FP8.  fp4_fused (scope "all"): the operands of mlp.2 and
+        linear2 are emitted by their producers -- the GELU epilogue of mlp.0 / linear1 writes e2m1 + block scales directly, the
+        attention output takes a chunk quantiser, fx_fp4_finalize lifts the chunk scales to the row's -- instead of a bf16
+        round trip through `cat` and the row quantiser (oracle: nvfp4_quant_rows_chunked).  Shapes the NVFP4 kernel does not tile
         (token counts that are not multiples of 128) fall back to the FP8 Linears, which are always prepared."""
         if bits not in (4, 8):
             raise ValueError("quantize(bits=...) must be 8 or 4")
@@ -241,6 +245,7 @@ class Flux:
         self._q8_attention = bool(attention)
         self._q4 = {k: ops.fp4_weight(self._w(k)) for k in self.fp4_keys()} if bits == 4 else {}
         self._q4_all = bits == 4 and fp4_scope == "all"
+        self._q4_fused = bool(fp4_fused)
         if self._q4_all:
             p, D3 = self.params, 3 * self.hidden_size
             for i in range(p.depth):
@@ -325,6 +330,8 @@ class Flux:
                 if self._q4 and N % 128 == 0 and L % 128 == 0 and S % 128 == 0:  # NVFP4 operand of proj / mlp.2 / linear2
                     u8 = lambda n: torch.empty((n,), device=dev, dtype=torch.uint8)  # noqa: E731
                     ws.update(a4=(u8(B * N * (D + M) // 2), u8(B * N * (D + M) // 16), torch.empty((B * N,), device=dev, dtype=torch.float32)))
+                    if self._q4_all and self._q4_fused:
+                        ws.update(c4=ops.Fp4Operand(B * N, D + M, dev))
                 ws.update(xm8=torch.empty((B, N, D), device=dev, dtype=ops.fp8),
                           cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
                           xs=torch.empty((B, N), device=dev, dtype=torch.float32),
@@ -510,6 +517,7 @@ class Flux:
         xm, xm8, cat8, xs, cs = ws["xm"], ws["xm8"], ws["cat8"], ws["xs"], ws["cs"]
         B = x.shape[0]
         f4 = self._q4_all and "a4" in ws   # NVFP4 for the norm-fed Linears too: the AdaLN row norm writes the NVFP4 operand
+        fused = f4 and "c4" in ws          # ... and the producers of mlp.2's / linear2's operand emit it directly
         for i in range(p.depth):
             pre = f"double_blocks.{i}."
             streams = (("img", slice(S, None), S), ("txt", slice(0, S), 0))
@@ -537,6 +545,13 @@ class Flux:
                 if f4:
                     a4, sfa, sa = ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out_fp4=ws["a4"])
                     w4, sfw, sw = self._q4[mlp + "0"]
+                    if fused:  # GELU epilogue -> mlp.2's NVFP4 operand; the hidden activation never exists in bf16
+                        dst = ws["c4"].view(a4.shape[0], p.mlp_hidden)
+                        ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=self._b(mlp + "0"), act="gelu_tanh", out4=dst)
+                        h4, sfh, sh = ops.fp4_finalize(dst)
+                        w4, sfw, sw = self._q4[mlp + "2"]
+                        ops.gemm_fp4(h4, sfh, sh, w4, sfw, sw, B, bias=self._b(mlp + "2"), gate=self._mod(ws, mk, 5), resid=xr, out=xr)
+                        continue
                     ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=self._b(mlp + "0"), act="gelu_tanh", out=cat[:, rows, D:])
                 else:
                     ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out=xm8[:, rows], out_scale=xs[:, rows])
@@ -554,6 +569,16 @@ class Flux:
                 ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, None if bias is None else bias[:3 * D], qn, kn, pe, q, k, v, 0,
                                  rms_eps=QK_RMS_EPS, pe_blocked=pe_blocked)
                 w4, sfw, sw = self._q4[pre + "linear1.mlp"]
+                if fused:  # linear2's operand = [attention | GELU(mlp)]: the mlp columns come from this epilogue, the attention
+                    dst = ws["c4"].view(a4.shape[0], D + p.mlp_hidden)   # columns from the chunk quantiser below
+                    ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=None if bias is None else bias[3 * D:], act="gelu_tanh", out4=dst,
+                                 out4_col0=D)
+                    ops.attention(q, k, v, cat[:, :, :D], scale)
+                    ops.quantize_chunks_fp4(cat[:, :, :D], dst, 0)
+                    c4, sfc, sc = ops.fp4_finalize(dst)
+                    w4, sfw, sw = self._q4[pre + "linear2"]
+                    ops.gemm_fp4(c4, sfc, sc, w4, sfw, sw, B, bias=self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x)
+                    continue
                 ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=None if bias is None else bias[3 * D:], act="gelu_tanh", out=cat[:, :, D:])
             else:
                 ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out=xm8, out_scale=xs)
@@ -595,7 +620,7 @@ class Flux:
         S = txt.shape[1]
         pe, _ = self._pe(txt_ids, img_ids)
         temb = self._txt_in(txt.to(bf16) if txt.dtype != bf16 else txt)
-        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8), bool(self._q4), self._q4_all)
+        key = (B, L, S, pe.data_ptr(), guidance is not None, uniform, mod_row is not None, bool(self._q8), bool(self._q4), self._q4_all, self._q4_fused)
         g = self._graphs.get(key)
         if g is None:
             D = self.hidden_size

@@ -383,12 +383,54 @@ def gemm_fp4_qkv(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4:
     N.check(N.lib().fx_gemm_fp4_qkv(C.byref(args), N.stream()))
 
 
+class Fp4Operand:
+    """Buffers of an NVFP4 operand that its PRODUCERS fill chunk by chunk (gemm_fp4(out4=...), quantize_chunks_fp4) and
+    fp4_finalize completes: e2m1 rows, UE4M3 scale atoms, per-chunk exponents, fp32 row scales.  `view(rows, kc)` carves the
+    tensors of one use from the flat buffers (no allocation on the hot path)."""
+
+    def __init__(self, max_rows: int, max_kc: int, device):
+        self.q = torch.empty((max_rows * max_kc // 2,), device=device, dtype=torch.uint8)
+        self.sf = torch.empty((max_rows * max_kc // 16,), device=device, dtype=torch.uint8)
+        self.e = torch.empty((max_rows * max_kc // 32,), device=device, dtype=torch.int8)
+        self.scale = torch.empty((max_rows,), device=device, dtype=torch.float32)
+
+    def view(self, rows: int, kc: int):
+        if rows % 128 or kc % 128:
+            raise ValueError("an NVFP4 operand needs multiples of 128 rows and columns")
+        return (self.q[:rows * kc // 2].view(rows, kc // 2), self.sf[:rows * kc // 16].view(rows // 128, kc // 64, 512),
+                self.e[:rows * kc // 32].view(rows, kc // 32), self.scale[:rows])
+
+
+def quantize_chunks_fp4(x: torch.Tensor, dst, col0: int = 0) -> None:
+    """x bf16 [B,R,C] -> columns [col0, col0 + C) of the operand `dst` = Fp4Operand.view(B * R, kc) (chunked form: call
+    fp4_finalize once every column of the operand has been produced)."""
+    _chk(x)
+    B, R, Cc, ldx, xbs = _as3(x)
+    q, sf, e, _ = dst
+    if q.shape[0] != B * R:
+        raise ValueError("operand rows do not match")
+    args = N.Quant4cArgs()
+    args.x, args.ldx, args.x_bs, args.batch, args.rows, args.C = x.data_ptr(), ldx, xbs, B, R, Cc
+    args.q, args.sf, args.e, args.kc, args.col0 = q.data_ptr(), sf.data_ptr(), e.data_ptr(), 2 * q.shape[1], col0
+    N.check(N.lib().fx_quantize_chunks_fp4(C.byref(args), N.stream()))
+
+
+def fp4_finalize(dst):
+    """Completes a chunk-produced operand (row scale = 2^max chunk exponent, block scales shifted to it); returns
+    (a4, sfa, a_scale) for gemm_fp4."""
+    q, sf, e, scale = dst
+    N.check(N.lib().fx_fp4_finalize(sf.data_ptr(), e.data_ptr(), scale.data_ptr(), q.shape[0], 2 * q.shape[1], N.stream()))
+    return q, sf, scale
+
+
 def gemm_fp4(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4: torch.Tensor, sfw: torch.Tensor,
              w_scale: torch.Tensor, batch: int, bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
              act=None, gate: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-             out_dtype: torch.dtype = bf16) -> torch.Tensor:
+             out_dtype: torch.dtype = bf16, out4=None, out4_col0: int = 0) -> Optional[torch.Tensor]:
     """out = resid + gate * act((a4 @ w4.T) * a_scale[:, None] * w_scale + bias) on tcgen05 kind::mxf4nvf4.block_scale.
-    a4 / sfa / a_scale from quantize_rows_fp4 (rows = batch * rows_per_batch), w4 / sfw / w_scale from fp4_weight."""
+    a4 / sfa / a_scale from quantize_rows_fp4 (rows = batch * rows_per_batch), w4 / sfw / w_scale from fp4_weight.
+    out4 = Fp4Operand.view(rows, kc): instead of `out`, act(. + bias) is written as columns [out4_col0, out4_col0 + N) of that
+    NVFP4 operand (the epilogue quantises; the result never exists in bf16); returns None."""
     _chk(a4, torch.uint8), _chk(w4, torch.uint8), _chk(sfa, torch.uint8), _chk(sfw, torch.uint8)
     _chk(a_scale, torch.float32), _chk(w_scale, torch.float32)
     rows_total, kb = a4.shape
@@ -396,16 +438,24 @@ def gemm_fp4(a4: torch.Tensor, sfa: torch.Tensor, a_scale: torch.Tensor, w4: tor
     if w4.shape[1] != kb or rows_total % batch:
         raise ValueError("fp4 operands do not match")
     R = rows_total // batch
-    if out is None:
-        out = torch.empty((batch, R, Nn), device=a4.device, dtype=out_dtype)
-    _chk(out, out.dtype)
-    _, _, _, ldo, obs = _as3(out)
     args = N.Gemm4Args()
     args.A, args.sfa, args.a_scale = a4.data_ptr(), sfa.data_ptr(), a_scale.data_ptr()
     args.W, args.sfw, args.w_scale = w4.data_ptr(), sfw.data_ptr(), w_scale.data_ptr()
     args.bias = N.ptr(bias)
-    args.out, args.ldo, args.out_bs = out.data_ptr(), ldo, obs
-    args.out_f32 = 1 if out.dtype == torch.float32 else 0
+    if out4 is not None:
+        q4, sf4, e4, _ = out4
+        if q4.shape[0] != rows_total or gate is not None or resid is not None:
+            raise ValueError("gemm_fp4(out4=...): operand rows must match and no gate / residual")
+        args.q_out, args.sf_out, args.e_out = q4.data_ptr(), sf4.data_ptr(), e4.data_ptr()
+        args.out_kc, args.out_col0 = 2 * q4.shape[1], out4_col0
+        out = None
+    else:
+        if out is None:
+            out = torch.empty((batch, R, Nn), device=a4.device, dtype=out_dtype)
+        _chk(out, out.dtype)
+        _, _, _, ldo, obs = _as3(out)
+        args.out, args.ldo, args.out_bs = out.data_ptr(), ldo, obs
+        args.out_f32 = 1 if out.dtype == torch.float32 else 0
     args.act = ACT[act]
     if gate is not None:
         _chk(gate)

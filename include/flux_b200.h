@@ -147,8 +147,25 @@ typedef struct fx_gemm4_args {
   const void* gate; int64_t gate_bs;
   const void* resid; int64_t ldr; int64_t resid_bs;
   int32_t batch, rows, N, K;
+  /* q_out != NULL: instead of `out`, the epilogue (bias, act) writes columns [out_col0, out_col0 + N) of the NEXT GEMM's NVFP4
+   * operand (K = out_kc): e2m1 rows q_out [batch * rows][out_kc / 2], scale atoms sf_out, one power-of-two exponent per 32-column
+   * chunk e_out int8 (256 bytes per 128-row block and K-group of 64, byte (r % 32) * 8 + (r / 32) * 2 + (chunk & 1): the scale atoms'
+   * order); fx_fp4_finalize completes the operand once every column has been produced
+   * (the GELU(mlp) hidden never exists in bf16).  N % 64 == 0, rows % 128 == 0, no gate / residual. */
+  void* q_out; void* sf_out; void* e_out; int32_t out_kc; int32_t out_col0;
 } fx_gemm4_args;
 int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream);
+
+/* The same chunked producer for a bf16 tensor x [batch][rows][C] (the attention output that shares `linear2`'s operand with the
+ * GELU(mlp) columns): C % 64 == 0; layout of q / sf / e as fx_gemm4_args.q_out. */
+typedef struct fx_quant4c_args {
+  const void* x; int64_t ldx; int64_t x_bs;
+  int32_t batch, rows, C;
+  void* q; void* sf; void* e; int32_t kc; int32_t col0;
+} fx_quant4c_args;
+int fx_quantize_chunks_fp4(const fx_quant4c_args* a, fx_stream stream);
+/* scale[row] = 2^max(e[row][:]); every block scale of sf shifted from its chunk's exponent to the row's.  rows % 128 == 0. */
+int fx_fp4_finalize(void* sf, const void* e, float* scale, int64_t rows, int32_t kc, fx_stream stream);
 
 /* fx_gemm_fp4_qkv: the NVFP4 form of fx_gemm_qkv (flux/layers.py:195-214: qkv Linear -> per-head QK-RMSNorm -> RoPE -> q, k, v
  * [batch][heads][seq_total][128] at rows seq_off + r, bf16 or e4m3).  N = 3 * heads * 128; tiles are one head (128 columns) wide,

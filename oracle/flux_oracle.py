@@ -44,7 +44,7 @@ class Mode:
     op rounded to bfloat16 (how an unfused bf16 MLX graph behaves: flux/flux.py:24)."""
 
     def __init__(self, name: str = "fp32", quantize: bool = False, quantize_attention: Optional[bool] = None, bits: int = 8,
-                 fp4_scope: str = "all"):
+                 fp4_scope: str = "all", fp4_fused: bool = True):
         assert name in ("fp32", "fp64", "bf16")
         self.name = name
         self.dtype = torch.float64 if name == "fp64" else torch.float32
@@ -58,6 +58,9 @@ class Mode:
         self.bits = bits
         assert fp4_scope in ("all", "cat")
         self.fp4_scope = fp4_scope
+        # fp4_fused (with fp4_scope "all"): the operands of mlp.2 / linear2 are emitted by their producers (GELU epilogue,
+        # attention-output quantiser) in the chunked form of nvfp4_quant_rows_chunked instead of the row quantiser's
+        self.fp4_fused = fp4_fused
         # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
         # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
         # e4m3 activations and weights (fx_quantize_rows in include/flux_b200.h), everything else is unchanged.
@@ -76,6 +79,9 @@ FP32 = Mode("fp32")
 
 
 FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|attn\.proj|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
+
+
+FP4_FUSED_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_mlp\.2|single_blocks\.\d+\.linear2)$")
 
 
 FP4_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.proj|mlp\.2)|single_blocks\.\d+\.linear2)$")
@@ -130,11 +136,44 @@ def nvfp4_quant_rows(x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     return q.reshape(x32.shape), sf, g
 
 
+def nvfp4_quant_rows_chunked(x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """The NVFP4 operand as the PRODUCING kernels emit it (fx_gemm_fp4 with q_out / fx_quantize_chunks_fp4, then fx_fp4_finalize):
+    the first-level scale cannot be the row's absmax (a GEMM epilogue sees 32 columns of a row at a time), so every chunk of 32
+    columns takes a power-of-two scale g_c = 2^e_c, e_c = ceil(log2(absmax(chunk) * (1/2688))) (>= -100), the two blocks of 16
+    quantise against it exactly like nvfp4_quant_rows does against g (sf = e4m3_rn(absmax(block) * (1/6) * 2^-e_c), d = sf * g_c,
+    q = e2m1_rn_sat(x * rcp(d))), and a finalise pass lifts everything to the row's scale g = 2^max(e_c): sf' = e4m3_rn(sf *
+    2^(e_c - e_row)) -- an exact exponent shift unless sf' leaves the normal range (blocks 2^-14 below the row maximum).
+    Returns (q values, sf' values [.., K/16], g [.., 1]); x ~= q * sf' * g."""
+    x32 = x.to(torch.float32)
+    K = x32.shape[-1]
+    cmax = x32.reshape(*x32.shape[:-1], K // 32, 32).abs().amax(dim=-1)
+    t = cmax * torch.tensor(1.0 / 2688.0, dtype=torch.float32)
+    mant, ex = torch.frexp(t)
+    e_c = torch.where(mant == 0.5, ex - 1, ex).clamp(min=-100)
+    e_c = torch.where(t > 0, e_c, torch.full_like(e_c, -100))
+    e_row = e_c.amax(dim=-1, keepdim=True)
+    one = torch.ones((), dtype=torch.float32)
+    ones = torch.ones_like(t)
+    g_c = torch.ldexp(ones, e_c).repeat_interleave(2, dim=-1)                # per block of 16
+    inv_g = torch.ldexp(ones, -e_c).repeat_interleave(2, dim=-1)
+    xb = x32.reshape(*x32.shape[:-1], K // 16, 16)
+    bmax = xb.abs().amax(dim=-1)
+    u = (bmax * torch.tensor(1.0 / 6.0, dtype=torch.float32)) * inv_g
+    sf = u.clamp(max=448.0).to(torch.float8_e4m3fn).to(torch.float32)
+    d = (sf * g_c).unsqueeze(-1)
+    rd = torch.where(d > 0, one / torch.where(d > 0, d, torch.ones_like(d)), torch.zeros_like(d))
+    q = e2m1_round(xb * rd)
+    shift = torch.ldexp(ones, (e_c - e_row).clamp(min=-60)).repeat_interleave(2, dim=-1)
+    sf_final = (sf * shift).to(torch.float8_e4m3fn).to(torch.float32)
+    return q.reshape(x32.shape), sf_final, torch.ldexp(torch.ones_like(e_row, dtype=torch.float32), e_row)
+
+
 def _linear(m: Mode, x: Tensor, sd: Dict[str, Tensor], key: str, bias: bool = True) -> Tensor:
     w = m.w(sd[key + ".weight"])
     b = m.w(sd[key + ".bias"]) if bias and (key + ".bias") in sd else None
     if m.quantize and m.bits == 4 and (FP8_LINEARS if m.fp4_scope == "all" else FP4_LINEARS).match(key):
-        qx, sx, gx = nvfp4_quant_rows(x)
+        chunked = m.fp4_fused and m.fp4_scope == "all" and FP4_FUSED_LINEARS.match(key)
+        qx, sx, gx = nvfp4_quant_rows_chunked(x) if chunked else nvfp4_quant_rows(x)
         qw, sw, gw = nvfp4_quant_rows(w)
         xd = qx * sx.repeat_interleave(16, dim=-1) * gx
         wd = qw * sw.repeat_interleave(16, dim=-1) * gw

@@ -123,6 +123,81 @@ def test_gemm_fp4_qkv_epilogue(B, R, H, K, off, f8out):
         assert all(torch.equal(x_, y_) for x_, y_ in zip(got, got2))
 
 
+def _decode_operand(q, sf, scale, K):
+    return decode(q, sf.view(-1, K // 64, 512), scale, K)
+
+
+@pytest.mark.parametrize("B,R,C,kc,col0", [(1, 128, 256, 256, 0), (2, 256, 3072, 15360, 0), (3, 128, 1024, 2048, 512)])
+def test_chunk_quantiser_and_finalise_bit_exact_vs_oracle(B, R, C, kc, col0):
+    """fx_quantize_chunks_fp4 + fx_fp4_finalize (the producer-side NVFP4 format: power-of-two chunk scales lifted to the row's)
+    against oracle.nvfp4_quant_rows_chunked: e2m1 bytes, UE4M3 block scales and row scales bit-exact, also when the chunks fill
+    only a column window of a wider operand whose other columns come from elsewhere."""
+    rows = B * R
+    full = rnd(B, R, kc, seed=51) * torch.logspace(-3, 2, kc, device=dev).to(bf)[None, None]   # magnitudes spread over 1e5
+    full[0, 0] = 0                                                                               # a zero row
+    op = ops.Fp4Operand(rows, kc, dev)
+    dst = op.view(rows, kc)
+    if col0 or C != kc:   # the other columns first (two calls: left and right of the window)
+        if col0:
+            ops.quantize_chunks_fp4(full[:, :, :col0], dst, 0)
+        if col0 + C < kc:
+            ops.quantize_chunks_fp4(full[:, :, col0 + C:], dst, col0 + C)
+    ops.quantize_chunks_fp4(full[:, :, col0:col0 + C], dst, col0)
+    q, sf, scale = ops.fp4_finalize(dst)
+    oq, osf, og = O.nvfp4_quant_rows_chunked(full.view(rows, kc).float().cpu())
+    lut = {float(v): i for i, v in enumerate(E2M1.tolist()[:8])}
+    code = torch.tensor([[lut[abs(float(v))] + (8 if (v < 0 or (v == 0 and torch.signbit(v))) else 0) for v in row] for row in oq[:4]])
+    got = torch.stack([(q[:4] & 15), (q[:4] >> 4)], dim=-1).reshape(4, kc).cpu()
+    assert torch.equal(got & 7, code & 7)                                       # magnitudes of the first rows, nibble by nibble
+    deq = _decode_operand(q, sf, scale, kc).cpu()
+    want = oq * osf.repeat_interleave(16, dim=-1) * og
+    assert torch.equal(deq, want)                                               # every dequantised value identical
+    assert torch.equal(scale.cpu(), og.flatten())
+    sfm = ops.sf_atoms_to_matrix(sf.view(-1, kc // 64, 512), kc)[:rows].view(torch.float8_e4m3fn).float().cpu()
+    assert torch.equal(sfm, osf)
+    print(f"chunked NVFP4 error rows={rows} kc={kc}: rel-L2 {rel_l2(deq, full.view(rows, kc).float().cpu()):.3e}")
+
+
+@pytest.mark.parametrize("B,R,N,K,kc,col0", [(1, 128, 192, 256, 256, 64), (2, 256, 3072, 3072, 3072, 0), (8, 128, 384, 1024, 1536, 1152)])
+def test_gemm_fp4_epilogue_emits_the_next_operand(B, R, N, K, kc, col0):
+    """fx_gemm_fp4 with q_out: act(A W^T + bias) leaves the epilogue as columns [col0, col0 + N) of the next GEMM's NVFP4 operand.
+    Against the oracle's chunked quantisation of the fp32 reference result: dequantised rel-L2 <= 2e-2 and >= 97 % identical
+    nibbles (the two differ only where the fp32 summation order moves a value across a rounding boundary); the remaining columns of
+    the operand, produced by the chunk quantiser, are untouched by the GEMM."""
+    a, w = rnd(B, R, K, seed=2), rnd(N, K, seed=3, scale=K ** -0.5)
+    bias = rnd(N, seed=4, scale=0.1)
+    a4, sfa, sa = ops.quantize_rows_fp4(a)
+    w4, sfw, sw = ops.fp4_weight(w)
+    wq, wsf, _ = ops.quantize_rows_fp4(w)
+    ref = torch.nn.functional.gelu(decode(a4, sfa, sa, K) @ decode(wq, wsf, sw, K).T + bias.float(), approximate="tanh")
+    rows = B * R
+    other = rnd(B, R, kc, seed=9)
+    op = ops.Fp4Operand(rows, kc, dev)
+    dst = op.view(rows, kc)
+    if col0:
+        ops.quantize_chunks_fp4(other[:, :, :col0], dst, 0)
+    if col0 + N < kc:
+        ops.quantize_chunks_fp4(other[:, :, col0 + N:], dst, col0 + N)
+    assert ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=bias, act="gelu_tanh", out4=dst, out4_col0=col0) is None
+    q, sf, scale = ops.fp4_finalize(dst)
+    deq = _decode_operand(q, sf, scale, kc)
+    full = other.view(rows, kc).float().clone()
+    full[:, col0:col0 + N] = ref
+    oq, osf, og = O.nvfp4_quant_rows_chunked(full.cpu())
+    want = (oq * osf.repeat_interleave(16, dim=-1) * og).to(dev)
+    win = slice(col0, col0 + N)
+    assert rel_l2(deq[:, win], want[:, win]) <= 2e-2 and rel_l2(deq[:, win], ref) <= 1.2e-1
+    same = (deq[:, win] == want[:, win]).float().mean().item()
+    print(f"epilogue-quantised operand B={B} R={R} N={N}: identical values {same:.4f}, vs fp32 result {rel_l2(deq[:, win], ref):.3e}")
+    assert same >= 0.97
+    keep = torch.ones(kc, dtype=torch.bool, device=dev)
+    keep[win] = False
+    # the other columns: same nibbles and block scales as the oracle's (their chunk exponents do not depend on the GEMM's columns;
+    # the row scale does, through the max -- already inside `want`)
+    if keep.any():
+        assert (deq[:, keep] == want[:, keep]).float().mean().item() >= 0.999
+
+
 @pytest.mark.parametrize("B,R,D,mode", [(2, 256, 3072, 0), (1, 128, 4096, 2), (3, 128, 1024, 1)])
 def test_rownorm_nvfp4_output_bit_identical_to_two_kernels(B, R, D, mode):
     """fx_rownorm with out_fp8 == 2 (the AdaLN / LayerNorm / RMSNorm row kernel writing the NVFP4 operand directly) produces
@@ -157,7 +232,7 @@ def test_flow_nvfp4_full_width_vs_quantised_oracle(scope):
     sd = synthetic.synthetic_state_dict(specs.flow_manifest(p))
     model = Flux(p, device=dev).load_weights(list(sd.items()))
     model.quantize(bits=4, fp4_scope=scope)
-    assert len(model._q4) == (2 * 4 + 3 if scope == "all" else 2 * 2 + 1) and model.quantized
+    assert len(model._q4) == (2 * 4 + 3 if scope == "all" else 2 * 2 + 1) and model.quantized and model._q4_fused
     g = torch.Generator().manual_seed(3)
     B, h, w, S = 2, 16, 96, 128                      # L = 384, S = 128: row counts the NVFP4 kernel tiles
     x = torch.randn(B, h, w, 16, generator=g).to(bf)
@@ -172,6 +247,14 @@ def test_flow_nvfp4_full_width_vs_quantised_oracle(scope):
     ref4 = O.flux_forward(sd, op, *args, mode=O.Mode("fp32", quantize=True, bits=4, fp4_scope=scope))
     out = model(*(t_.to(dev) for t_ in (img, ids, txt, tids, ts, y, gd)))
     assert "a4" in next(iter(model._ws.values()))    # the NVFP4 path did run
+    assert ("c4" in next(iter(model._ws.values()))) == (scope == "all")   # ... with producer-emitted operands under scope "all"
+    if scope == "all":   # the unfused form (bf16 `cat` + row quantiser) stays available and agrees with its own oracle restatement
+        model.quantize(bits=4, fp4_fused=False)
+        ref4u = O.flux_forward(sd, op, *args, mode=O.Mode("fp32", quantize=True, bits=4, fp4_fused=False))
+        outu = model(*(t_.to(dev) for t_ in (img, ids, txt, tids, ts, y, gd)))
+        print("nvfp4 (all, unfused) vs its oracle", rel_l2(outu, ref4u), "| fused vs unfused", rel_l2(out, outu))
+        assert rel_l2(outu, ref4u) <= 3e-2 and rel_l2(out, outu) <= 3e-2
+        model.quantize(bits=4, fp4_scope=scope)
     print(f"nvfp4 ({scope}) vs quantised oracle", rel_l2(out, ref4), cosine(out, ref4), "| vs fp32 oracle", rel_l2(out, ref), cosine(out, ref),
           "| oracle nvfp4 vs fp32", rel_l2(ref4, ref))
     assert rel_l2(out, ref4) <= 3e-2 and cosine(out, ref4) >= 0.999
