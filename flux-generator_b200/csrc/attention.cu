@@ -80,6 +80,26 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 #define FX_ATTN_EMU_MASK 0x11u  // bit i set: pair i of every 8 uses the software exp2 (25 %: 3471 -> 3303 clocks per key tile)
 #endif
 constexpr uint32_t EMU_MASK = FX_ATTN_EMU_MASK;
+// the e4m3 kernel: P is rounded to three mantissa bits, so a QUADRATIC 2^f (max relative error 1.8e-3, three instructions fewer per
+// pair) is as good as exact, and with the MMAs halved the MUFU pipe weighs more in the loop: its share is tuned separately
+#ifndef FX_ATTN_EMU_MASK_F8
+#define FX_ATTN_EMU_MASK_F8 0x11u
+#endif
+constexpr uint32_t EMU_MASK_F8 = FX_ATTN_EMU_MASK_F8;
+__device__ __forceinline__ void exp2_emu2_quad(uint64_t t2, float& p0, float& p1) {
+  float2 t = unpack2f(t2);
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  t2 = pack2f(t.x, t.y);
+  const uint64_t r2 = fadd2(t2, pack2f(12582912.0f, 12582912.0f));
+  const uint64_t f2 = fadd2(r2, pack2f(-12582912.0f, -12582912.0f));
+  const uint64_t x2 = ffma2(f2, pack2f(-1.0f, -1.0f), t2);
+  uint64_t q2 = ffma2(pack2f(0.23783042f, 0.23783042f), x2, pack2f(0.70339652f, 0.70339652f));
+  q2 = ffma2(q2, x2, pack2f(1.0005137f, 1.0005137f));
+  const float2 q = unpack2f(q2), r = unpack2f(r2);
+  p0 = __int_as_float(__float_as_int(q.x) + (__float_as_int(r.x) << 23));
+  p1 = __int_as_float(__float_as_int(q.y) + (__float_as_int(r.y) << 23));
+}
 
 // FX_ATTN_PROBE (profiling builds only): one CTA records SM-clock timestamps of its pipeline events into
 // a global buffer [role 3][step 64][event 8]; roles: 0 MMA issuer, 1/2 softmax warpgroup 0/1 (first warp).
@@ -840,8 +860,13 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
           for (int e = 0; e < 32; e += 2) {
             const uint64_t t2 = ffma2(pack2(__uint_as_float(sv[c * 32 + e]), __uint_as_float(sv[c * 32 + e + 1])), sl2_2, nm2);
             float p0, p1;
-            if (EMU_MASK & (1u << ((e >> 1) & 7))) {
+            if ((F8 ? EMU_MASK_F8 : EMU_MASK) & (1u << ((e >> 1) & 7))) {
+#ifdef FX_ATTN_EMU_F8_CUBIC
               exp2_emu2(t2, p0, p1);
+#else
+              if (F8) exp2_emu2_quad(t2, p0, p1);
+              else exp2_emu2(t2, p0, p1);
+#endif
             } else {
               const float2 t = unpack2(t2);
               p0 = fast_exp2(t.x);
