@@ -14,6 +14,7 @@
 #include <mutex>
 
 #include "api_common.cuh"
+#include "fp4.cuh"
 #include "sm100.cuh"
 #include "tmap.cuh"
 
@@ -33,6 +34,11 @@ struct AttnParams {
   float scale_log2;
   __nv_bfloat16* out;
   long long ld_out, out_bs;
+  // NVFP4 output (persistent kernel): O / l leaves the epilogue as chunks of the next GEMM's operand (fp4.cuh) instead of bf16.
+  // Rows >= out4_split of every batch element go to out4[0] (flattened row b * (seq - split) + row - split), rows below it to
+  // out4[1] (b * split + row): the image / text streams of a double block feed different `proj` operands.
+  ChunkQ out4[2];
+  int out4_split;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -967,7 +973,19 @@ attn_pkernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         float f[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * inv_l;
-        store_chunk32_coalesced(wst, lane, f, dst0 + c * 32, p.ld_out, vmask);
+        if (p.out4[0].q != nullptr) {
+          const bool hi = q_row >= p.out4_split;
+          ChunkQ o;  // (static indices: a dynamic index into a kernel parameter array forces a local-memory copy)
+          o.q = hi ? p.out4[0].q : p.out4[1].q;
+          o.sf = hi ? p.out4[0].sf : p.out4[1].sf;
+          o.e = hi ? p.out4[0].e : p.out4[1].e;
+          o.kc = hi ? p.out4[0].kc : p.out4[1].kc;
+          o.col0 = hi ? p.out4[0].col0 : 0;
+          const long long m = hi ? (long long)bz * (p.seq - p.out4_split) + (q_row - p.out4_split) : (long long)bz * p.out4_split + q_row;
+          fp4_chunk_quantise(f, m, o.col0 + hy * 128 + c * 32, o, q_row < p.seq);
+        } else {
+          store_chunk32_coalesced(wst, lane, f, dst0 + c * 32, p.ld_out, vmask);
+        }
       }
       // O has been read out of TMEM (tcgen05.wait::ld above): order it before the next item's first p_full arrive, which
       // is what allows the issuer to overwrite O with P.V of the next item
@@ -1496,15 +1514,31 @@ static bool persistent_default() {
 }
 
 extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
-  FX_REQUIRE(a && a->q && a->k && a->v && a->out, "fx_attention: null pointer");
+  FX_REQUIRE(a && a->q && a->k && a->v && (a->out || a->q_out), "fx_attention: null pointer");
   FX_REQUIRE(a->batch > 0 && a->heads > 0 && a->seq > 0, "fx_attention: empty problem");
-  FX_REQUIRE(a->ld_out % 8 == 0 && a->out_bs % 8 == 0 && aligned16(a->out), "fx_attention: out must be 16-byte aligned rows");
+  FX_REQUIRE(a->q_out || (a->ld_out % 8 == 0 && a->out_bs % 8 == 0 && aligned16(a->out)), "fx_attention: out must be 16-byte aligned rows");
   FX_REQUIRE(aligned16(a->q) && aligned16(a->k) && aligned16(a->v), "fx_attention: q/k/v must be 16-byte aligned");
   AttnParams p{};
   p.seq = a->seq; p.heads = a->heads; p.kv_tiles = (a->seq + 127) / 128;
   p.sequence = (a->variant == 4) ? 1 : 0;  // turn taking lost its edge once the issuer was fixed: 3314 vs 3230 clocks per key tile
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.out = (__nv_bfloat16*)a->out; p.ld_out = a->ld_out; p.out_bs = a->out_bs;
+  p.out4[0] = ChunkQ{nullptr, nullptr, nullptr, 0, 0};
+  p.out4[1] = p.out4[0];
+  p.out4_split = 0;
+  if (a->q_out) {  // NVFP4 chunks instead of bf16 (persistent kernel only)
+    FX_REQUIRE(a->variant == 0 || a->variant == 7, "fx_attention: q_out runs on the persistent kernel only (variant 0 / 7)");
+    FX_REQUIRE(a->sf_out && a->e_out && a->out_kc % 128 == 0 && a->out_col0 % 64 == 0 && a->out_col0 + a->heads * 128 <= a->out_kc &&
+                   aligned16(a->q_out) && aligned16(a->sf_out),
+               "fx_attention: q_out needs sf_out, e_out, out_kc %% 128 == 0 and the heads inside out_kc");
+    FX_REQUIRE(a->out_split >= 0 && a->out_split <= a->seq && a->out_split % 128 == 0 && (a->seq - a->out_split) % 128 == 0,
+               "fx_attention: q_out needs multiples of 128 rows on both sides of out_split");
+    FX_REQUIRE(a->out_split == 0 || (a->q_out2 && a->sf_out2 && a->e_out2 && a->out_kc2 % 128 == 0 && a->heads * 128 <= a->out_kc2),
+               "fx_attention: out_split > 0 needs the second operand");
+    p.out4[0] = ChunkQ{(uint8_t*)a->q_out, (uint8_t*)a->sf_out, (int8_t*)a->e_out, a->out_kc, a->out_col0};
+    p.out4[1] = ChunkQ{(uint8_t*)a->q_out2, (uint8_t*)a->sf_out2, (int8_t*)a->e_out2, a->out_kc2, 0};
+    p.out4_split = a->out_split;
+  }
   CUtensorMap tq, tk, tv;
   const uint64_t esz = a->fp8 ? 1 : 2;  // fp8: e4m3 q / k / v, one 128-byte row per token and head
   const uint64_t dims[3] = {128, (uint64_t)a->seq, (uint64_t)a->batch * a->heads};
@@ -1515,7 +1549,7 @@ extern "C" int fx_attention(const fx_attn_args* a, fx_stream stream) {
   if ((rc = make_tmap_bf16(&tk, a->k, 3, dims, strides, box, a->fp8 != 0))) return rc;
   if ((rc = make_tmap_bf16(&tv, a->v, 3, dims, strides, box, a->fp8 != 0))) return rc;
   FX_REQUIRE(!a->fp8 || a->variant == 0 || a->variant == 7, "fx_attention: fp8 operands run on the persistent kernel only (variant 0 / 7)");
-  if (a->variant == 7 || a->fp8 || (a->variant == 0 && persistent_default())) {
+  if (a->variant == 7 || a->fp8 || a->q_out || (a->variant == 0 && persistent_default())) {
     // persistent work loop (attn_pkernel): one CTA per SM over the (q-block, head, batch) items
     static std::once_flag oncep;
     static cudaError_t attrp_err = cudaSuccess;

@@ -43,7 +43,9 @@ class ConvArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("q", c_vp), ("k", c_vp), ("v", c_vp), ("out", c_vp), ("ld_out", c_i64), ("out_bs", c_i64),
-                ("scale", c_f32), ("batch", c_i32), ("heads", c_i32), ("seq", c_i32), ("variant", c_i32), ("fp8", c_i32)]
+                ("scale", c_f32), ("batch", c_i32), ("heads", c_i32), ("seq", c_i32), ("variant", c_i32), ("fp8", c_i32),
+                ("q_out", c_vp), ("sf_out", c_vp), ("e_out", c_vp), ("out_kc", c_i32), ("out_col0", c_i32),
+                ("q_out2", c_vp), ("sf_out2", c_vp), ("e_out2", c_vp), ("out_kc2", c_i32), ("out_split", c_i32)]
 
 
 class AttnSmallArgs(C.Structure):

@@ -331,7 +331,7 @@ class Flux:
                     u8 = lambda n: torch.empty((n,), device=dev, dtype=torch.uint8)  # noqa: E731
                     ws.update(a4=(u8(B * N * (D + M) // 2), u8(B * N * (D + M) // 16), torch.empty((B * N,), device=dev, dtype=torch.float32)))
                     if self._q4_all and self._q4_fused:
-                        ws.update(c4=ops.Fp4Operand(B * N, D + M, dev))
+                        ws.update(c4=ops.Fp4Operand(B * N, D + M, dev), p4=ops.Fp4Operand(B * S, D, dev))
                 ws.update(xm8=torch.empty((B, N, D), device=dev, dtype=ops.fp8),
                           cat8=torch.empty((B, N, D + M), device=dev, dtype=ops.fp8),
                           xs=torch.empty((B, N), device=dev, dtype=torch.float32),
@@ -535,13 +535,23 @@ class Flux:
                 w8, wsc = self._q8[ak + "qkv"]
                 ops.gemm_qkv(xm8[:, rows], w8, self._b(ak + "qkv"), qn, kn, pe, q, k, v, off, rms_eps=QK_RMS_EPS,
                              a_scale=xs[:, rows], w_scale=wsc, pe_blocked=pe_blocked)
-            ops.attention(q, k, v, cat[:, :, :D], scale)
+            if fused:  # the attention epilogue emits both streams' `proj` operands (NVFP4 chunks): no bf16 attention output
+                L_ = x.shape[1] - S
+                proj_in = {"img": ws["c4"].view(B * L_, D), "txt": ws["p4"].view(B * S, D)}
+                ops.attention(q, k, v, None, scale, out4=proj_in["img"], out4_low=proj_in["txt"], split=S)
+            else:
+                ops.attention(q, k, v, cat[:, :, :D], scale)
             for name, rows, off in streams:
                 mk = pre + name + "_mod.lin"
                 ak = pre + name + "_attn."
                 mlp = pre + name + "_mlp."
                 xr = x[:, rows]
-                self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
+                if fused:
+                    o4, sfo, so = ops.fp4_finalize(proj_in[name])
+                    w4, sfw, sw = self._q4[ak + "proj"]
+                    ops.gemm_fp4(o4, sfo, so, w4, sfw, sw, B, bias=self._b(ak + "proj"), gate=self._mod(ws, mk, 2), resid=xr, out=xr)
+                else:
+                    self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
                 if f4:
                     a4, sfa, sa = ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out_fp4=ws["a4"])
                     w4, sfw, sw = self._q4[mlp + "0"]
@@ -569,12 +579,11 @@ class Flux:
                 ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, None if bias is None else bias[:3 * D], qn, kn, pe, q, k, v, 0,
                                  rms_eps=QK_RMS_EPS, pe_blocked=pe_blocked)
                 w4, sfw, sw = self._q4[pre + "linear1.mlp"]
-                if fused:  # linear2's operand = [attention | GELU(mlp)]: the mlp columns come from this epilogue, the attention
-                    dst = ws["c4"].view(a4.shape[0], D + p.mlp_hidden)   # columns from the chunk quantiser below
+                if fused:  # linear2's operand = [attention | GELU(mlp)]: the mlp columns come from this GEMM's epilogue ...
+                    dst = ws["c4"].view(a4.shape[0], D + p.mlp_hidden)
                     ops.gemm_fp4(a4, sfa, sa, w4, sfw, sw, B, bias=None if bias is None else bias[3 * D:], act="gelu_tanh", out4=dst,
                                  out4_col0=D)
-                    ops.attention(q, k, v, cat[:, :, :D], scale)
-                    ops.quantize_chunks_fp4(cat[:, :, :D], dst, 0)
+                    ops.attention(q, k, v, None, scale, out4=dst)   # ... the attention columns from the attention epilogue
                     c4, sfc, sc = ops.fp4_finalize(dst)
                     w4, sfw, sw = self._q4[pre + "linear2"]
                     ops.gemm_fp4(c4, sfc, sc, w4, sfw, sw, B, bias=self._b(pre + "linear2"), gate=self._mod(ws, mk, 2), resid=x, out=x)

@@ -184,21 +184,36 @@ def upconv_weights(w: torch.Tensor) -> torch.Tensor:
     return out.view(4 * Cout, 4 * Cin).to(w.dtype).contiguous()
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float,
-              variant: int = 0) -> torch.Tensor:
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: Optional[torch.Tensor], scale: float,
+              variant: int = 0, out4=None, out4_col0: int = 0, out4_low=None, split: int = 0) -> Optional[torch.Tensor]:
     """q,k,v [B,H,S,128] contiguous (bf16, or all three float8_e4m3fn: both products then run in FP8);
-    out [B,S,>=H*128] bf16 view (head h -> columns h*128..)."""
+    out [B,S,>=H*128] bf16 view (head h -> columns h*128..).
+    out4 = Fp4Operand.view(B * (S - split), kc): instead of `out`, the epilogue writes O / l as columns [out4_col0 + h * 128, ...)
+    of that NVFP4 operand (chunked form: fp4_finalize completes it); with split > 0 the rows [0, split) of every batch element go to
+    out4_low = Fp4Operand.view(B * split, kc2) at column 0 (text / image streams of a double block)."""
     is8 = q.dtype == fp8
-    _chk(q, fp8 if is8 else bf16), _chk(k, fp8 if is8 else bf16), _chk(v, fp8 if is8 else bf16), _chk(out)
+    _chk(q, fp8 if is8 else bf16), _chk(k, fp8 if is8 else bf16), _chk(v, fp8 if is8 else bf16)
     if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
         raise ValueError("attention operands must be contiguous [B, H, S, 128]")
     B, H, S, D = q.shape
     if D != 128:
         raise ValueError("attention kernel is specialised for head_dim 128")
-    _, _, _, ldo, obs = _as3(out)
     args = N.AttnArgs()
-    args.q, args.k, args.v, args.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
-    args.ld_out, args.out_bs, args.scale = ldo, obs, scale
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    if out4 is not None:
+        q4, sf4, e4, _ = out4
+        if q4.shape[0] != B * (S - split) or (split and (out4_low is None or out4_low[0].shape[0] != B * split)):
+            raise ValueError("attention(out4=...): operand rows do not match")
+        args.q_out, args.sf_out, args.e_out, args.out_kc, args.out_col0 = q4.data_ptr(), sf4.data_ptr(), e4.data_ptr(), 2 * q4.shape[1], out4_col0
+        if split:
+            q2, sf2, e2, _ = out4_low
+            args.q_out2, args.sf_out2, args.e_out2, args.out_kc2, args.out_split = q2.data_ptr(), sf2.data_ptr(), e2.data_ptr(), 2 * q2.shape[1], split
+        out = None
+    else:
+        _chk(out)
+        _, _, _, ldo, obs = _as3(out)
+        args.out, args.ld_out, args.out_bs = out.data_ptr(), ldo, obs
+    args.scale = scale
     args.batch, args.heads, args.seq, args.variant = B, H, S, variant
     args.fp8 = int(is8)
     N.check(N.lib().fx_attention(C.byref(args), N.stream()))

@@ -197,6 +197,12 @@ typedef struct fx_attn_args {
                                   FX_ATTN_PERSISTENT=0) */
   int32_t fp8;                 /* 1: q, k, v are e4m3 [batch][heads][seq][128] bytes (written by fx_gemm_qkv with qkv_fp8);
                                   both products run in FP8 (P is converted to e4m3), fp32 softmax, bf16 output */
+  /* q_out != NULL (persistent kernel): instead of bf16 `out`, O / l is written as columns [out_col0 + h * 128, ...) of the NEXT
+   * GEMM's NVFP4 operand (layout and finalisation as fx_gemm4_args.q_out).  Rows >= out_split of every batch element go to the first
+   * operand (flattened row b * (seq - out_split) + row - out_split), rows below it to the second (b * out_split + row, column 0):
+   * the image / text streams of a double block feed different `proj` GEMMs.  Both row counts multiples of 128. */
+  void* q_out; void* sf_out; void* e_out; int32_t out_kc; int32_t out_col0;
+  void* q_out2; void* sf_out2; void* e_out2; int32_t out_kc2; int32_t out_split;
 } fx_attn_args;
 int fx_attention(const fx_attn_args* a, fx_stream stream);
 

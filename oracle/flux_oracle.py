@@ -58,8 +58,8 @@ class Mode:
         self.bits = bits
         assert fp4_scope in ("all", "cat")
         self.fp4_scope = fp4_scope
-        # fp4_fused (with fp4_scope "all"): the operands of mlp.2 / linear2 are emitted by their producers (GELU epilogue,
-        # attention-output quantiser) in the chunked form of nvfp4_quant_rows_chunked instead of the row quantiser's
+        # fp4_fused (with fp4_scope "all"): the operands of proj / mlp.2 / linear2 are emitted by their producers (attention
+        # epilogue, GELU epilogue) in the chunked form of nvfp4_quant_rows_chunked instead of the row quantiser's
         self.fp4_fused = fp4_fused
         # quantize: restates THIS repo's --quantize path (not the reference's MLX 4-bit nn.quantize, which cannot be
         # restated without MLX's packed group format): the block Linears matched by FP8_LINEARS see row-quantised
@@ -81,7 +81,7 @@ FP32 = Mode("fp32")
 FP8_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.qkv|attn\.proj|mlp\.0|mlp\.2)|single_blocks\.\d+\.linear[12])$")
 
 
-FP4_FUSED_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_mlp\.2|single_blocks\.\d+\.linear2)$")
+FP4_FUSED_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.proj|mlp\.2)|single_blocks\.\d+\.linear2)$")
 
 
 FP4_LINEARS = re.compile(r"^(double_blocks\.\d+\.(img|txt)_(attn\.proj|mlp\.2)|single_blocks\.\d+\.linear2)$")

@@ -198,6 +198,54 @@ def test_gemm_fp4_epilogue_emits_the_next_operand(B, R, N, K, kc, col0):
         assert (deq[:, keep] == want[:, keep]).float().mean().item() >= 0.999
 
 
+@pytest.mark.parametrize("f8,split,col0,kc", [(True, 0, 0, 384), (True, 128, 0, 384), (False, 0, 256, 1024)])
+def test_attention_epilogue_emits_nvfp4_chunks(f8, split, col0, kc):
+    """fx_attention with q_out: O / l leaves the epilogue as NVFP4 chunks of the next GEMM's operand(s).  Against the oracle's
+    chunked quantisation of the SAME kernel's bf16 output: >= 95 % identical values and rel-L2 <= 5e-2 (the epilogue quantises the
+    fp32 O / l, the comparison its bf16 rounding -- a value moves, by one e2m1 step, only when that rounding crosses an e2m1
+    boundary: measured 3.5 % of the values, rel-L2 3.6e-2, against 9e-2 for the 4-bit format itself); with
+    split > 0 the rows below it land in the second operand; other columns of the operand are untouched."""
+    B, H, S = 2, 3, 384
+    q, k, v = (rnd(B, H, S, 128, seed=60 + i) for i in range(3))
+    if f8:
+        q, k, v = (t_.to(ops.fp8) for t_ in (q, k, v))
+    ref = torch.zeros(B, S, H * 128, device=dev, dtype=bf)
+    ops.attention(q, k, v, ref, 128 ** -0.5)
+    hi_rows, lo_rows = B * (S - split), B * split
+    op_hi, op_lo = ops.Fp4Operand(hi_rows, kc, dev), ops.Fp4Operand(max(lo_rows, 128), 384, dev)
+    dst = op_hi.view(hi_rows, kc)
+    other = rnd(B, S - split, kc, seed=70)
+    if col0:
+        ops.quantize_chunks_fp4(other[:, :, :col0], dst, 0)
+    if col0 + H * 128 < kc:
+        ops.quantize_chunks_fp4(other[:, :, col0 + H * 128:], dst, col0 + H * 128)
+    low = op_lo.view(lo_rows, 384) if split else None
+    assert ops.attention(q, k, v, None, 128 ** -0.5, out4=dst, out4_col0=col0, out4_low=low, split=split) is None
+    qh, sfh, sh = ops.fp4_finalize(dst)
+    full = other.reshape(hi_rows, kc).float().clone()
+    full[:, col0:col0 + H * 128] = ref[:, split:].reshape(hi_rows, H * 128).float()
+    oq, osf, og = O.nvfp4_quant_rows_chunked(full.cpu())
+    want = (oq * osf.repeat_interleave(16, dim=-1) * og).to(dev)
+    got = _decode_operand(qh, sfh, sh, kc)
+    win = slice(col0, col0 + H * 128)
+    same = (got[:, win] == want[:, win]).float().mean().item()
+    print(f"attention-emitted operand f8={f8} split={split}: identical {same:.4f}, rel-L2 vs oracle-quantised bf16 output "
+          f"{rel_l2(got[:, win], want[:, win]):.3e}, vs the bf16 output {rel_l2(got[:, win], full[:, win].to(dev)):.3e}")
+    assert same >= 0.95 and rel_l2(got[:, win], want[:, win]) <= 5e-2
+    assert rel_l2(got[:, win], full[:, win].to(dev)) <= 1.2e-1   # and it IS the attention output, to 4-bit accuracy
+    keep = torch.ones(kc, dtype=torch.bool, device=dev)
+    keep[win] = False
+    if keep.any():
+        assert (got[:, keep] == want[:, keep]).float().mean().item() >= 0.999
+    if split:
+        ql, sfl, sl = ops.fp4_finalize(low)
+        lo_ref = ref[:, :split].reshape(lo_rows, H * 128).float()
+        oq, osf, og = O.nvfp4_quant_rows_chunked(lo_ref.cpu())
+        want_lo = (oq * osf.repeat_interleave(16, dim=-1) * og).to(dev)
+        got_lo = _decode_operand(ql, sfl, sl, 384)
+        assert (got_lo == want_lo).float().mean().item() >= 0.95 and rel_l2(got_lo, want_lo) <= 5e-2
+
+
 @pytest.mark.parametrize("B,R,D,mode", [(2, 256, 3072, 0), (1, 128, 4096, 2), (3, 128, 1024, 1)])
 def test_rownorm_nvfp4_output_bit_identical_to_two_kernels(B, R, D, mode):
     """fx_rownorm with out_fp8 == 2 (the AdaLN / LayerNorm / RMSNorm row kernel writing the NVFP4 operand directly) produces
