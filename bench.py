@@ -407,7 +407,7 @@ def main_arm(args) -> None:
             "clocks": q4_clocks, "flag": "txt2image.py --quantize / Flux.quantize(bits=4)",
             "parity": "tests/test_gpu_fp4.py (quantiser bit-exact vs the oracle, GEMM / QKV epilogue vs dequantised fp32 matmul), "
                       "tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (latents rel-L2 vs the fp32 oracle 1.1e-2 .. 2.3e-2 per "
-                      "step, image mean |diff| 1.47/255; operands of mlp.2 / linear2 emitted by the producing epilogues; the reference's own --quantize is 4-bit weights, txt2image.py:79-82)"}
+                      "step, image mean |diff| 1.47/255; operands of proj / mlp.2 / linear2 emitted by the attention / GELU epilogues; the reference's own --quantize is 4-bit weights, txt2image.py:79-82)"}
         quant["flag"] = "txt2image.py --quantize --quantize-bits 8 / Flux.quantize()"
         quant4["fp8"] = quant
         quant = quant4
