@@ -1,4 +1,5 @@
-// NVFP4 (W4A4) GEMM for the K-long projections of the MMDiT under `--quantize 4`, and its activation quantiser.
+// NVFP4 (W4A4) GEMMs for every block Linear of the MMDiT under `--quantize` (qkv, proj, mlp.0, mlp.2, linear1, linear2), the
+// activation quantisers and the finalise pass of producer-emitted operands.
 //   out = epilogue( (A4 . W4^T) * a_scale[row] * w_scale[col] ),   A4, W4: e2m1 (two per byte, K contiguous) with one
 //   UE4M3 scale per 16 elements of K -- tcgen05.mma.kind::mxf4nvf4.block_scale.block16: the tensor core applies the
 //   block scales itself, from TMEM, at four times the bf16 MAC rate.
@@ -10,11 +11,16 @@
 //   scales   512-byte atoms of 128 rows x 4 scales: byte (r % 32) * 16 + (r / 32) * 4 + s.  One tcgen05.cp.32x128b.warpx4
 //            drops an atom into 4 TMEM columns (lane r % 32 of every sub-partition, column r / 32, byte s), which is
 //            where the MMA reads the four scales of its 64 elements of K for row r.
-//            A: atoms [row block of 128][K / 64]; W: atoms [192-row column tile][K / 64][2] (rows 0-127, 128-191 of the tile)
+//            A: atoms [row block of 128][K / 64]; W: atoms [column tile][K / 64][atoms per tile] (192-row tiles: rows 0-127 and
+//            128-191; 128-row tiles for the QKV epilogue)
 //   a_scale  fp32 per row, w_scale fp32 per output channel: the second quantisation level (see fx_quantize_rows_fp4)
-// Kernel: persistent, 192-column tiles (192 so that two accumulators AND two scale-factor slots fit the 512 TMEM columns:
-// 2 x 192 + 2 x 48); CTA pairs (256 x 192 tiles, cta_group::2: the W tile is split over the pair, half the W bytes per FLOP)
-// when the row count allows, single CTAs (128 x 192) otherwise; TMA ring of A + W + scale atoms; warp roles as gemm_kernel.
+// Kernel: persistent CTA pairs (cta_group::2: the W tile is split over the pair) -- single CTAs when a batch element is not a
+// whole number of 256-row tiles -- with 16 warps: 12 epilogue warps, TMA producer, MMA issuer (both in uniform control flow).
+//   EPI_GENERIC: 256 x 192 tiles (two accumulators AND two scale-factor slots fit the 512 TMEM columns: 2 x 192 + 2 x 48);
+//                bias / act / gate / residual; bf16 output through TMA stores, fp32 output, or -- q_out -- the epilogue emits
+//                the NEXT GEMM's NVFP4 operand (fp4.cuh) and the result never exists in bf16.
+//   EPI_QKV:     256 x 128 tiles = one head, three accumulators (3 x 128 + 2 x 32 columns); QK-RMSNorm + RoPE + scatter.
+// Ring: A + W + scale atoms by TMA; per stage 4 (SFA) + 4 or 8 (SFB) tcgen05.cp and 4 MMAs of K = 64.
 #include <cuda_fp4.h>
 #include <cuda_fp8.h>
 #include <stdlib.h>
