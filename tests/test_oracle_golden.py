@@ -197,3 +197,47 @@ def test_quantised_oracle_stays_close_to_fp32():
     qnt = O.flux_forward(sd, op, a[0].float(), a[1], a[2].float(), a[3], tt, y.float(), mode=O.Mode("fp32", quantize=True))
     rel = ((qnt - ref).norm() / ref.norm()).item()
     assert 1e-4 < rel < 5e-2, rel
+
+
+def test_nvfp4_quantisers_known_answers():
+    """oracle.nvfp4_quant_rows (fx_quantize_rows_fp4) and nvfp4_quant_rows_chunked (the producer-emitted form: fx_gemm_fp4 /
+    fx_attention with q_out + fx_fp4_finalize): known answers and the properties the GPU kernels are held to bit-exactly."""
+    import torch
+
+    from oracle import flux_oracle as O
+    # e2m1 rounding: ties to the even mantissa, saturation at 6
+    v = torch.tensor([0.25, 0.2500001, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 5.0001, 7.0, -0.75, -100.0])
+    assert O.e2m1_round(v).tolist() == [0.0, 0.5, 1.0, 1.0, 2.0, 2.0, 4.0, 4.0, 6.0, 6.0, -1.0, -6.0]
+    # row quantiser: the row maximum maps to block scale 448 and value 6 exactly; a zero row to scale 1, zeros
+    x = torch.zeros(2, 64)
+    x[0, :16] = torch.linspace(-2688.0, 2688.0, 16)
+    x[0, 16:32] = 1.0
+    q, sf, g = O.nvfp4_quant_rows(x)
+    assert g.flatten().tolist() == [1.0, 1.0] and sf[0].tolist() == [448.0, float(torch.tensor(1.0 / 6.0).to(torch.float8_e4m3fn)), 0.0, 0.0]
+    assert q[0, 0].item() == -6.0 and q[0, 15].item() == 6.0 and (q[1] == 0).all() and (sf[1] == 0).all()
+    # chunked form: power-of-two scales; row scale = the largest chunk's; block scales of smaller chunks shifted exactly
+    x = torch.zeros(3, 128)
+    x[0, :32] = 2688.0 * 4          # chunk 0: e = 2
+    x[0, 32:64] = 2688.0 / 8        # chunk 1: e = -3  -> its block scales are shifted by 2^-5
+    x[0, 64:96] = 1.0               # chunk 2: 1/2688 -> e = ceil(log2(3.72e-4)) = -11
+    x[1] = torch.randn(128, generator=torch.Generator().manual_seed(1))
+    q, sf, g = O.nvfp4_quant_rows_chunked(x)
+    assert g.flatten()[0].item() == 4.0 and g.flatten()[2].item() == 2.0 ** -100
+    assert sf[0, :2].tolist() == [448.0, 448.0] and sf[0, 2:4].tolist() == [14.0, 14.0]       # 448 * 2^-5
+    assert (q[0, :64].abs() == 6.0).all()
+    deq = q * sf.repeat_interleave(16, dim=-1) * g
+    assert torch.equal(deq[0, :64], x[0, :64])                                                  # exactly representable inputs
+    assert abs(deq[0, 64].item() - 1.0) <= 0.07                                                 # 2^-13 of the row maximum: still there
+    assert (deq[2] == 0).all()
+    # against the row quantiser on Gaussian data: the same error to within a few percent (the chunk scale costs at most one bit
+    # of the block scale's RANGE, none of its precision)
+    x = torch.randn(64, 3072, generator=torch.Generator().manual_seed(2)) * torch.logspace(-2, 1, 3072)
+    qa, sa, ga = O.nvfp4_quant_rows(x)
+    qb, sb, gb = O.nvfp4_quant_rows_chunked(x)
+    ea = ((qa * sa.repeat_interleave(16, dim=-1) * ga - x).norm() / x.norm()).item()
+    eb = ((qb * sb.repeat_interleave(16, dim=-1) * gb - x).norm() / x.norm()).item()
+    assert 0.05 < ea < 0.12 and abs(eb - ea) <= 0.05 * ea, (ea, eb)
+    # powers of two only, and never below the row quantiser's scale
+    assert torch.equal(torch.frexp(gb)[0], torch.full_like(gb, 0.5)) and (gb >= ga).all() and (gb < 2 * ga + 1e-30).all()
+    assert O.FP4_FUSED_LINEARS.match("double_blocks.0.img_attn.proj") and O.FP4_FUSED_LINEARS.match("single_blocks.9.linear2")
+    assert not O.FP4_FUSED_LINEARS.match("single_blocks.9.linear1") and not O.FP4_FUSED_LINEARS.match("double_blocks.0.txt_mlp.0")
