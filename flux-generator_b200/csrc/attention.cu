@@ -1485,6 +1485,135 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const AttnSmallParams p
   *reinterpret_cast<__nv_bfloat162*>(op) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
 }
 
+// ------------------------------------------------------------------------------------------
+// The same attention on the tensor cores (warp-level mma.sync.m16n8k16, bf16 in / fp32 accumulate): a flash loop over 64-key
+// chunks staged in shared memory, 64 queries per CTA (16 per warp), S and O in registers.  The text encoders run once per
+// prompt on a few thousand query rows per head -- far too small for the tcgen05 / TMEM kernel above (its 256-row CTA tiles
+// and 128-wide heads do not apply: head_dim is 64, T5 adds a relative-position bias to every score, CLIP is causal) -- but
+// the warp-per-query kernel re-read every key row from L2 for every query: 285 us per T5 layer, 66 % of the text-encode time.
+// Fragment layouts (PTX ISA, mma.m16n8k16 .row.col): g = lane / 4, t = lane % 4;
+//   A (16 x 16): a0 = (g, 2t..2t+1), a1 = (g + 8, 2t..), a2 = (g, 2t + 8..), a3 = (g + 8, 2t + 8..)
+//   B (16 x 8):  b0 = (k = 2t..2t+1, n = g), b1 = (k = 2t + 8.., n = g);   C (16 x 8): c0,c1 = (g, 2t..2t+1), c2,c3 = (g + 8, ..)
+// ------------------------------------------------------------------------------------------
+constexpr int AS_PAD = 72;  // padded row of the K / V chunks (bf16): 144-byte stride = conflict-free fragment loads
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) attn_small_mma_kernel(const AttnSmallParams p) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[64][AS_PAD];
+  __shared__ __align__(16) __nv_bfloat16 Vs[64][AS_PAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;  // this thread's two query rows
+  const __nv_bfloat16* qb = p.q + b * p.bs + h * 64;
+  uint32_t qa[4][4];  // Q fragments of the four 16-wide slices of head_dim (rows past the end: zeros)
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int c = ks * 16 + 2 * t;
+    qa[ks][0] = r0 < p.seq ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * p.ld + c) : 0u;
+    qa[ks][1] = r1 < p.seq ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * p.ld + c) : 0u;
+    qa[ks][2] = r0 < p.seq ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * p.ld + c + 8) : 0u;
+    qa[ks][3] = r1 < p.seq ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * p.ld + c + 8) : 0u;
+  }
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const int nk = p.causal ? min(p.seq, q0 + 64) : p.seq;  // keys any query of this CTA may see
+  const float* bias0 = p.bias ? p.bias + ((long long)h * p.seq + min(r0, p.seq - 1)) * p.seq : nullptr;
+  const float* bias1 = p.bias ? p.bias + ((long long)h * p.seq + min(r1, p.seq - 1)) * p.seq : nullptr;
+  for (int k0 = 0; k0 < nk; k0 += 64) {
+    __syncthreads();  // the previous chunk has been consumed
+    for (int i = tid; i < 512; i += 128) {  // 64 rows x 8 pieces of 16 bytes, K and V
+      const int row = i >> 3, c = (i & 7) * 8;
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+      if (k0 + row < p.seq) {
+        const long long off = b * p.bs + (long long)(k0 + row) * p.ld + h * 64 + c;
+        kv = *reinterpret_cast<const uint4*>(p.k + off);
+        vv = *reinterpret_cast<const uint4*>(p.v + off);
+      }
+      *reinterpret_cast<uint4*>(&Ks[row][c]) = kv;
+      *reinterpret_cast<uint4*>(&Vs[row][c]) = vv;
+    }
+    __syncthreads();
+    // S = Q K^T for 16 queries x 64 keys
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + g][ks * 16 + 2 * t + 8]);
+        mma_bf16_16816(sc[nt], qa[ks], b0, b1);
+      }
+    }
+    // scale, bias, masks, chunk maxima of the two rows
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int kj = k0 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = kj + e;
+        float s0 = sc[nt][e] * p.scale, s1 = sc[nt][2 + e] * p.scale;
+        if (key < p.seq) {
+          if (bias0) { s0 += __ldg(bias0 + key); s1 += __ldg(bias1 + key); }
+          if (p.causal && key > r0) s0 = -INFINITY;
+          if (p.causal && key > r1) s1 = -INFINITY;
+        } else {
+          s0 = s1 = -INFINITY;
+        }
+        sc[nt][e] = s0; sc[nt][2 + e] = s1;
+        mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);
+    const float a0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - n0), a1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - n1);
+    m0 = n0; m1 = n1;
+    const float e0 = (n0 == -INFINITY) ? 0.f : n0, e1 = (n1 == -INFINITY) ? 0.f : n1;  // a fully masked row so far: all p = 0
+    float cs0 = 0.f, cs1 = 0.f;
+    uint32_t pa[4][4];  // P as the A operand of P V: 16 queries x 64 keys = four 16-key slices
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p00 = __expf(sc[nt][0] - e0), p01 = __expf(sc[nt][1] - e0);
+      const float p10 = __expf(sc[nt][2] - e1), p11 = __expf(sc[nt][3] - e1);
+      cs0 += p00 + p01; cs1 += p10 + p11;
+      pa[nt >> 1][(nt & 1) * 2] = pack_bf16(p00, p01);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p10, p11);
+    }
+    l0 = l0 * a0 + cs0; l1 = l1 * a1 + cs1;  // (per-thread partial sums: reduced over the quad at the end)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= a0; o[i][1] *= a0; o[i][2] *= a1; o[i][3] *= a1; }
+    // O += P V: B[k = key][n = d] from V[key][d] through ldmatrix.trans (two d-tiles per instruction)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dt = 0; dt < 8; dt += 2) {
+        uint32_t v0, v1, v2, v3;
+        const uint32_t addr = smem_u32(&Vs[kk * 16 + (lane & 15)][dt * 8 + (lane >> 4) * 8]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
+        mma_bf16_16816(o[dt], pa[kk], v0, v1);
+        mma_bf16_16816(o[dt + 1], pa[kk], v2, v3);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  __nv_bfloat16* ob = p.out + b * p.out_bs + h * 64 + 2 * t;
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    if (r0 < p.seq) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * p.ld_out + dt * 8) = pack_bf16(o[dt][0] * i0, o[dt][1] * i0);
+    if (r1 < p.seq) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * p.ld_out + dt * 8) = pack_bf16(o[dt][2] * i1, o[dt][3] * i1);
+  }
+}
+
 }  // namespace fx
 
 using namespace fx;
@@ -1598,6 +1727,17 @@ extern "C" int fx_attention_small(const fx_attn_small_args* a, fx_stream stream)
   FX_REQUIRE(a->ld % 8 == 0 && a->bs % 8 == 0 && a->ld_out % 2 == 0, "fx_attention_small: unaligned strides");
   AttnSmallParams p{(const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k, (const __nv_bfloat16*)a->v, a->ld, a->bs,
                     a->bias, (__nv_bfloat16*)a->out, a->ld_out, a->out_bs, a->scale, a->batch, a->heads, a->seq, a->causal};
+  static int use_mma = -1;  // FX_ATTN_SMALL_MMA=0: the warp-per-query CUDA-core kernel (A/B)
+  if (use_mma < 0) {
+    const char* e = getenv("FX_ATTN_SMALL_MMA");
+    use_mma = e ? atoi(e) : 1;
+  }
+  if (use_mma && a->batch <= 65535 && a->heads <= 65535 && aligned16(a->q) && aligned16(a->k) && aligned16(a->v) &&
+      (reinterpret_cast<uintptr_t>(a->out) & 3) == 0) {
+    dim3 grid((unsigned)((a->seq + 63) / 64), (unsigned)a->heads, (unsigned)a->batch);
+    attn_small_mma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    return launched("attn_small_mma_kernel");
+  }
   const long long warps = (long long)a->batch * a->heads * a->seq;
   const int blocks = int((warps + 7) / 8);
   attn_small_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
