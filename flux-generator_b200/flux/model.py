@@ -526,7 +526,7 @@ class Flux:
                 ak = pre + name + "_attn."
                 qn, kn = self.arena[ak + "norm.query_norm.scale"], self.arena[ak + "norm.key_norm.scale"]
                 if f4:
-                    a4, sfa, sa = ops.rownorm(x[:, rows], 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out_fp4=ws["a4"])
+                    a4, sfa, sa = self._norm_fp4(ws, x[:, rows], xm[:, rows], self._mod(ws, mk, 0), self._mod(ws, mk, 1))
                     w4, sfw, sw = self._q4[ak + "qkv"]
                     ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, self._b(ak + "qkv"), qn, kn, pe, q, k, v, off, rms_eps=QK_RMS_EPS,
                                      pe_blocked=pe_blocked)
@@ -553,7 +553,7 @@ class Flux:
                 else:
                     self._cat_gemm(ws, ak + "proj", cat[:, rows, :D], cat8[:, rows, :D], cs[:, rows], self._mod(ws, mk, 2), xr)
                 if f4:
-                    a4, sfa, sa = ops.rownorm(xr, 0, self._mod(ws, mk, 3), self._mod(ws, mk, 4), 1e-6, out_fp4=ws["a4"])
+                    a4, sfa, sa = self._norm_fp4(ws, xr, xm[:, rows], self._mod(ws, mk, 3), self._mod(ws, mk, 4))
                     w4, sfw, sw = self._q4[mlp + "0"]
                     if fused:  # GELU epilogue -> mlp.2's NVFP4 operand; the hidden activation never exists in bf16
                         dst = ws["c4"].view(a4.shape[0], p.mlp_hidden)
@@ -573,7 +573,7 @@ class Flux:
             mk = pre + "modulation.lin"
             qn, kn = self.arena[pre + "norm.query_norm.scale"], self.arena[pre + "norm.key_norm.scale"]
             if f4:
-                a4, sfa, sa = ops.rownorm(x, 0, self._mod(ws, mk, 0), self._mod(ws, mk, 1), 1e-6, out_fp4=ws["a4"])
+                a4, sfa, sa = self._norm_fp4(ws, x, xm, self._mod(ws, mk, 0), self._mod(ws, mk, 1))
                 bias = self._b(pre + "linear1")
                 w4, sfw, sw = self._q4[pre + "linear1.qkv"]
                 ops.gemm_fp4_qkv(a4, sfa, sa, w4, sfw, sw, B, None if bias is None else bias[:3 * D], qn, kn, pe, q, k, v, 0,
@@ -596,6 +596,14 @@ class Flux:
                              a_scale=xs, w_scale=wsc, pe_blocked=pe_blocked)
             ops.attention(q, k, v, cat[:, :, :D], scale)
             self._cat_gemm(ws, pre + "linear2", cat, cat8, cs, self._mod(ws, mk, 2), x)
+
+    def _norm_fp4(self, ws: dict, x: torch.Tensor, xm: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor):
+        """AdaLN row norm -> NVFP4 operand (q, scale atoms, row scales): one kernel for the wide rows the block kernel handles
+        (hidden >= 1024: every real Flux), norm + row quantiser (the same bytes) for reduced-width models."""
+        if x.shape[-1] >= 1024:
+            return ops.rownorm(x, 0, shift, scale, 1e-6, out_fp4=ws["a4"])
+        ops.rownorm(x, 0, shift, scale, 1e-6, out=xm)
+        return ops.quantize_rows_fp4(xm, out=ws["a4"])
 
     def _cat_gemm(self, ws: dict, key: str, a: torch.Tensor, a8: torch.Tensor, a8_scale: torch.Tensor, gate: torch.Tensor,
                   x: torch.Tensor) -> None:

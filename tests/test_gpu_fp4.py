@@ -314,3 +314,45 @@ def test_flow_nvfp4_full_width_vs_quantised_oracle(scope):
     out2 = model(img2.to(dev), ids2.to(dev), txt[:1, :40].contiguous().to(dev), tids[:1, :40].contiguous().to(dev), ts[:1].to(dev),
                  y[:1].to(dev), gd[:1].to(dev))
     assert torch.isfinite(out2.float()).all()
+
+
+def test_pipeline_nvfp4_end_to_end():
+    """FluxPipeline with Flux.quantize(bits=4) -- what `txt2image.py --quantize` runs -- at a shape the NVFP4 kernels tile
+    (reduced-width model of the golden fixtures, 256 image + 128 text tokens, 2 steps, 2 images): every block Linear in NVFP4 with
+    producer-emitted operands, e4m3 attention, CUDA-graph replay.  Against the same pipeline in bf16: latents rel-L2 <= 5e-2,
+    cosine >= 0.998, image mean |diff| <= 3/255 (measured 9.2e-3, 0.99996, 0.82/255; the full-size figures are in
+    tests/test_gpu_fullsize.py); the unfused form (bf16 `cat` + row quantiser) lands within the same bound of the fused one
+    (measured 5.7e-3)."""
+    from flux import FluxPipeline, specs, synthetic
+    from helpers import FixedTokenizer, cosine, small_configs
+    fcfg, acfg, t5c, clc = small_configs()
+    pipe = FluxPipeline("flux-schnell", synthetic=True, device=dev, flow_params=specs.FluxParams(**fcfg, guidance_embed=False),
+                        ae_params=specs.AutoEncoderParams(**acfg), t5_config=specs.T5Config(**t5c),
+                        clip_config=specs.CLIPTextModelConfig(**clc))
+    for mod, man in ((pipe.flow, specs.flow_manifest(pipe.flow.params)), (pipe.ae, specs.ae_decoder_manifest(pipe.ae.params)),
+                     (pipe.t5, specs.t5_manifest(pipe.t5.config)), (pipe.clip, specs.clip_manifest(pipe.clip.config))):
+        sd = synthetic.synthetic_state_dict(man)
+        mod.load_weights(list(mod.sanitize(sd).items()) if mod is pipe.ae else list(sd.items()))
+    gen_ = torch.Generator().manual_seed(5)
+    pipe.t5_tokenizer = FixedTokenizer(torch.randint(3, t5c["vocab_size"], (1, 128), generator=gen_))
+    pipe.clip_tokenizer = FixedTokenizer(torch.randint(3, clc["vocab_size"] - 2, (1, 16), generator=gen_))
+
+    def run():
+        gen = pipe.generate_latents("a prompt", n_images=2, num_steps=2, latent_size=(32, 32), seed=11)
+        next(gen)
+        lat = list(gen)[-1]
+        return lat.float(), pipe.decode(lat, (32, 32)).float()
+
+    l16, i16 = run()
+    pipe.flow.quantize(bits=4)
+    l4, i4 = run()
+    ws = next(iter(pipe.flow._ws.values()))
+    assert pipe.flow.quantized and "c4" in ws and "p4" in ws            # NVFP4 with producer-emitted operands did run
+    pipe.flow.quantize(bits=4, fp4_fused=False)
+    l4u, _ = run()
+    pipe.flow.dequantize()
+    d = (i4 - i16).abs().mean().item() * 255
+    print(f"NVFP4 pipeline vs bf16: latents rel-L2 {rel_l2(l4, l16):.3e} cosine {cosine(l4, l16):.5f} image mean |diff| {d:.2f}/255; "
+          f"fused vs unfused latents {rel_l2(l4, l4u):.3e}")
+    assert rel_l2(l4, l16) <= 5e-2 and cosine(l4, l16) >= 0.998 and d <= 3.0
+    assert rel_l2(l4, l4u) <= 5e-2

@@ -270,7 +270,8 @@ def test_pipeline_quantised_vs_golden(variant):
 
 
 def test_cli_quantize_flag(tmp_path, monkeypatch):
-    """txt2image.py --quantize (txt2image.py:56,79-82) switches the flow model to the FP8 path and still writes images."""
+    """txt2image.py --quantize (txt2image.py:56,79-82) switches the flow model to the quantised path (4-bit by default; this
+    tiny shape -- 24 image tokens -- is not tileable by the NVFP4 kernels and runs on the FP8 Linears) and still writes images."""
     import flux
     import txt2image
     from helpers import small_configs
