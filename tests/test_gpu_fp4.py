@@ -356,3 +356,30 @@ def test_pipeline_nvfp4_end_to_end():
           f"fused vs unfused latents {rel_l2(l4, l4u):.3e}")
     assert rel_l2(l4, l16) <= 5e-2 and cosine(l4, l16) >= 0.998 and d <= 3.0
     assert rel_l2(l4, l4u) <= 5e-2
+
+
+@pytest.mark.parametrize("B,h,w,S", [(1, 64, 64, 256), (3, 32, 32, 128), (2, 48, 96, 128), (1, 128, 128, 512)])
+def test_flow_nvfp4_shapes(B, h, w, S):
+    """Flux.quantize(bits=4) at full width (depth 1+1) over the token counts of other image sizes / batch sizes / the dev model's
+    512 text tokens -- CTA pairs (rows % 256 == 0) and single CTAs (L = 1152), batch 1 and odd batches: against the bf16 forward
+    of the same model rel-L2 <= 4e-2, cosine >= 0.999; graph replay bit-identical."""
+    from flux import specs, synthetic
+    from flux.model import Flux
+    from helpers import cosine
+    p = specs.FluxParams(depth=1, depth_single_blocks=1, guidance_embed=True)
+    sd = synthetic.synthetic_state_dict(specs.flow_manifest(p))
+    model = Flux(p, device=dev).load_weights(list(sd.items()))
+    g = torch.Generator().manual_seed(B * 1000 + S)
+    img, ids = O.prepare_latent_images(torch.randn(B, h, w, 16, generator=g).to(bf))
+    txt = torch.randn(B, S, 4096, generator=g).to(bf)
+    y = torch.randn(B, 768, generator=g).to(bf)
+    tids = torch.zeros(B, S, 3, dtype=torch.int32)
+    ts, gd = torch.full((B,), 0.5, dtype=bf), torch.full((B,), 4.0, dtype=bf)
+    a = [t_.to(dev) for t_ in (img, ids, txt, tids, ts, y, gd)]
+    ref = model(*a).float().clone()
+    model.quantize(bits=4)
+    out = model(*a).float().clone()
+    assert "c4" in next(iter(model._ws.values()))
+    print(f"nvfp4 B={B} L={img.shape[1]} S={S}: vs bf16 rel-L2 {rel_l2(out, ref):.3e} cosine {cosine(out, ref):.5f}")
+    assert torch.isfinite(out).all() and rel_l2(out, ref) <= 4e-2 and cosine(out, ref) >= 0.999
+    assert torch.equal(model.forward(*a).clone(), model.forward_graphed(*a))
