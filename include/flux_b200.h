@@ -117,7 +117,7 @@ typedef struct fx_conv3x3_args {
 int fx_conv3x3(const fx_conv3x3_args* a, fx_stream stream);
 int64_t fx_conv3x3_gn_blocks(int32_t H, int32_t Wd, int32_t Cout, int32_t upsample2x);
 
-/* ---------------------------------------------------------------- NVFP4 (W4A4) projections: `--quantize 4`
+/* ---------------------------------------------------------------- NVFP4 (W4A4) block Linears: `--quantize` (4 bits, the default)
  * The Blackwell analogue of the reference's 4-bit `nn.quantize(group_size=64)` of the Linear layers
  * (txt2image.py:28-29,79-82): e2m1 values (two per byte) with one UE4M3 scale per 16 elements of K, consumed by
  * tcgen05.mma.kind::mxf4nvf4.block_scale, plus one fp32 scale per row (activations) / output channel (weights).
@@ -156,8 +156,11 @@ typedef struct fx_gemm4_args {
 } fx_gemm4_args;
 int fx_gemm_fp4(const fx_gemm4_args* a, fx_stream stream);
 
-/* The same chunked producer for a bf16 tensor x [batch][rows][C] (the attention output that shares `linear2`'s operand with the
- * GELU(mlp) columns): C % 64 == 0; layout of q / sf / e as fx_gemm4_args.q_out. */
+/* The same chunked producer for a bf16 tensor x [batch][rows][C] (stand-alone form; in the model the attention epilogue emits
+ * its chunks itself, fx_attn_args.q_out): C % 64 == 0; layout of q / sf / e as fx_gemm4_args.q_out.
+ * Format of a producer-emitted operand (oracle: nvfp4_quant_rows_chunked): per 32-column chunk e_c = ceil(log2(absmax(chunk) / 2688))
+ * (>= -100), per block of 16 sf = e4m3_rn(absmax(block) / 6 * 2^-e_c), q = e2m1_rn(x * rcp(sf * 2^e_c)); fx_fp4_finalize then sets
+ * scale[row] = 2^max_c(e_c) and sf <- e4m3_rn(sf * 2^(e_c - max e_c)), so that x ~= e2m1 * ue4m3 * scale as for fx_quantize_rows_fp4. */
 typedef struct fx_quant4c_args {
   const void* x; int64_t ldx; int64_t x_bs;
   int32_t batch, rows, C;
