@@ -384,33 +384,40 @@ def main_arm(args) -> None:
     # `quantized.fp8` = --quantize --quantize-bits 8 (FP8 e4m3 W8A8 block Linears + e4m3 attention)
     quant = None
     if not args.no_quantized:
-        pipe.flow.quantize()
-        split_events.clear()
-        q_ms, _, q_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
-        quant = {"dtype": "fp8_e4m3 (block Linears W8A8 with per-row scales, fp32 accumulate; attention Q K^T and P V in e4m3 with fp32 "
-                          "softmax; embedders / final layer / VAE bf16)",
-                 "value": B * world * args.steps / (q_ms * 1e-3), "unit": UNIT, "ms_per_step": q_ms / args.steps,
-                 "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
-                 "clocks": q_clocks, "flag": "txt2image.py --quantize / Flux.quantize()",
-                 "parity": "tests/test_gpu_fp8.py, tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (19+38 blocks, N=4352, 4 steps: "
-                           "latents rel-L2 vs the fp32 oracle 4.7e-3 .. 8.7e-3 per step, bf16 3.8e-3 .. 6.3e-3; image mean |diff| 0.76/255 vs "
-                           "0.67/255; own tolerance -- the bf16 line above is the headline)"}
-        # --quantize --quantize-bits 4: every block Linear as NVFP4 W4A4 (tcgen05 kind::mxf4nvf4.block_scale), FP8 attention
-        pipe.flow.quantize(bits=4)
-        split_events.clear()
-        q4_ms, _, q4_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
-        quant4 = {
-            "dtype": "nvfp4 (block Linears W4A4: e2m1 + UE4M3 scale per 16 + fp32 row / channel scales, fp32 accumulate; attention e4m3; "
-                     "embedders / final layer / VAE bf16)",
-            "value": B * world * args.steps / (q4_ms * 1e-3), "unit": UNIT, "ms_per_step": q4_ms / args.steps,
-            "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
-            "clocks": q4_clocks, "flag": "txt2image.py --quantize / Flux.quantize(bits=4)",
-            "parity": "tests/test_gpu_fp4.py (quantiser bit-exact vs the oracle, GEMM / QKV epilogue vs dequantised fp32 matmul), "
-                      "tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (latents rel-L2 vs the fp32 oracle 1.1e-2 .. 2.3e-2 per "
-                      "step, image mean |diff| 1.47/255; operands of proj / mlp.2 / linear2 emitted by the attention / GELU epilogues; the reference's own --quantize is 4-bit weights, txt2image.py:79-82)"}
-        quant["flag"] = "txt2image.py --quantize --quantize-bits 8 / Flux.quantize()"
-        quant4["fp8"] = quant
-        quant = quant4
+        try:  # a failure of an extra leg must not take the headline line with it (it would fail on every rank alike)
+            pipe.flow.quantize()
+            split_events.clear()
+            q_ms, _, q_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
+            quant = {"dtype": "fp8_e4m3 (block Linears W8A8 with per-row scales, fp32 accumulate; attention Q K^T and P V in e4m3 with fp32 "
+                              "softmax; embedders / final layer / VAE bf16)",
+                     "value": B * world * args.steps / (q_ms * 1e-3), "unit": UNIT, "ms_per_step": q_ms / args.steps,
+                     "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
+                     "clocks": q_clocks, "flag": "txt2image.py --quantize / Flux.quantize()",
+                     "parity": "tests/test_gpu_fp8.py, tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (19+38 blocks, N=4352, 4 steps: "
+                               "latents rel-L2 vs the fp32 oracle 4.7e-3 .. 8.7e-3 per step, bf16 3.8e-3 .. 6.3e-3; image mean |diff| 0.76/255 vs "
+                               "0.67/255; own tolerance -- the bf16 line above is the headline)"}
+            # --quantize --quantize-bits 4: every block Linear as NVFP4 W4A4 (tcgen05 kind::mxf4nvf4.block_scale), FP8 attention
+            pipe.flow.quantize(bits=4)
+            split_events.clear()
+            q4_ms, _, q4_clocks = timed(step_resident, args.steps, 2, with_clocks=True)
+            quant4 = {
+                "dtype": "nvfp4 (block Linears W4A4: e2m1 + UE4M3 scale per 16 + fp32 row / channel scales, fp32 accumulate; attention e4m3; "
+                         "embedders / final layer / VAE bf16)",
+                "value": B * world * args.steps / (q4_ms * 1e-3), "unit": UNIT, "ms_per_step": q4_ms / args.steps,
+                "ms_per_denoise_step": sum(e[0].elapsed_time(e[1]) for e in split_events[-args.steps:]) / args.steps / STEPS_DENOISE,
+                "clocks": q4_clocks, "flag": "txt2image.py --quantize / Flux.quantize(bits=4)",
+                "parity": "tests/test_gpu_fp4.py (quantiser bit-exact vs the oracle, GEMM / QKV epilogue vs dequantised fp32 matmul), "
+                          "tests/test_gpu_fullsize.py::test_fp8_full_depth_four_steps (latents rel-L2 vs the fp32 oracle 1.1e-2 .. 2.3e-2 per "
+                          "step, image mean |diff| 1.47/255; operands of proj / mlp.2 / linear2 emitted by the attention / GELU epilogues; the reference's own --quantize is 4-bit weights, txt2image.py:79-82)"}
+            quant["flag"] = "txt2image.py --quantize --quantize-bits 8 / Flux.quantize()"
+            quant4["fp8"] = quant
+            quant = quant4
+        except Exception as exc:  # noqa: BLE001
+            quant = {"error": repr(exc)[:300]}
+            try:
+                pipe.flow.dequantize()
+            except Exception:  # noqa: BLE001
+                pass
 
     if rank == 0:
         pk = peaks()
